@@ -1,0 +1,147 @@
+"""Pin the oracle (oracle/vit_oracle.py) against outputs of the real reference.
+
+The fixtures were produced by tests/golden/make_golden.py importing
+/root/reference; nothing here reads /root/reference at run time.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+TOL = 2e-6  # same ATen ops in the same order: bit-exact on the same build, tiny slack across builds
+
+
+def _close(a, b, tol=TOL):
+    assert a.shape == b.shape
+    err = O.max_rel(a, b)
+    assert err <= tol, err
+
+
+def _leaf(t):
+    return t.clone().requires_grad_(True)
+
+
+@pytest.fixture(scope="module")
+def comp(golden_dir):
+    return torch.load(os.path.join(golden_dir, "components.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def bb(golden_dir):
+    return torch.load(os.path.join(golden_dir, "backbones.pt"), weights_only=False)
+
+
+def test_self_attention(comp):
+    c = comp["self_attn"]
+    sd = {k: _leaf(v) for k, v in c["sd"].items()}
+    x = _leaf(c["x"])
+    y = O.self_attention(x, sd, "", c["num_heads"])
+    _close(y, c["y"])
+    (y * c["r"]).sum().backward()
+    _close(x.grad, c["xgrad"])
+    for k, g in c["pgrad"].items():
+        _close(sd[k].grad, g)
+    # chunked attention is the same function
+    y2 = O.self_attention(c["x"], c["sd"], "", c["num_heads"], attn_chunk=7)
+    _close(y2, c["y"], 1e-5)
+
+
+def test_cross_attention(comp):
+    c = comp["cross_attn"]
+    sd = {k: _leaf(v) for k, v in c["sd"].items()}
+    x, ctx = _leaf(c["x"]), _leaf(c["ctx"])
+    y, probs = O.cross_attention(x, ctx, sd, "", c["num_heads"], return_probs=True)
+    _close(y, c["y"])
+    _close(probs, c["probs"])
+    (y * c["r"]).sum().backward()
+    _close(x.grad, c["xgrad"])
+    _close(ctx.grad, c["ctxgrad"])
+    for k, g in c["pgrad"].items():
+        _close(sd[k].grad, g)
+
+
+def test_adaln_and_time_embedding(comp):
+    c = comp["adaln"]
+    assert c["zero_init_max"] == 0.0   # reference zero-inits AdaLN (vit_components.py:131-133)
+    for a, b in zip(O.adaln(c["cond"], c["sd"], ""), c["chunks"]):
+        _close(a, b)
+    t = comp["time_embed"]
+    _close(O.sinusoidal_time_embedding(t["t"], 64), t["y"])
+
+
+@pytest.mark.parametrize("name", ["block", "block_prev"])
+def test_block(comp, name):
+    c = comp[name]
+    sd = {k: _leaf(v) for k, v in c["sd"].items()}
+    x, ctx, cond = _leaf(c["x"]), _leaf(c["ctx"]), _leaf(c["cond"])
+    res = O.block(x, ctx, cond, sd, "", c["num_heads"], use_prev_stage=c["use_prev_stage"],
+                  return_attention=c["use_prev_stage"])
+    if c["use_prev_stage"]:
+        res, amap = res
+        _close(amap, c["attn_map"])
+    _close(res, c["y"])
+    (res * c["r"]).sum().backward()
+    _close(x.grad, c["xgrad"])
+    _close(ctx.grad, c["ctxgrad"])
+    _close(cond.grad, c["condgrad"])
+    for k, g in c["pgrad"].items():
+        _close(sd[k].grad, g, 5e-6)
+
+
+@pytest.mark.parametrize("name", ["vit_s2", "vit_s4_quirk", "vit_s1"])
+def test_backbone(bb, name):
+    c = bb[name]
+    cfg = O.BackboneConfig(**c["kwargs"])
+    assert tuple(cfg.downsampled_size) == tuple(c["downsampled_size"])
+    sd = {k: _leaf(v) for k, v in c["sd"].items()}
+    x, ctx, cond = _leaf(c["x"]), _leaf(c["ctx"]), _leaf(c["cond"])
+    y = O.backbone(x, ctx, cond, sd, cfg, prev_stage_embed=c["prev"])
+    _close(y, c["y"])
+    (y * c["r"]).sum().backward()
+    _close(x.grad, c["xgrad"], 1e-5)
+    _close(ctx.grad, c["ctxgrad"], 1e-5)
+    _close(cond.grad, c["condgrad"], 1e-5)
+    for k, g in c["pgrad"].items():
+        _close(sd[k].grad, g, 1e-5)
+
+
+def test_constructor_table(golden_dir):
+    """Token-grid rule, conv plan (incl. the in_channels==C//4 quirk) and every state_dict shape."""
+    rows = json.load(open(os.path.join(golden_dir, "ctor_table.json")))
+    for row in rows:
+        kw = dict(row["kwargs"])
+        kw["volume_size"] = tuple(kw["volume_size"])
+        cfg = O.BackboneConfig(**kw)
+        assert list(cfg.downsampled_size) == row["downsampled_size"], kw
+        assert [[c.index, c.cin, c.cout, c.stride] for c in cfg.convs] == row["convs"], kw
+        sd = O.init_state_dict(cfg)
+        assert {k: list(v.shape) for k, v in sd.items()} == row["shapes"], kw
+
+
+def test_128_defect_is_reproduced_and_patched():
+    """Committed reference: pos_embed 25^3 vs conv stack 32^3 at 128^3 (SURVEY finding 2)."""
+    ref = O.BackboneConfig(volume_size=(128,) * 3, voxel_dim=256, depth=1, num_heads=4)
+    assert ref.downsampled_size == (25, 25, 25)
+    assert O.conv_output_grid(ref.volume_size, ref.convs) == (32, 32, 32)
+    conv = O.BackboneConfig(volume_size=(128,) * 3, voxel_dim=256, depth=1, num_heads=4, token_grid="conv")
+    assert conv.downsampled_size == (32, 32, 32)
+    fix16 = O.BackboneConfig(volume_size=(128,) * 3, voxel_dim=256, depth=1, num_heads=4, token_grid=16)
+    assert fix16.downsampled_size == (16, 16, 16)
+    assert O.conv_output_grid(fix16.volume_size, fix16.convs) == (16, 16, 16)
+    # where the reference is self-consistent the variants coincide
+    for vs in ((64,) * 3, (256,) * 3):
+        a = O.BackboneConfig(volume_size=vs, voxel_dim=256, depth=1, num_heads=4)
+        b = O.BackboneConfig(volume_size=vs, voxel_dim=256, depth=1, num_heads=4, token_grid="conv")
+        assert a.downsampled_size == b.downsampled_size and a.convs == b.convs
+
+
+def test_flops_table_matches_survey():
+    cfg = O.BackboneConfig(volume_size=(64,) * 3, voxel_dim=256, depth=4, num_heads=4)
+    f = O.forward_flops(cfg, 4096)
+    assert abs(f["total"] / 1e9 - 185.3) < 0.5
+    cfg = O.BackboneConfig(volume_size=(128,) * 3, voxel_dim=256, depth=4, num_heads=4, token_grid="conv")
+    f = O.forward_flops(cfg, 4096)
+    assert abs(f["total"] / 1e9 - 5270) < 10
