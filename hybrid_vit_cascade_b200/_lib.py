@@ -1,0 +1,100 @@
+"""ctypes binding of libhvc_sm100a.so (the C ABI declared in include/hvc.h).
+
+There is no fallback: if the shared library is missing, fails to load, or the device is not
+sm_100, every compute entry point raises.  ``python -m hybrid_vit_cascade_b200.build`` (or
+``__graft_entry__.build()``) produces the library in-tree.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libhvc_sm100a.so")
+
+c_f32p = C.c_void_p
+_lib = None
+_device_ok = {}
+
+
+class HvcError(RuntimeError):
+    pass
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("size", C.c_uint32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("lda", C.c_int64), ("a_major", C.c_int32),
+        ("B", C.c_void_p), ("ldb", C.c_int64), ("b_major", C.c_int32),
+        ("epilogue", C.c_int32), ("activation", C.c_int32),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("out2", C.c_void_p), ("ldo2", C.c_int64),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p), ("ldr", C.c_int64),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int64),
+        ("rows_per_batch", C.c_int32),
+        ("aux", C.c_void_p), ("ldaux", C.c_int64),
+        ("alpha", C.c_float), ("k_splits", C.c_int32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("size", C.c_uint32),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32), ("head_dim", C.c_int32),
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("o", C.c_void_p), ("ldo", C.c_int64),
+        ("lse", C.c_void_p),
+        ("d_o", C.c_void_p), ("lddo", C.c_int64),
+        ("dq", C.c_void_p), ("lddq", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64),
+        ("delta", C.c_void_p),
+        ("dq_accum", C.c_void_p),
+        ("probs", C.c_void_p),
+        ("scale", C.c_float),
+    ]
+
+
+def lib():
+    """Load the shared library once; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise HvcError(
+            f"{LIB_PATH} not found: the hybrid_vit_cascade_b200 CUDA extension is not built "
+            "(run `python -m hybrid_vit_cascade_b200.build`). There is no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.hvc_version.restype = C.c_int
+    L.hvc_last_error.restype = C.c_char_p
+    L.hvc_launch_count.restype = C.c_uint64
+    L.hvc_check_device.restype = C.c_int
+    for name in EXPORTS:
+        getattr(L, name)  # AttributeError here = header/library mismatch
+    _lib = L
+    return L
+
+
+# every symbol include/hvc.h declares (tests/test_abi.py checks header <-> library <-> this list)
+EXPORTS = [
+    "hvc_version", "hvc_last_error", "hvc_launch_count", "hvc_check_device",
+    "hvc_gemm",
+]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().hvc_last_error().decode(errors="replace")
+        raise HvcError(f"{what} failed ({rc}): {msg}")
+
+
+def require_device(dev_index):
+    """Verify once per device that we are on sm_100 with a usable driver."""
+    if not _device_ok.get(dev_index):
+        check(lib().hvc_check_device(), "hvc_check_device")
+        _device_ok[dev_index] = True
+
+
+def launch_count():
+    return int(lib().hvc_launch_count())

@@ -1,0 +1,90 @@
+// hvc_host.cu -- error channel, device checks, TMA tensor-map encoding, launch accounting.
+#include <atomic>
+#include <mutex>
+
+#include "hvc_host.h"
+
+namespace hvc {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // resolved at run time so the library has no link-time dependency on libcuda.so
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_cols, uint32_t box_rows, bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) HVC_FAIL(HVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) HVC_FAIL(HVC_ERR_INVALID, "TMA base %p not 16-byte aligned", base);
+  if ((ld * elem_bytes) % 16 != 0)
+    HVC_FAIL(HVC_ERR_INVALID, "TMA row pitch %llu bytes not a multiple of 16", (unsigned long long)(ld * elem_bytes));
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    HVC_FAIL(HVC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u", (int)r,
+             (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_cols, box_rows);
+  return HVC_OK;
+}
+
+int device_sm_count() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev] = n;
+  }
+  return sms[dev];
+}
+
+}  // namespace hvc
+
+extern "C" {
+
+int hvc_version(void) { return HVC_VERSION; }
+const char* hvc_last_error(void) { return hvc::g_err; }
+uint64_t hvc_launch_count(void) { return hvc::g_launches.load(std::memory_order_relaxed); }
+
+int hvc_check_device(void) {
+  int dev = 0;
+  HVC_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  HVC_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  HVC_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) HVC_FAIL(HVC_ERR_ARCH, "libhvc_sm100a needs an sm_100 device (B200); found sm_%d%d", major, minor);
+  if (!hvc::get_encode_fn()) HVC_FAIL(HVC_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  return HVC_OK;
+}
+
+}  // extern "C"
