@@ -79,7 +79,7 @@ def lib():
 # every symbol include/hvc.h declares (tests/test_abi.py checks header <-> library <-> this list)
 EXPORTS = [
     "hvc_version", "hvc_last_error", "hvc_launch_count", "hvc_check_device",
-    "hvc_gemm",
+    "hvc_gemm", "hvc_attn_fwd",
 ]
 
 

@@ -1,0 +1,305 @@
+// hvc_attn_fwd.cu -- fused flash-style attention forward for sm_100a (self- and cross-attention).
+//
+// Replaces  attn = softmax(q k^T * d^-1/2);  out = attn v   (vit_components.py:46-51, :103-113)
+// without ever writing the (B,h,N,M) score matrix: S and P live in TMEM, O accumulates in TMEM.
+//
+// One CTA = one (batch, head) x 256 queries (two 128-row tiles A and B), 320 threads:
+//   warps 0-3   softmax warpgroup A : thread == query row == TMEM lane; online softmax in registers,
+//   warps 4-7   softmax warpgroup B   no cross-thread reductions at all; writes P (bf16) back over S
+//   warp  8     TMA producer        : Q (once), then K/V tiles through two 3-stage rings
+//   warp  9     MMA issuer          : S = Q K^T (SS, 128x128xd), O += P V (TS: P from TMEM, V MN-major)
+// While one warpgroup runs exp2 on tile j the tensor core computes S for the other one, so the MUFU
+// pipe (the real bound at d<=64: 16 ex2/clk/SM vs 4*d flop per score) stays busy.
+// O is rescaled lazily: only when a row maximum grows by more than 2^8 (then the owning warp fixes O
+// in TMEM); otherwise stale maxima are carried and cancel in the final 1/l normalisation.
+//
+// Q, K, V are read in place from the packed projection outputs (row = token, column = head*d + j),
+// O is written token-major [T, h*d] ready for the output projection -- no head split/merge copies.
+#include "hvc_common.cuh"
+#include "hvc_host.h"
+
+namespace hvc {
+
+constexpr int kFwdThreads = 320;
+constexpr int kQTile = 128;
+constexpr int kKTile = 128;
+constexpr int kKvStages = 3;
+
+struct AttnFwdKArgs {
+  int batch, heads, nq, nk, n_kv_tiles;
+  bf16* o; long long ldo;
+  float* lse2;      // [B, H, nq_pad]  log2-domain logsumexp of the scaled scores
+  int nq_pad;
+  float scale2;     // softmax scale * log2(e)
+};
+
+template <int HD>
+struct FwdSmem {
+  static constexpr int kTile = kQTile * HD * 2;       // bytes of one 128 x HD bf16 tile
+  static constexpr int kQ = 0;
+  static constexpr int kK = 2 * kTile;
+  static constexpr int kV = kK + kKvStages * kTile;
+  static constexpr int kBar = kV + kKvStages * kTile;
+  static constexpr int kTotal = kBar + 256 + 1024;
+};
+
+enum { BAR_Q = 0, BAR_KF = 1, BAR_KE = 4, BAR_VF = 7, BAR_VE = 10, BAR_SF = 13, BAR_PF = 15, BAR_OD = 17, BAR_N = 19 };
+
+template <int HD>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdKArgs p) {
+  static_assert(HD == 64, "head_dim 64 (128-byte rows, SWIZZLE_128B) only for now");
+  using L = FwdSmem<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + BAR_N);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads, h = bh - b * p.heads;
+  const int q0 = blockIdx.x * (2 * kQTile);
+  const int n_tiles = p.n_kv_tiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(&bar[BAR_Q], 1);
+    for (int s = 0; s < kKvStages; ++s) {
+      mbar_init(&bar[BAR_KF + s], 1);
+      mbar_init(&bar[BAR_KE + s], 1);
+      mbar_init(&bar[BAR_VF + s], 1);
+      mbar_init(&bar[BAR_VE + s], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&bar[BAR_SF + x], 1);
+      mbar_init(&bar[BAR_PF + x], 128);
+      mbar_init(&bar[BAR_OD + x], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t kColS = 0, kColO = 256;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar[BAR_Q], 2 * L::kTile);
+      tma_load_2d(smem + L::kQ, &tmQ, &bar[BAR_Q], h * HD, b * p.nq + q0, kEvictFirst);
+      tma_load_2d(smem + L::kQ + L::kTile, &tmQ, &bar[BAR_Q], h * HD, b * p.nq + q0 + kQTile, kEvictFirst);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        mbar_wait(&bar[BAR_KE + st], ph ^ 1, 10);
+        mbar_arrive_expect_tx(&bar[BAR_KF + st], L::kTile);
+        tma_load_2d(smem + L::kK + st * L::kTile, &tmK, &bar[BAR_KF + st], h * HD, b * p.nk + j * kKTile, kEvictLast);
+        mbar_wait(&bar[BAR_VE + st], ph ^ 1, 11);
+        mbar_arrive_expect_tx(&bar[BAR_VF + st], L::kTile);
+        tma_load_2d(smem + L::kV + st * L::kTile, &tmV, &bar[BAR_VF + st], h * HD, b * p.nk + j * kKTile, kEvictLast);
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKTile, kMajorK, kMajorK);
+      constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, HD, kMajorK, kMajorMN);
+      const uint32_t sQ = smem_u32(smem + L::kQ), sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
+      auto issue_s = [&](int x, int st) {   // S_x = Q_x K^T
+#pragma unroll
+        for (int k16 = 0; k16 < HD / 16; ++k16)
+          umma_ss(tmem_base + kColS + x * kKTile, make_sdesc_sw128(sQ + x * L::kTile + k16 * 32, 16, 1024),
+                  make_sdesc_sw128(sK + st * L::kTile + k16 * 32, 16, 1024), idesc_s, k16 > 0 ? 1u : 0u);
+      };
+      auto issue_pv = [&](int x, int st, bool acc) {   // O_x (+)= P_x V   (P: TMEM, 8 columns per K=16 step)
+#pragma unroll
+        for (int k16 = 0; k16 < kKTile / 16; ++k16)
+          umma_ts(tmem_base + kColO + x * HD, tmem_base + kColS + x * kKTile + k16 * 8,
+                  make_sdesc_sw128(sV + st * L::kTile + k16 * 2048, 8192, 1024), idesc_o, (acc || k16 > 0) ? 1u : 0u);
+      };
+      mbar_wait(&bar[BAR_Q], 0, 20);
+      mbar_wait(&bar[BAR_KF + 0], 0, 21);
+      tc_fence_after();
+      issue_s(0, 0); tc_commit(&bar[BAR_SF + 0]);
+      issue_s(1, 0); tc_commit(&bar[BAR_SF + 1]);
+      tc_commit(&bar[BAR_KE + 0]);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        const int st1 = (j + 1) % kKvStages;
+        const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
+        const bool more = (j + 1 < n_tiles);
+        mbar_wait(&bar[BAR_VF + st], ph, 22);
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&bar[BAR_PF + x], j & 1, 23);
+          tc_fence_after();
+          issue_pv(x, st, j > 0);
+          tc_commit(&bar[BAR_OD + x]);
+          if (x == 1) tc_commit(&bar[BAR_VE + st]);
+          if (more) {
+            if (x == 0) { mbar_wait(&bar[BAR_KF + st1], ph1, 24); tc_fence_after(); }
+            issue_s(x, st1);
+            tc_commit(&bar[BAR_SF + x]);
+            if (x == 1) tc_commit(&bar[BAR_KE + st1]);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int x = warp >> 2;                 // 0 = tile A, 1 = tile B
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;     // row inside the 128-query tile
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kColS + x * kKTile;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kColO + x * HD;
+    const float scale2 = p.scale2;
+    float m = -INFINITY, l = 0.f;
+    const int tail = p.nk - (n_tiles - 1) * kKTile;   // valid keys in the last tile (1..128)
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&bar[BAR_SF + x], j & 1, 30);
+      tc_fence_after();
+      uint32_t s[128];
+      {
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
+        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
+        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
+        tmem_ld_32x32(tS, s0);
+        tmem_ld_32x32(tS + 32, s1);
+        tmem_ld_32x32(tS + 64, s2);
+        tmem_ld_32x32(tS + 96, s3);
+        tmem_ld_wait();
+      }
+      if (j == n_tiles - 1 && tail < kKTile) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c >= tail) s[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
+            mx3 = __uint_as_float(s[3]);
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
+      }
+      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale2);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = m_new > m + 8.0f;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare: fix up the O accumulator of this warp's 32 rows in TMEM
+          mbar_wait(&bar[BAR_OD + x], (j - 1) & 1, 31);
+          tc_fence_after();
+          const float f = need ? ex2_approx(m - m_new) : 1.0f;
+#pragma unroll
+          for (int c = 0; c < HD; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32(tO + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st_32x32(tO + c, o);
+          }
+          tmem_st_wait();
+          if (need) { l *= f; m = m_new; }
+        }
+      }
+      const float neg_m = -m;
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + c]), scale2, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + c + 1]), scale2, neg_m));
+          sum0 += p0;
+          sum1 += p1;
+          pk[c >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st_32x32(tS + hh * 32, pk);   // P (bf16 pairs) overwrites S columns already held in registers
+      }
+      l += sum0 + sum1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&bar[BAR_PF + x]);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global, logsumexp
+    mbar_wait(&bar[BAR_OD + x], (n_tiles - 1) & 1, 32);
+    tc_fence_after();
+    const int q = q0 + x * kQTile + row;
+    const float inv = 1.0f / l;
+    bf16* optr = p.o + (long long)(b * p.nq + q) * p.ldo + h * HD;
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32(tO + c, o);
+      tmem_ld_wait();
+      if (q < p.nq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c + i) = u;
+        }
+      }
+    }
+    if (q < p.nq && p.lse2 != nullptr) p.lse2[(long long)bh * p.nq_pad + q] = m + log2f(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace hvc
+
+extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
+  using namespace hvc;
+  HVC_CHECK_ARG(a != nullptr && a->size == sizeof(hvc_attn_args), "hvc_attn_fwd: bad args struct");
+  HVC_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->nq > 0 && a->nk > 0, "hvc_attn_fwd: empty problem");
+  HVC_CHECK_ARG(a->head_dim == 64, "hvc_attn_fwd: head_dim %d not supported (64 only)", a->head_dim);
+  HVC_CHECK_ARG(a->q && a->k && a->v && a->o, "hvc_attn_fwd: null operand");
+  HVC_CHECK_ARG((a->ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "hvc_attn_fwd: o must be 16-byte aligned rows");
+  constexpr int HD = 64;
+  using L = FwdSmem<HD>;
+  const uint64_t width = (uint64_t)a->heads * HD;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kQTile, true))) return rc;
+  if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kKTile, true))) return rc;
+  if ((rc = make_tmap_2d(&tmV, a->v, 2, (uint64_t)a->batch * a->nk, width, a->ldv, HD, kKTile, true))) return rc;
+  AttnFwdKArgs ka;
+  ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk;
+  ka.n_kv_tiles = (a->nk + kKTile - 1) / kKTile;
+  ka.o = reinterpret_cast<bf16*>(a->o); ka.ldo = a->ldo;
+  ka.lse2 = reinterpret_cast<float*>(a->lse);
+  ka.nq_pad = (a->nq + 127) / 128 * 128;
+  ka.scale2 = a->scale * 1.4426950408889634f;
+  static bool configured = false;
+  if (!configured) {
+    HVC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  dim3 grid((a->nq + 2 * kQTile - 1) / (2 * kQTile), a->batch * a->heads);
+  attn_fwd_kernel<HD><<<grid, kFwdThreads, L::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, ka);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}

@@ -81,3 +81,35 @@ def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epil
     args.k_splits = k_splits
     _lib.check(_lib.lib().hvc_gemm(C.byref(args), _stream()), "hvc_gemm")
     return out
+
+
+def _pad128(n):
+    return (n + 127) // 128 * 128
+
+
+def _attn_args(q, k, v, B, H, nq, nk, d, scale):
+    args = _lib.AttnArgs()
+    args.size = C.sizeof(_lib.AttnArgs)
+    args.batch, args.heads, args.nq, args.nk, args.head_dim = B, H, nq, nk, d
+    args.q, args.ldq = q.data_ptr(), _row_major_2d(q, "q")
+    args.k, args.ldk = k.data_ptr(), _row_major_2d(k, "k")
+    args.v, args.ldv = v.data_ptr(), _row_major_2d(v, "v")
+    args.scale = scale
+    return args
+
+
+def attn_fwd(q, k, v, B, H, nq, nk, d, scale):
+    """q: bf16 view [B*nq, H*d] (may be a column slice of a packed projection output), k/v: [B*nk, H*d].
+
+    Returns (o bf16 [B*nq, H*d], lse2 f32 [B, H, pad128(nq)]).
+    """
+    _need_cuda(q, k, v)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.shape == (B * nq, H * d) and k.shape == (B * nk, H * d) and v.shape == (B * nk, H * d)
+    o = torch.empty(B * nq, H * d, device=q.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, _pad128(nq), device=q.device, dtype=torch.float32)
+    args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
+    args.o, args.ldo = o.data_ptr(), o.stride(0)
+    args.lse = lse.data_ptr()
+    _lib.check(_lib.lib().hvc_attn_fwd(C.byref(args), _stream()), "hvc_attn_fwd")
+    return o, lse

@@ -91,6 +91,110 @@ typedef struct hvc_gemm_args {
 
 int hvc_gemm(const hvc_gemm_args* args, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused flash-style attention (self- and cross-), forward and backward.
+ *   out = softmax(q k^T * scale) v      per (batch, head); scores never leave TMEM
+ * Replaces vit_components.py:46-51 (self) and :103-113 (cross) and their autograd backward.
+ * q/k/v/o are read/written IN PLACE in token-major packed buffers: row = b*n + token, the head's
+ * columns are [head*head_dim, (head+1)*head_dim) starting at the given base pointer (so q, k, v may
+ * all point into one [T, 3C] qkv projection output; ld* are the row pitches in elements).
+ * lse: f32 [batch, heads, nq_pad] base-2 logsumexp of the scaled scores (forward output, backward
+ * input), nq_pad = nq rounded up to 128.  delta: f32 [batch, heads, nq_pad] = rowsum(dO * O)
+ * (scratch, written by hvc_attn_bwd).  dq_accum: f32 [batch, heads, nq_pad, head_dim] zero-filled
+ * scratch for the cross-CTA dQ reduction.
+ * head_dim: 64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hvc_attn_args {
+  uint32_t size;
+  int32_t batch, heads, nq, nk, head_dim;
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  void* o; int64_t ldo;           /* bf16 [batch*nq, heads*head_dim] (forward: output; backward: input) */
+  float* lse;
+  const void* d_o; int64_t lddo;  /* backward only from here on */
+  void* dq; int64_t lddq;
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
+  float* delta;
+  float* dq_accum;
+  void* probs;                    /* optional f32 [batch, heads, nq, nk]: materialised softmax (store_attention) */
+  float scale;
+} hvc_attn_args;
+
+int hvc_attn_fwd(const hvc_attn_args* args, void* stream);
+int hvc_attn_bwd(const hvc_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused LayerNorm (+AdaLN modulate) -> GEMM operand, and its backward.  HBM-bound, one pass.
+ *   y = LN(x; w, b, eps=1e-5) [* (1 + scale[batch]) + shift[batch]]
+ * Replaces nn.LayerNorm + the modulate elementwise ops, hybrid_vit_backbone.py:120-121,126,136-137,265.
+ * x: f32 [T, C]; y: bf16 (y_is_bf16) or f32 [T, C]; mean/rstd: f32 [T] saved for backward (may be NULL);
+ * shift/scale: f32, element (b, c) at [b*mod_ld + c] (both or neither); C multiple of 4, <= 1024.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hvc_ln_args {
+  uint32_t size;
+  int32_t T, C;
+  const float* x; int64_t ldx;
+  const float* w; const float* b;
+  const float* shift; const float* scale; int64_t mod_ld; int32_t rows_per_batch;
+  void* y; int64_t ldy; int32_t y_is_bf16;
+  float* mean; float* rstd;
+} hvc_ln_args;
+int hvc_ln_fwd(const hvc_ln_args* args, void* stream);
+
+/* Backward of the above.  dz (gradient w.r.t. y) comes from exactly one of: dz_bf16 [T,C], dz_f32 [T,C],
+ * dz_row [T] (the output head: y is contracted with mult_vec = output_proj.weight, hybrid_vit_backbone.py:266,
+ * so dz[t,c] = dz_row[t] * mult_vec[c]).  Outputs: dx f32 [T,C] (= dx_in + LN backward when dx_in != NULL),
+ * dw/db [C], dshift/dscale [batch, C] at pitch dmod_ld (modulated LN), dvec [C] + dscalar [1] (head:
+ * d output_proj.weight / .bias).  S1/S2: f32 [batch, C] scratch. */
+typedef struct hvc_ln_bwd_args {
+  uint32_t size;
+  int32_t batch, rows_per_batch, C;
+  const void* dz_bf16; const float* dz_f32; int64_t lddz; const float* dz_row;
+  const float* x; int64_t ldx;
+  const float* mean; const float* rstd;
+  const float* w; const float* b;
+  const float* scale; int64_t mod_ld;
+  const float* mult_vec;
+  const float* dx_in; int64_t lddx_in;
+  float* dx; int64_t lddx;
+  float* dw; float* db;
+  float* dshift; float* dscale; int64_t dmod_ld;
+  float* dvec; float* dscalar;
+  float* S1; float* S2;
+} hvc_ln_bwd_args;
+int hvc_ln_bwd(const hvc_ln_bwd_args* args, void* stream);
+
+/* Backward of the gated residual  out = resid + gate[batch] * branch  (hybrid_vit_backbone.py:123,128,139):
+ *   dbranch bf16 [T,C] = gate * dout;  dgate f32 [batch,C] = sum_n dout*branch (optional, needs branch);
+ *   dbias f32 [C] = sum_T dbranch (optional; the bias of the projection that produced branch).
+ * gate == NULL means 1 (cross-attention residual).  D1: f32 [batch, C] scratch. */
+typedef struct hvc_resid_bwd_args {
+  uint32_t size;
+  int32_t batch, rows_per_batch, C;
+  const float* dout; int64_t lddout;
+  const void* branch; int64_t ldbranch;
+  const float* gate; int64_t gate_ld;
+  void* dbranch; int64_t lddbranch;
+  float* dgate; float* dbias; float* D1;
+} hvc_resid_bwd_args;
+int hvc_resid_bwd(const hvc_resid_bwd_args* args, void* stream);
+
+/* out[c] = sum_t x[t,c] for bf16 x [T,C] (bias gradient of mlp.0, hybrid_vit_backbone.py:76). */
+int hvc_colsum_bf16(const void* x, int64_t ldx, int32_t T, int32_t C, float* out, void* stream);
+/* f32 -> bf16, contiguous (weights are cast once per optimizer step). */
+int hvc_cast_bf16(const float* x, void* y, int64_t n, void* stream);
+/* x[b,m,c] (f32 or bf16, element strides sb/sm/sc -- e.g. the transposed view of the (B,C,H,W) X-ray
+ * feature map, model_direct.py:80) -> y bf16 [B*M, C] contiguous. */
+int hvc_cast_tokens(const void* x, int32_t x_is_bf16, int64_t sb, int64_t sm, int64_t sc, void* y, int32_t B,
+                    int32_t M, int32_t C, void* stream);
+/* AdaLN modulation linear, vit_components.py:144: out[B,J] = cond[B,K] W[J,K]^T + bias[J] (fp32 throughout). */
+int hvc_adaln_fwd(const float* cond, int64_t ldc, const float* W, const float* bias, float* out, int32_t B,
+                  int32_t K, int32_t J, void* stream);
+int hvc_adaln_bwd(const float* dparams, const float* cond, int64_t ldc, const float* W, float* dW, float* dbias,
+                  float* dcond, int32_t B, int32_t K, int32_t J, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

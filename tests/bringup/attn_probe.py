@@ -1,0 +1,85 @@
+"""Bring-up probe for hvc_attn_fwd / hvc_attn_bwd; each case in its own process."""
+import math
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+CASES = {
+    # name: (B, H, nq, nk, d, packed_self)
+    "fwd_1tile": (1, 1, 256, 128, 64, False),
+    "fwd_multi": (1, 2, 512, 640, 64, False),
+    "fwd_self_packed": (2, 4, 1024, 1024, 64, True),
+    "fwd_ragged": (2, 2, 200, 72, 64, False),
+    "fwd_bigrange": (1, 1, 256, 1024, 64, False),
+    "fwd_4096": (2, 4, 4096, 4096, 64, True),
+}
+
+
+def ref_attn(q, k, v, scale):
+    s = (q.float() @ k.float().transpose(-1, -2)) * scale
+    p = s.softmax(-1)
+    return p @ v.float(), torch.logsumexp(s, -1)
+
+
+def run_case(name, bwd=False):
+    global torch
+    import torch
+    from hybrid_vit_cascade_b200 import kernels as K
+    B, H, nq, nk, d, packed = CASES[name]
+    g = torch.Generator(device="cuda").manual_seed(3)
+    C = H * d
+    amp = 4.0 if name == "fwd_bigrange" else 1.0
+    if packed:
+        qkv = (torch.randn(B * nq, 3 * C, device="cuda", generator=g) * amp).bfloat16()
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q = (torch.randn(B * nq, C, device="cuda", generator=g) * amp).bfloat16()
+        k = (torch.randn(B * nk, C, device="cuda", generator=g) * amp).bfloat16()
+        v = torch.randn(B * nk, C, device="cuda", generator=g).bfloat16()
+    scale = d ** -0.5
+    o, lse2 = K.attn_fwd(q, k, v, B, H, nq, nk, d, scale)
+    torch.cuda.synchronize()
+    q4 = q.reshape(B, nq, H, d).permute(0, 2, 1, 3)
+    k4 = k.reshape(B, nk, H, d).permute(0, 2, 1, 3)
+    v4 = v.reshape(B, nk, H, d).permute(0, 2, 1, 3)
+    ro, rlse = ref_attn(q4, k4, v4, scale)
+    ro = ro.permute(0, 2, 1, 3).reshape(B * nq, C)
+    err = float((o.float() - ro).abs().max() / ro.abs().max())
+    lerr = float((lse2[:, :, :nq] * math.log(2.0) - rlse).abs().max())
+    ok = err < 2e-2 and lerr < 2e-2
+    print(f"CASE {name}: out relerr {err:.3e} lse abserr {lerr:.3e} {'OK' if ok else 'FAIL'}")
+    if name == "fwd_4096":
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for _ in range(3):
+            K.attn_fwd(q, k, v, B, H, nq, nk, d, scale)
+        ev[0].record()
+        for _ in range(10):
+            K.attn_fwd(q, k, v, B, H, nq, nk, d, scale)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 10
+        fl = 4.0 * B * H * nq * nk * d
+        print(f"  fwd_4096: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s")
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:]
+    if names:
+        sys.exit(max(run_case(n) for n in names))
+    bad = 0
+    for n in CASES:
+        try:
+            r = subprocess.run([sys.executable, __file__, n], capture_output=True, text=True, timeout=120)
+            print(r.stdout.strip() or f"CASE {n}: no output")
+            if r.returncode != 0:
+                bad += 1
+                print("  rc", r.returncode, r.stderr.strip()[-800:])
+        except subprocess.TimeoutExpired:
+            bad += 1
+            print(f"CASE {n}: TIMEOUT")
+    print("attn_probe failures:", bad)
+    sys.exit(1 if bad else 0)
