@@ -56,6 +56,46 @@ class AttnArgs(C.Structure):
     ]
 
 
+class LnArgs(C.Structure):
+    _fields_ = [
+        ("size", C.c_uint32), ("T", C.c_int32), ("C", C.c_int32),
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("w", C.c_void_p), ("b", C.c_void_p),
+        ("shift", C.c_void_p), ("scale", C.c_void_p), ("mod_ld", C.c_int64), ("rows_per_batch", C.c_int32),
+        ("y", C.c_void_p), ("ldy", C.c_int64), ("y_is_bf16", C.c_int32),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
+    ]
+
+
+class LnBwdArgs(C.Structure):
+    _fields_ = [
+        ("size", C.c_uint32), ("batch", C.c_int32), ("rows_per_batch", C.c_int32), ("C", C.c_int32),
+        ("dz_bf16", C.c_void_p), ("dz_f32", C.c_void_p), ("lddz", C.c_int64), ("dz_row", C.c_void_p),
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("w", C.c_void_p), ("b", C.c_void_p),
+        ("scale", C.c_void_p), ("mod_ld", C.c_int64),
+        ("mult_vec", C.c_void_p),
+        ("dx_in", C.c_void_p), ("lddx_in", C.c_int64),
+        ("dx", C.c_void_p), ("lddx", C.c_int64),
+        ("dw", C.c_void_p), ("db", C.c_void_p),
+        ("dshift", C.c_void_p), ("dscale", C.c_void_p), ("dmod_ld", C.c_int64),
+        ("dvec", C.c_void_p), ("dscalar", C.c_void_p),
+        ("S1", C.c_void_p), ("S2", C.c_void_p),
+    ]
+
+
+class ResidBwdArgs(C.Structure):
+    _fields_ = [
+        ("size", C.c_uint32), ("batch", C.c_int32), ("rows_per_batch", C.c_int32), ("C", C.c_int32),
+        ("dout", C.c_void_p), ("lddout", C.c_int64),
+        ("branch", C.c_void_p), ("ldbranch", C.c_int64),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int64),
+        ("dbranch", C.c_void_p), ("lddbranch", C.c_int64),
+        ("dgate", C.c_void_p), ("dbias", C.c_void_p), ("D1", C.c_void_p),
+    ]
+
+
 def lib():
     """Load the shared library once; raise loudly if it is not there."""
     global _lib
@@ -79,7 +119,9 @@ def lib():
 # every symbol include/hvc.h declares (tests/test_abi.py checks header <-> library <-> this list)
 EXPORTS = [
     "hvc_version", "hvc_last_error", "hvc_launch_count", "hvc_check_device",
-    "hvc_gemm", "hvc_attn_fwd",
+    "hvc_gemm", "hvc_attn_fwd", "hvc_attn_bwd",
+    "hvc_ln_fwd", "hvc_ln_bwd", "hvc_resid_bwd", "hvc_colsum_bf16", "hvc_cast_bf16", "hvc_cast_tokens",
+    "hvc_adaln_fwd", "hvc_adaln_bwd",
 ]
 
 

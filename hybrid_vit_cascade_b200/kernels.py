@@ -113,3 +113,169 @@ def attn_fwd(q, k, v, B, H, nq, nk, d, scale):
     args.lse = lse.data_ptr()
     _lib.check(_lib.lib().hvc_attn_fwd(C.byref(args), _stream()), "hvc_attn_fwd")
     return o, lse
+
+
+def attn_bwd(q, k, v, o, lse, d_o, B, H, nq, nk, d, scale, dq, dk, dv):
+    """Backward of attn_fwd.  dq/dk/dv: bf16 views [B*n, H*d] (column slices of packed gradient buffers)."""
+    _need_cuda(q, k, v, o, d_o)
+    assert d_o.dtype == torch.bfloat16 and o.dtype == torch.bfloat16
+    nq_pad = _pad128(nq)
+    delta = torch.empty(B, H, nq_pad, device=q.device, dtype=torch.float32)
+    dq_accum = torch.zeros(B, H, nq_pad, d, device=q.device, dtype=torch.float32)
+    args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
+    args.o, args.ldo = o.data_ptr(), _row_major_2d(o, "o")
+    args.lse = lse.data_ptr()
+    args.d_o, args.lddo = d_o.data_ptr(), _row_major_2d(d_o, "d_o")
+    args.dq, args.lddq = dq.data_ptr(), _row_major_2d(dq, "dq")
+    args.dk, args.lddk = dk.data_ptr(), _row_major_2d(dk, "dk")
+    args.dv, args.lddv = dv.data_ptr(), _row_major_2d(dv, "dv")
+    args.delta = delta.data_ptr()
+    args.dq_accum = dq_accum.data_ptr()
+    _lib.check(_lib.lib().hvc_attn_bwd(C.byref(args), _stream()), "hvc_attn_bwd")
+    return dq, dk, dv
+
+
+# ------------------------------------------------------------------ LayerNorm / residual / casts / AdaLN
+
+def ln_fwd(x, w, b, shift=None, scale=None, mod_ld=0, rows_per_batch=0, out_dtype=torch.bfloat16, save_stats=True):
+    """x f32 [T,C] -> (y [T,C] bf16|f32, mean [T], rstd [T]).  shift/scale: f32 views with unit inner stride."""
+    _need_cuda(x, w, b)
+    assert x.dtype == torch.float32
+    T, Cc = x.shape
+    y = torch.empty(T, Cc, device=x.device, dtype=out_dtype)
+    mean = torch.empty(T, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32) if save_stats else None
+    a = _lib.LnArgs()
+    a.size = C.sizeof(_lib.LnArgs)
+    a.T, a.C = T, Cc
+    a.x, a.ldx = x.data_ptr(), _row_major_2d(x, "x")
+    a.w, a.b = w.data_ptr(), b.data_ptr()
+    if scale is not None:
+        a.shift, a.scale, a.mod_ld, a.rows_per_batch = shift.data_ptr(), scale.data_ptr(), mod_ld, rows_per_batch
+    a.y, a.ldy, a.y_is_bf16 = y.data_ptr(), y.stride(0), int(out_dtype == torch.bfloat16)
+    a.mean, a.rstd = _ptr(mean), _ptr(rstd)
+    _lib.check(_lib.lib().hvc_ln_fwd(C.byref(a), _stream()), "hvc_ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(dz, x, mean, rstd, w, b, batch, rows_per_batch, scale=None, mod_ld=0, mult_vec=None, dx_in=None,
+           want_mod=False, head=False):
+    """Returns dict(dx, dw, db[, dshift, dscale][, dvec, dscalar]).  dz: bf16/f32 [T,C] or f32 [T] (head)."""
+    _need_cuda(dz, x)
+    T, Cc = x.shape
+    dev = x.device
+    a = _lib.LnBwdArgs()
+    a.size = C.sizeof(_lib.LnBwdArgs)
+    a.batch, a.rows_per_batch, a.C = batch, rows_per_batch, Cc
+    if dz.dim() == 1:
+        assert dz.dtype == torch.float32 and dz.is_contiguous()
+        a.dz_row = dz.data_ptr()
+    elif dz.dtype == torch.bfloat16:
+        a.dz_bf16, a.lddz = dz.data_ptr(), _row_major_2d(dz, "dz")
+    else:
+        assert dz.dtype == torch.float32
+        a.dz_f32, a.lddz = dz.data_ptr(), _row_major_2d(dz, "dz")
+    a.x, a.ldx = x.data_ptr(), _row_major_2d(x, "x")
+    a.mean, a.rstd, a.w, a.b = mean.data_ptr(), rstd.data_ptr(), w.data_ptr(), b.data_ptr()
+    if scale is not None:
+        a.scale, a.mod_ld = scale.data_ptr(), mod_ld
+    if mult_vec is not None:
+        a.mult_vec = mult_vec.data_ptr()
+    if dx_in is not None:
+        a.dx_in, a.lddx_in = dx_in.data_ptr(), _row_major_2d(dx_in, "dx_in")
+    out = {"dx": torch.empty(T, Cc, device=dev, dtype=torch.float32),
+           "dw": torch.empty(Cc, device=dev, dtype=torch.float32),
+           "db": torch.empty(Cc, device=dev, dtype=torch.float32)}
+    a.dx, a.lddx = out["dx"].data_ptr(), Cc
+    a.dw, a.db = out["dw"].data_ptr(), out["db"].data_ptr()
+    if want_mod:
+        out["dmod"] = torch.empty(batch, 2, Cc, device=dev, dtype=torch.float32)   # [:,0]=dshift [:,1]=dscale
+        a.dshift, a.dscale, a.dmod_ld = out["dmod"][:, 0].data_ptr(), out["dmod"][:, 1].data_ptr(), 2 * Cc
+    if head:
+        out["dvec"] = torch.empty(Cc, device=dev, dtype=torch.float32)
+        out["dscalar"] = torch.empty(1, device=dev, dtype=torch.float32)
+        a.dvec, a.dscalar = out["dvec"].data_ptr(), out["dscalar"].data_ptr()
+    scratch = torch.empty(2, batch, Cc, device=dev, dtype=torch.float32)
+    a.S1, a.S2 = scratch[0].data_ptr(), scratch[1].data_ptr()
+    _lib.check(_lib.lib().hvc_ln_bwd(C.byref(a), _stream()), "hvc_ln_bwd")
+    return out
+
+
+def resid_bwd(dout, batch, rows_per_batch, branch=None, gate=None, gate_ld=0, want_dbias=True):
+    """dout f32 [T,C] -> (dbranch bf16 [T,C], dgate f32 [batch,C] | None, dbias f32 [C] | None)."""
+    _need_cuda(dout)
+    T, Cc = dout.shape
+    dev = dout.device
+    a = _lib.ResidBwdArgs()
+    a.size = C.sizeof(_lib.ResidBwdArgs)
+    a.batch, a.rows_per_batch, a.C = batch, rows_per_batch, Cc
+    a.dout, a.lddout = dout.data_ptr(), _row_major_2d(dout, "dout")
+    dbranch = torch.empty(T, Cc, device=dev, dtype=torch.bfloat16)
+    a.dbranch, a.lddbranch = dbranch.data_ptr(), Cc
+    dgate = None
+    if gate is not None:
+        a.gate, a.gate_ld = gate.data_ptr(), gate_ld
+        if branch is not None:
+            a.branch, a.ldbranch = branch.data_ptr(), _row_major_2d(branch, "branch")
+            dgate = torch.empty(batch, Cc, device=dev, dtype=torch.float32)
+            a.dgate = dgate.data_ptr()
+    dbias = torch.empty(Cc, device=dev, dtype=torch.float32) if want_dbias else None
+    a.dbias = _ptr(dbias)
+    d1 = torch.empty(batch, Cc, device=dev, dtype=torch.float32)
+    a.D1 = d1.data_ptr()
+    _lib.check(_lib.lib().hvc_resid_bwd(C.byref(a), _stream()), "hvc_resid_bwd")
+    return dbranch, dgate, dbias
+
+
+def colsum_bf16(x):
+    _need_cuda(x)
+    assert x.dtype == torch.bfloat16
+    out = torch.empty(x.shape[1], device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_colsum_bf16(_ptr(x), C.c_int64(_row_major_2d(x, "x")), x.shape[0], x.shape[1], _ptr(out),
+                                          _stream()), "hvc_colsum_bf16")
+    return out
+
+
+def cast_bf16(x):
+    """Contiguous f32 -> bf16."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().hvc_cast_bf16(_ptr(x), _ptr(y), C.c_int64(x.numel()), _stream()), "hvc_cast_bf16")
+    return y
+
+
+def cast_tokens(x):
+    """x (B, M, C) f32|bf16 with arbitrary strides -> bf16 [B*M, C] contiguous."""
+    _need_cuda(x)
+    assert x.dim() == 3 and x.dtype in (torch.float32, torch.bfloat16)
+    B, M, Cc = x.shape
+    y = torch.empty(B * M, Cc, device=x.device, dtype=torch.bfloat16)
+    sb, sm, sc = x.stride()
+    _lib.check(_lib.lib().hvc_cast_tokens(_ptr(x), int(x.dtype == torch.bfloat16), C.c_int64(sb), C.c_int64(sm),
+                                          C.c_int64(sc), _ptr(y), B, M, Cc, _stream()), "hvc_cast_tokens")
+    return y
+
+
+def adaln_fwd(cond, W, bias):
+    _need_cuda(cond, W)
+    assert cond.dtype == W.dtype == torch.float32 and W.is_contiguous() and cond.stride(1) == 1
+    B, K = cond.shape
+    J = W.shape[0]
+    out = torch.empty(B, J, device=cond.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_adaln_fwd(_ptr(cond), C.c_int64(cond.stride(0)), _ptr(W), _ptr(bias), _ptr(out), B, K, J,
+                                        _stream()), "hvc_adaln_fwd")
+    return out
+
+
+def adaln_bwd(dparams, cond, W, need_w=True, need_cond=True):
+    _need_cuda(dparams, cond, W)
+    assert dparams.dtype == torch.float32 and dparams.is_contiguous() and cond.stride(1) == 1
+    B, K = cond.shape
+    J = W.shape[0]
+    dW = torch.empty(J, K, device=cond.device, dtype=torch.float32) if need_w else None
+    db = torch.empty(J, device=cond.device, dtype=torch.float32) if need_w else None
+    dcond = torch.empty(B, K, device=cond.device, dtype=torch.float32) if need_cond else None
+    _lib.check(_lib.lib().hvc_adaln_bwd(_ptr(dparams), _ptr(cond), C.c_int64(cond.stride(0)), _ptr(W), _ptr(dW), _ptr(db),
+                                        _ptr(dcond), B, K, J, _stream()), "hvc_adaln_bwd")
+    return dW, db, dcond

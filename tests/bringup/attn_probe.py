@@ -15,6 +15,11 @@ CASES = {
     "fwd_ragged": (2, 2, 200, 72, 64, False),
     "fwd_bigrange": (1, 1, 256, 1024, 64, False),
     "fwd_4096": (2, 4, 4096, 4096, 64, True),
+    "bwd_1tile": (1, 1, 128, 128, 64, False),
+    "bwd_multi": (1, 2, 384, 256, 64, False),
+    "bwd_ragged": (2, 2, 200, 72, 64, False),
+    "bwd_self_packed": (2, 4, 1024, 1024, 64, True),
+    "bwd_4096": (2, 4, 4096, 4096, 64, True),
 }
 
 
@@ -51,6 +56,39 @@ def run_case(name, bwd=False):
     lerr = float((lse2[:, :, :nq] * math.log(2.0) - rlse).abs().max())
     ok = err < 2e-2 and lerr < 2e-2
     print(f"CASE {name}: out relerr {err:.3e} lse abserr {lerr:.3e} {'OK' if ok else 'FAIL'}")
+    if name.startswith("bwd"):
+        d_o = torch.randn(B * nq, C, device="cuda", generator=g).bfloat16()
+        if packed:
+            dqkv = torch.full((B * nq, 3 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            dq, dk, dv = dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]
+        else:
+            dq = torch.full((B * nq, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            dk = torch.full((B * nk, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+            dv = torch.full((B * nk, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+        K.attn_bwd(q, k, v, o, lse2, d_o, B, H, nq, nk, d, scale, dq, dk, dv)
+        torch.cuda.synchronize()
+        qf, kf, vf = [t.float().detach().requires_grad_(True) for t in (q4, k4, v4)]
+        ro2, _ = ref_attn(qf, kf, vf, scale)
+        ro2.backward(d_o.float().reshape(B, nq, H, d).permute(0, 2, 1, 3))
+        for nm, mine, ref, n in (("dq", dq, qf.grad, nq), ("dk", dk, kf.grad, nk), ("dv", dv, vf.grad, nk)):
+            ref2 = ref.permute(0, 2, 1, 3).reshape(B * n, C)
+            e = float((mine.float() - ref2).abs().max() / ref2.abs().max())
+            cs = float(torch.nn.functional.cosine_similarity(mine.float().flatten(), ref2.flatten(), dim=0))
+            good = e < 3e-2 and cs > 0.999
+            ok = ok and good
+            print(f"  {nm}: relerr {e:.3e} cos {cs:.6f} {'OK' if good else 'FAIL'}")
+        if name == "bwd_4096":
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            for _ in range(3):
+                K.attn_bwd(q, k, v, o, lse2, d_o, B, H, nq, nk, d, scale, dq, dk, dv)
+            ev[0].record()
+            for _ in range(10):
+                K.attn_bwd(q, k, v, o, lse2, d_o, B, H, nq, nk, d, scale, dq, dk, dv)
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / 10
+            fl = 10.0 * B * H * nq * nk * d
+            print(f"  bwd_4096: {ms*1e3:.1f} us  {fl/ms/1e9:.1f} TFLOP/s (incl. delta/zero/convert)")
     if name == "fwd_4096":
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         for _ in range(3):
