@@ -1,0 +1,323 @@
+// hvc_embed.cu -- the voxel-embedding stack of HybridViT3D (hybrid_vit_backbone.py:195-210,252):
+//   Conv3d(k3, p1, stride 1|2) [+ GroupNorm(min(8,C)) + SiLU] ... -> token-major activations.
+// Each conv runs as  im2col (bf16 patch matrix) -> tcgen05 GEMM (hvc_gemm, bias fused) with
+// channels-last activations [B, voxels, C], so the last conv emits the (B, N, C) token layout
+// directly (the reference's flatten(2).transpose(1,2), :255, costs nothing).  Backward = dgrad GEMM +
+// col2im gather, wgrad GEMM (split-K).  GroupNorm+SiLU forward/backward are HBM-bound passes over the
+// channels-last tensor with per-(batch, channel) partial sums reduced through shared memory.
+// (Round-2 item: fold im2col into the GEMM's TMA producer -- cuTensorMapEncodeIm2col -- so the patch
+// matrix never exists in HBM.)
+#include "hvc_common.cuh"
+#include "hvc_host.h"
+
+namespace hvc {
+
+struct Conv3dGeom {
+  int B, Cin, D, H, W;        // input
+  int Do, Ho, Wo, stride;     // output grid (k=3, pad=1)
+  long long sb, sc, sd, sh, sw;  // input element strides
+  int K, Kp;                  // Cin*27 and its padding to a multiple of 8
+};
+
+// cols[m, k] = x[b, cin, od*s-1+kd, oh*s-1+kh, ow*s-1+kw]   (0 outside), k = cin*27 + kd*9 + kh*3 + kw
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2col3d_kernel(const TIn* __restrict__ x, bf16* __restrict__ cols, const Conv3dGeom g) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * g.Kp;
+  if (idx >= total) return;
+  const int k = (int)(idx % g.Kp);
+  long long m = idx / g.Kp;
+  float v = 0.f;
+  if (k < g.K) {
+    const int cin = k / 27, tap = k - cin * 27;
+    const int kd = tap / 9, kh = (tap - kd * 9) / 3, kw = tap - kd * 9 - kh * 3;
+    const int ow = (int)(m % g.Wo); m /= g.Wo;
+    const int oh = (int)(m % g.Ho); m /= g.Ho;
+    const int od = (int)(m % g.Do);
+    const int b = (int)(m / g.Do);
+    const int id = od * g.stride - 1 + kd, ih = oh * g.stride - 1 + kh, iw = ow * g.stride - 1 + kw;
+    if (id >= 0 && id < g.D && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+      v = static_cast<float>(x[b * g.sb + cin * g.sc + id * g.sd + ih * g.sh + iw * g.sw]);
+  }
+  cols[idx] = __float2bfloat16(v);
+}
+
+// dx[b, c, d, h, w] = sum over taps/outputs that read it of dcols[(b,od,oh,ow), c*27 + tap]
+__global__ void __launch_bounds__(256) col2im3d_kernel(const bf16* __restrict__ dcols, float* __restrict__ dx, const Conv3dGeom g) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*D*H*W*Cin, c fastest when channels-last
+  const long long total = (long long)g.B * g.Cin * g.D * g.H * g.W;
+  if (idx >= total) return;
+  int c, w, h, d, b;
+  long long t = idx;
+  if (g.sc == 1) {   // channels-last: keep c fastest so writes coalesce
+    c = (int)(t % g.Cin); t /= g.Cin;
+    w = (int)(t % g.W); t /= g.W;
+    h = (int)(t % g.H); t /= g.H;
+    d = (int)(t % g.D); b = (int)(t / g.D);
+  } else {
+    w = (int)(t % g.W); t /= g.W;
+    h = (int)(t % g.H); t /= g.H;
+    d = (int)(t % g.D); t /= g.D;
+    c = (int)(t % g.Cin); b = (int)(t / g.Cin);
+  }
+  float acc = 0.f;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    const int nd = d + 1 - kd;
+    if (nd < 0 || nd % g.stride) continue;
+    const int od = nd / g.stride;
+    if (od >= g.Do) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int nh = h + 1 - kh;
+      if (nh < 0 || nh % g.stride) continue;
+      const int oh = nh / g.stride;
+      if (oh >= g.Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int nw = w + 1 - kw;
+        if (nw < 0 || nw % g.stride) continue;
+        const int ow = nw / g.stride;
+        if (ow >= g.Wo) continue;
+        const long long m = (((long long)b * g.Do + od) * g.Ho + oh) * g.Wo + ow;
+        acc += __bfloat162float(dcols[m * g.Kp + c * 27 + kd * 9 + kh * 3 + kw]);
+      }
+    }
+  }
+  dx[b * g.sb + c * g.sc + d * g.sd + h * g.sh + w * g.sw] = acc;
+}
+
+// ------------------------------------------------------------------ per-(batch, channel) sums over voxels
+// MODE 0: S1 = sum x,        S2 = sum x^2                          (GroupNorm forward statistics)
+// MODE 1: S1 = sum ds,       S2 = sum ds * xhat   with ds = dy * silu'(z), z = xhat*w + b   (backward)
+struct GnStatArgs {
+  const float* x; const float* dy;      // [B, V, C] channels-last f32
+  const float* mean; const float* rstd; // [B, G]
+  const float* w; const float* b;       // [C]
+  float* S1; float* S2;                 // [B, C]
+  int V, C, cpg, rows_per_block;
+};
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const GnStatArgs a) {
+  __shared__ float4 red1[256], red2[256];
+  const int tpr = a.C >> 2;                 // threads per row (C/4 <= 256)
+  const int rpp = 256 / tpr;                // rows per pass
+  const int rin = threadIdx.x / tpr, cv = threadIdx.x - rin * tpr;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * a.rows_per_block, r1 = min(r0 + a.rows_per_block, a.V);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+  float mean[4] = {0, 0, 0, 0}, rstd[4] = {1, 1, 1, 1};
+  float4 wv = make_float4(1, 1, 1, 1), bv = make_float4(0, 0, 0, 0);
+  if (MODE == 1 && rin < rpp) {
+    const int G = a.C / a.cpg;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int g = (4 * cv + e) / a.cpg;
+      mean[e] = a.mean[b * G + g];
+      rstd[e] = a.rstd[b * G + g];
+    }
+    wv = *reinterpret_cast<const float4*>(a.w + 4 * cv);
+    bv = *reinterpret_cast<const float4*>(a.b + 4 * cv);
+  }
+  if (rin < rpp) {
+    for (int r = r0 + rin; r < r1; r += rpp) {
+      const long long off = ((long long)b * a.V + r) * a.C + 4 * cv;
+      const float4 x = __ldg(reinterpret_cast<const float4*>(a.x + off));
+      if (MODE == 0) {
+        s1.x += x.x; s1.y += x.y; s1.z += x.z; s1.w += x.w;
+        s2.x += x.x * x.x; s2.y += x.y * x.y; s2.z += x.z * x.z; s2.w += x.w * x.w;
+      } else {
+        const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy + off));
+        const float xh[4] = {(x.x - mean[0]) * rstd[0], (x.y - mean[1]) * rstd[1], (x.z - mean[2]) * rstd[2], (x.w - mean[3]) * rstd[3]};
+        const float d0 = dy.x * silu_grad(xh[0] * wv.x + bv.x), d1 = dy.y * silu_grad(xh[1] * wv.y + bv.y);
+        const float d2 = dy.z * silu_grad(xh[2] * wv.z + bv.z), d3 = dy.w * silu_grad(xh[3] * wv.w + bv.w);
+        s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
+        s2.x += d0 * xh[0]; s2.y += d1 * xh[1]; s2.z += d2 * xh[2]; s2.w += d3 * xh[3];
+      }
+    }
+  }
+  red1[threadIdx.x] = s1;
+  red2[threadIdx.x] = s2;
+  __syncthreads();
+  if (rin == 0) {
+    for (int k = 1; k < rpp; ++k) {
+      const float4 u = red1[k * tpr + cv], v = red2[k * tpr + cv];
+      s1.x += u.x; s1.y += u.y; s1.z += u.z; s1.w += u.w;
+      s2.x += v.x; s2.y += v.y; s2.z += v.z; s2.w += v.w;
+    }
+    float* d1 = a.S1 + (long long)b * a.C + 4 * cv;
+    float* d2 = a.S2 + (long long)b * a.C + 4 * cv;
+    atomicAdd(d1, s1.x); atomicAdd(d1 + 1, s1.y); atomicAdd(d1 + 2, s1.z); atomicAdd(d1 + 3, s1.w);
+    atomicAdd(d2, s2.x); atomicAdd(d2 + 1, s2.y); atomicAdd(d2 + 2, s2.z); atomicAdd(d2 + 3, s2.w);
+  }
+}
+// forward: channel sums -> group mean / rstd
+__global__ void gn_fwd_finalize_kernel(const float* S1, const float* S2, float* mean, float* rstd, int B, int C, int cpg, int V) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = C / cpg;
+  if (idx >= B * G) return;
+  const int b = idx / G, g = idx - b * G;
+  double s = 0.0, q = 0.0;
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) { s += S1[b * C + c]; q += S2[b * C + c]; }
+  const double n = (double)V * cpg;
+  const double m = s / n;
+  double var = q / n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[idx] = (float)m;
+  rstd[idx] = (float)(1.0 / sqrt(var + 1e-5));
+}
+// backward: dw[c] = sum_b T2, db[c] = sum_b T1, A[b,g] = sum_{c in g} w_c T1 / n, Bq[b,g] = sum_{c in g} w_c T2 / n
+__global__ void gn_bwd_finalize_kernel(const float* T1, const float* T2, const float* w, float* dw, float* db, float* A, float* Bq,
+                                       int B, int C, int cpg, int V) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = C / cpg;
+  if (idx < C) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int b = 0; b < B; ++b) { t1 += T1[b * C + idx]; t2 += T2[b * C + idx]; }
+    dw[idx] = t2;
+    db[idx] = t1;
+  }
+  if (idx < B * G) {
+    const int b = idx / G, g = idx - b * G;
+    double a1 = 0.0, a2 = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a1 += (double)w[c] * T1[b * C + c]; a2 += (double)w[c] * T2[b * C + c]; }
+    const double n = (double)V * cpg;
+    A[idx] = (float)(a1 / n);
+    Bq[idx] = (float)(a2 / n);
+  }
+}
+// forward apply: y = silu(xhat*w + b) (bf16 channels-last).  backward apply: dx = rstd*(ds*w - A - xhat*Bq)
+template <int MODE>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
+                                                       const float* __restrict__ A, const float* __restrict__ Bq, bf16* __restrict__ y,
+                                                       float* __restrict__ dx, int B, int V, int C, int cpg) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*V*C/4
+  const int tpr = C >> 2;
+  const long long total = (long long)B * V * tpr;
+  if (idx >= total) return;
+  const int cv = (int)(idx % tpr);
+  const long long row = idx / tpr;
+  const int bb = (int)(row / V);
+  const int G = C / cpg;
+  const long long off = row * C + 4 * cv;
+  const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
+  const float4 wv = *reinterpret_cast<const float4*>(w + 4 * cv), bv = *reinterpret_cast<const float4*>(b + 4 * cv);
+  const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w}, bs[4] = {bv.x, bv.y, bv.z, bv.w};
+  float out[4];
+  float dys[4] = {0, 0, 0, 0};
+  if (MODE == 1) {
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + off));
+    dys[0] = d.x; dys[1] = d.y; dys[2] = d.z; dys[3] = d.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int g = (4 * cv + e) / cpg;
+    const float mu = mean[bb * G + g], rs = rstd[bb * G + g];
+    const float xh = (xs[e] - mu) * rs;
+    const float z = xh * ws[e] + bs[e];
+    if (MODE == 0) {
+      out[e] = z / (1.f + __expf(-z));
+    } else {
+      const float ds = dys[e] * silu_grad(z);
+      out[e] = rs * (ds * ws[e] - A[bb * G + g] - xh * Bq[bb * G + g]);
+    }
+  }
+  if (MODE == 0) {
+    *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_bf16(out[0], out[1]), pack_bf16(out[2], out[3]));
+  } else {
+    *reinterpret_cast<float4*>(dx + off) = make_float4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+static int fill_geom(Conv3dGeom* g, const hvc_conv3d_geom* a) {
+  HVC_CHECK_ARG(a->B > 0 && a->Cin > 0 && a->D > 0 && a->H > 0 && a->W > 0, "conv3d: empty input");
+  HVC_CHECK_ARG(a->stride == 1 || a->stride == 2, "conv3d: stride %d not supported", a->stride);
+  g->B = a->B; g->Cin = a->Cin; g->D = a->D; g->H = a->H; g->W = a->W; g->stride = a->stride;
+  g->Do = (a->D - 1) / a->stride + 1; g->Ho = (a->H - 1) / a->stride + 1; g->Wo = (a->W - 1) / a->stride + 1;
+  g->sb = a->sb; g->sc = a->sc; g->sd = a->sd; g->sh = a->sh; g->sw = a->sw;
+  g->K = a->Cin * 27; g->Kp = (g->K + 7) / 8 * 8;
+  return HVC_OK;
+}
+
+}  // namespace hvc
+
+using namespace hvc;
+
+extern "C" int hvc_im2col3d(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream) {
+  HVC_CHECK_ARG(x && geom && cols, "hvc_im2col3d: null operand");
+  Conv3dGeom g;
+  int rc = fill_geom(&g, geom);
+  if (rc) return rc;
+  const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * g.Kp;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x_is_bf16) im2col3d_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(cols), g);
+  else im2col3d_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(cols), g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream) {
+  HVC_CHECK_ARG(dcols && geom && dx, "hvc_col2im3d: null operand");
+  Conv3dGeom g;
+  int rc = fill_geom(&g, geom);
+  if (rc) return rc;
+  const long long total = (long long)g.B * g.Cin * g.D * g.H * g.W;
+  col2im3d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(dcols), dx, g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+static int gn_rows_per_block(int B, int V) {
+  int rpb = 1024;
+  while (rpb > 32 && (long long)B * ((V + rpb - 1) / rpb) < 4LL * device_sm_count()) rpb >>= 1;
+  return rpb;
+}
+
+extern "C" int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
+                                      void* y, float* mean, float* rstd, float* scratch, void* stream) {
+  HVC_CHECK_ARG(x && w && b && y && mean && rstd && scratch, "hvc_groupnorm_silu_fwd: null operand");
+  HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_groupnorm_silu_fwd: bad shape C=%d G=%d", C, groups);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HVC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * C, st));
+  GnStatArgs a;
+  a.x = x; a.dy = nullptr; a.mean = nullptr; a.rstd = nullptr; a.w = w; a.b = b; a.S1 = scratch; a.S2 = scratch + (long long)B * C;
+  a.V = V; a.C = C; a.cpg = C / groups; a.rows_per_block = gn_rows_per_block(B, V);
+  gn_stats_kernel<0><<<dim3((V + a.rows_per_block - 1) / a.rows_per_block, B), 256, 0, st>>>(a);
+  HVC_LAUNCH_CHECK();
+  gn_fwd_finalize_kernel<<<(B * groups + 127) / 128, 128, 0, st>>>(a.S1, a.S2, mean, rstd, B, C, a.cpg, V);
+  HVC_LAUNCH_CHECK();
+  const long long total = (long long)B * V * (C / 4);
+  gn_apply_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, nullptr, mean, rstd, w, b, nullptr, nullptr, reinterpret_cast<bf16*>(y),
+                                                                      nullptr, B, V, C, a.cpg);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_groupnorm_silu_bwd(const float* dy, const float* x, const float* w, const float* b, const float* mean, const float* rstd,
+                                      int32_t B, int32_t V, int32_t C, int32_t groups, float* dx, float* dw, float* db, float* scratch,
+                                      void* stream) {
+  HVC_CHECK_ARG(dy && x && w && b && mean && rstd && dx && dw && db && scratch, "hvc_groupnorm_silu_bwd: null operand");
+  HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_groupnorm_silu_bwd: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // scratch: T1 [B,C], T2 [B,C], A [B,G], Bq [B,G]
+  HVC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * C, st));
+  float* T1 = scratch; float* T2 = scratch + (long long)B * C; float* A = T2 + (long long)B * C; float* Bq = A + (long long)B * groups;
+  GnStatArgs a;
+  a.x = x; a.dy = dy; a.mean = mean; a.rstd = rstd; a.w = w; a.b = b; a.S1 = T1; a.S2 = T2;
+  a.V = V; a.C = C; a.cpg = C / groups; a.rows_per_block = gn_rows_per_block(B, V);
+  gn_stats_kernel<1><<<dim3((V + a.rows_per_block - 1) / a.rows_per_block, B), 256, 0, st>>>(a);
+  HVC_LAUNCH_CHECK();
+  const int n = C > B * groups ? C : B * groups;
+  gn_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(T1, T2, w, dw, db, A, Bq, B, C, a.cpg, V);
+  HVC_LAUNCH_CHECK();
+  const long long total = (long long)B * V * (C / 4);
+  gn_apply_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, B, V, C, a.cpg);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}

@@ -195,6 +195,44 @@ int hvc_adaln_fwd(const float* cond, int64_t ldc, const float* W, const float* b
 int hvc_adaln_bwd(const float* dparams, const float* cond, int64_t ldc, const float* W, float* dW, float* dbias,
                   float* dcond, int32_t B, int32_t K, int32_t J, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Voxel embedding (hybrid_vit_backbone.py:195-210,252): Conv3d(k=3, pad=1, stride 1|2) as
+ * im2col + hvc_gemm, GroupNorm(groups)+SiLU, on channels-last activations [B, voxels, C].
+ * hvc_conv3d_geom describes the conv INPUT: sizes and element strides (any layout: NCDHW for the
+ * module input, channels-last for intermediates).  Patch matrix: bf16 [B*Do*Ho*Wo, Kp], column
+ * k = cin*27 + kd*9 + kh*3 + kw (the order of weight.view(Cout, Cin*27)), Kp = K rounded up to 8.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hvc_conv3d_geom {
+  int32_t B, Cin, D, H, W, stride;
+  int64_t sb, sc, sd, sh, sw;
+} hvc_conv3d_geom;
+int hvc_im2col3d(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream);
+/* dx (f32, layout given by geom strides) = adjoint of im2col applied to dcols (bf16 [M, Kp]). */
+int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream);
+/* y bf16 [B,V,C] = SiLU(GroupNorm(x f32 [B,V,C])); mean/rstd f32 [B,groups] saved; scratch f32 [2*B*C]. */
+int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C,
+                           int32_t groups, void* y, float* mean, float* rstd, float* scratch, void* stream);
+/* dx f32 [B,V,C], dw/db f32 [C]; scratch f32 [2*B*C + 2*B*groups]. */
+int hvc_groupnorm_silu_bwd(const float* dy, const float* x, const float* w, const float* b, const float* mean,
+                           const float* rstd, int32_t B, int32_t V, int32_t C, int32_t groups, float* dx,
+                           float* dw, float* db, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ends of HybridViT3D.forward (hybrid_vit_backbone.py:258,265-272).
+ * ---------------------------------------------------------------------------------------------- */
+/* out[b,:] = x[b mod x_batch,:] + pos[:]  (n = N*C f32 elements per sample). */
+int hvc_add_pos(const float* x, int32_t x_batch, const float* pos, float* out, int32_t B, int64_t n, void* stream);
+/* out[:] = sum_b x[b,:]  (gradient of pos_embed / of a batch-expanded input). */
+int hvc_batch_sum(const float* x, float* out, int32_t B, int64_t n, void* stream);
+/* v[t] = output_proj(LayerNorm(x[t]))  (C -> 1), mean/rstd saved; backward is hvc_ln_bwd with dz_row. */
+int hvc_head_fwd(const float* x, int64_t ldx, const float* w, const float* b, const float* wo, const float* bo,
+                 float* v, float* mean, float* rstd, int32_t T, int32_t C, void* stream);
+/* F.interpolate(mode="trilinear", align_corners=True) on [B, Di,Hi,Wi] -> [B, Do,Ho,Wo], and its adjoint. */
+int hvc_upsample3d_fwd(const float* v, float* out, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do,
+                       int32_t Ho, int32_t Wo, void* stream);
+int hvc_upsample3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do,
+                       int32_t Ho, int32_t Wo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
