@@ -1,0 +1,15 @@
+"""hybrid_vit_cascade_b200 -- B200-native (sm_100a) drop-in for the 3D ViT backbone hot path of
+kanadm12/Hybrid-ViT-Cascade (models/vit_components.py, models/hybrid_vit_backbone.py).
+
+    from hybrid_vit_cascade_b200 import HybridViT3D            # same ctor / forward / state_dict
+
+Host code is PyTorch (memory, streams, autograd glue); every computation on the path is a kernel of
+``libhvc_sm100a.so`` (C ABI: include/hvc.h).  There is no CPU or eager fallback: without the built
+library or off sm_100 the modules raise.
+"""
+from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHeadSelfAttention,  # noqa: F401
+                             SinusoidalTimeEmbedding, set_dropout_policy)
+from .hybrid_vit_backbone import HybridViT3D, HybridViTBlock3D  # noqa: F401
+
+__all__ = ["AdaLNModulation", "MultiHeadCrossAttention", "MultiHeadSelfAttention", "SinusoidalTimeEmbedding",
+           "HybridViTBlock3D", "HybridViT3D", "set_dropout_policy"]

@@ -96,6 +96,13 @@ class ResidBwdArgs(C.Structure):
     ]
 
 
+class Conv3dGeom(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("Cin", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("stride", C.c_int32),
+        ("sb", C.c_int64), ("sc", C.c_int64), ("sd", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64),
+    ]
+
+
 def lib():
     """Load the shared library once; raise loudly if it is not there."""
     global _lib
@@ -122,6 +129,8 @@ EXPORTS = [
     "hvc_gemm", "hvc_attn_fwd", "hvc_attn_bwd",
     "hvc_ln_fwd", "hvc_ln_bwd", "hvc_resid_bwd", "hvc_colsum_bf16", "hvc_cast_bf16", "hvc_cast_tokens",
     "hvc_adaln_fwd", "hvc_adaln_bwd",
+    "hvc_im2col3d", "hvc_col2im3d", "hvc_groupnorm_silu_fwd", "hvc_groupnorm_silu_bwd",
+    "hvc_add_pos", "hvc_batch_sum", "hvc_head_fwd", "hvc_upsample3d_fwd", "hvc_upsample3d_bwd",
 ]
 
 

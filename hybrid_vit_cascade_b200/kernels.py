@@ -279,3 +279,110 @@ def adaln_bwd(dparams, cond, W, need_w=True, need_cond=True):
     _lib.check(_lib.lib().hvc_adaln_bwd(_ptr(dparams), _ptr(cond), C.c_int64(cond.stride(0)), _ptr(W), _ptr(dW), _ptr(db),
                                         _ptr(dcond), B, K, J, _stream()), "hvc_adaln_bwd")
     return dW, db, dcond
+
+
+# ------------------------------------------------------------------ embed (conv3d / groupnorm) and head
+
+def _geom(B, Cin, D, H, W, stride, strides):
+    g = _lib.Conv3dGeom()
+    g.B, g.Cin, g.D, g.H, g.W, g.stride = B, Cin, D, H, W, stride
+    g.sb, g.sc, g.sd, g.sh, g.sw = strides
+    return g
+
+
+def conv_out(n, stride):
+    return (n - 1) // stride + 1
+
+
+def im2col3d(x, B, Cin, D, H, W, stride, strides):
+    """x: f32|bf16 tensor holding the conv input with element strides (sb, sc, sd, sh, sw).
+    Returns bf16 [B*Do*Ho*Wo, Kp]."""
+    _need_cuda(x)
+    Do, Ho, Wo = conv_out(D, stride), conv_out(H, stride), conv_out(W, stride)
+    Kp = (Cin * 27 + 7) // 8 * 8
+    cols = torch.empty(B * Do * Ho * Wo, Kp, device=x.device, dtype=torch.bfloat16)
+    g = _geom(B, Cin, D, H, W, stride, strides)
+    _lib.check(_lib.lib().hvc_im2col3d(_ptr(x), int(x.dtype == torch.bfloat16), C.byref(g), _ptr(cols), _stream()),
+               "hvc_im2col3d")
+    return cols
+
+
+def col2im3d(dcols, B, Cin, D, H, W, stride, out, strides):
+    """Adjoint of im2col3d into `out` (f32, pre-allocated, every element written)."""
+    _need_cuda(dcols, out)
+    assert dcols.dtype == torch.bfloat16 and dcols.is_contiguous() and out.dtype == torch.float32
+    g = _geom(B, Cin, D, H, W, stride, strides)
+    _lib.check(_lib.lib().hvc_col2im3d(_ptr(dcols), C.byref(g), _ptr(out), _stream()), "hvc_col2im3d")
+    return out
+
+
+def groupnorm_silu_fwd(x, w, b, B, V, Cc, groups):
+    """x f32 [B*V, C] channels-last -> (y bf16 [B*V, C], mean [B,G], rstd [B,G])."""
+    _need_cuda(x, w, b)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    y = torch.empty(B * V, Cc, device=x.device, dtype=torch.bfloat16)
+    mean = torch.empty(B, groups, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(B, groups, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_groupnorm_silu_fwd(_ptr(x), _ptr(w), _ptr(b), B, V, Cc, groups, _ptr(y), _ptr(mean), _ptr(rstd),
+                                                 _ptr(scratch), _stream()), "hvc_groupnorm_silu_fwd")
+    return y, mean, rstd
+
+
+def groupnorm_silu_bwd(dy, x, w, b, mean, rstd, B, V, Cc, groups):
+    _need_cuda(dy, x)
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    dx = torch.empty(B * V, Cc, device=x.device, dtype=torch.float32)
+    dw = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc + 2 * B * groups, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_groupnorm_silu_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(b), _ptr(mean), _ptr(rstd), B, V, Cc, groups,
+                                                 _ptr(dx), _ptr(dw), _ptr(db), _ptr(scratch), _stream()), "hvc_groupnorm_silu_bwd")
+    return dx, dw, db
+
+
+def add_pos(x, pos, B):
+    """x f32 [xB, n] (xB divides into B by broadcast), pos f32 [n] -> out f32 [B, n]."""
+    _need_cuda(x, pos)
+    assert x.dtype == pos.dtype == torch.float32 and x.is_contiguous() and pos.is_contiguous()
+    xB, n = x.shape
+    out = torch.empty(B, n, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_add_pos(_ptr(x), xB, _ptr(pos), _ptr(out), B, C.c_int64(n), _stream()), "hvc_add_pos")
+    return out
+
+
+def batch_sum(x):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    B, n = x.shape
+    out = torch.empty(n, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_batch_sum(_ptr(x), _ptr(out), B, C.c_int64(n), _stream()), "hvc_batch_sum")
+    return out
+
+
+def head_fwd(x, w, b, wo, bo):
+    """x f32 [T,C] -> (v f32 [T], mean, rstd)."""
+    _need_cuda(x)
+    T, Cc = x.shape
+    v = torch.empty(T, device=x.device, dtype=torch.float32)
+    mean = torch.empty(T, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(T, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_head_fwd(_ptr(x), C.c_int64(_row_major_2d(x, "x")), _ptr(w), _ptr(b), _ptr(wo), _ptr(bo), _ptr(v),
+                                       _ptr(mean), _ptr(rstd), T, Cc, _stream()), "hvc_head_fwd")
+    return v, mean, rstd
+
+
+def upsample3d_fwd(v, B, grid, size):
+    _need_cuda(v)
+    assert v.dtype == torch.float32 and v.is_contiguous()
+    out = torch.empty(B, 1, *size, device=v.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_upsample3d_fwd(_ptr(v), _ptr(out), B, *grid, *size, _stream()), "hvc_upsample3d_fwd")
+    return out
+
+
+def upsample3d_bwd(dout, B, grid, size):
+    _need_cuda(dout)
+    assert dout.dtype == torch.float32 and dout.is_contiguous()
+    dv = torch.empty(B * grid[0] * grid[1] * grid[2], device=dout.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_upsample3d_bwd(_ptr(dout), _ptr(dv), B, *grid, *size, _stream()), "hvc_upsample3d_bwd")
+    return dv

@@ -1,0 +1,434 @@
+"""Autograd Functions of the hot path: each forward/backward is a fixed sequence of libhvc_sm100a kernels.
+
+Precision policy (matches what ``torch.autocast(bf16)`` does to the reference modules, but keeps more
+in fp32): parameters and the residual stream stay fp32; GEMM / attention operands are bf16 with fp32
+accumulation; LayerNorm / GroupNorm statistics, softmax statistics, gates and residual adds are fp32.
+
+Gradient layouts are what ``nn.Linear`` expects ((out, in) weights) so optimizers, clipping and
+checkpoints are untouched.  Nothing here falls back to torch math: torch only allocates.
+"""
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+
+_SM_COUNT = {}
+
+
+def _sms(dev):
+    i = dev.index if dev.index is not None else torch.cuda.current_device()
+    if i not in _SM_COUNT:
+        _SM_COUNT[i] = torch.cuda.get_device_properties(i).multi_processor_count
+    return _SM_COUNT[i]
+
+
+# ------------------------------------------------------------------ bf16 weight cache
+_W16 = {}
+
+
+def w16(p, pad_to=None):
+    """bf16 copy of an fp32 parameter viewed [out, in] (zero-padded along `in` to pad_to), cached until
+    the parameter is modified in place (optimizer step) or replaced (load_state_dict)."""
+    key = (id(p), pad_to)
+    ver = p._version
+    ent = _W16.get(key)
+    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr() and ent[3] == tuple(p.shape):
+        return ent[2]
+    src = p.detach()
+    if src.dtype != torch.float32:
+        src = src.float()
+    src = src.reshape(src.shape[0], -1).contiguous()
+    if pad_to is not None and pad_to != src.shape[1]:
+        padded = torch.zeros(src.shape[0], pad_to, device=src.device, dtype=torch.float32)
+        padded[:, :src.shape[1]] = src
+        src = padded
+    t = K.cast_bf16(src)
+    _W16[key] = (ver, p.data_ptr(), t, tuple(p.shape))
+    return t
+
+
+def clear_weight_cache():
+    _W16.clear()
+
+
+# ------------------------------------------------------------------ GEMM helpers (no autograd)
+
+def _wgrad(dy16, x16):
+    """dW[N,K] = dy[T,N]^T x[T,K], fp32, split over T."""
+    T, N = dy16.shape
+    Kd = x16.shape[1]
+    tiles = ((N + 127) // 128) * ((Kd + 127) // 128)
+    kb = (T + 63) // 64
+    splits = max(1, min(kb, (4 * _sms(dy16.device)) // max(tiles, 1)))
+    return K.gemm(dy16, x16, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=splits)
+
+
+def _dgrad(dy16, w_16, f32_out=False, **kw):
+    """dx[T,K] = dy[T,N] W[N,K] (W as stored)."""
+    if f32_out:
+        return K.gemm(dy16, w_16, b_major=1, epilogue=K.EPI_F32)
+    return K.gemm(dy16, w_16, b_major=1, **kw)
+
+
+def _mod_views(mod, off, C):
+    return mod[:, off:off + C], mod[:, off + C:off + 2 * C], mod[:, off + 2 * C:off + 3 * C]
+
+
+# ------------------------------------------------------------------ casts
+
+class CastTokens(Function):
+    """(B, M, C) f32|bf16 with any strides -> bf16 [B*M, C]; backward returns the f32/bf16 gradient as (B, M, C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        ctx.in_dtype = x.dtype
+        return K.cast_tokens(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, M, C = ctx.shape
+        return g.to(ctx.in_dtype).view(B, M, C)
+
+
+# ------------------------------------------------------------------ AdaLN modulation linear (a3)
+
+class AdaLN(Function):
+    """params[B, 6C] = cond W^T + b  (vit_components.py:144), fp32."""
+
+    @staticmethod
+    def forward(ctx, cond, weight, bias):
+        cond = cond.float().contiguous()
+        ctx.save_for_backward(cond, weight)
+        return K.adaln_fwd(cond, weight.contiguous(), bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        cond, weight = ctx.saved_tensors
+        need_w = ctx.needs_input_grad[1]
+        dW, db, dcond = K.adaln_bwd(g.contiguous(), cond, weight.contiguous(), need_w=need_w,
+                                    need_cond=ctx.needs_input_grad[0])
+        return dcond, dW, db
+
+
+# ------------------------------------------------------------------ self-attention sub-block (a1 inside a5)
+
+class SelfAttnBranch(Function):
+    """x + gate_sa * proj(attn(qkv((1+scale_sa) * LN1(x) + shift_sa)))   hybrid_vit_backbone.py:120-123."""
+
+    @staticmethod
+    def forward(ctx, x, mod, ln_w, ln_b, w_qkv, w_proj, b_proj, B, N, H, off):
+        T, C = x.shape
+        d = C // H
+        shift, scale, gate = _mod_views(mod, off, C)
+        y, mean, rstd = K.ln_fwd(x, ln_w, ln_b, shift, scale, mod.stride(0), N)
+        qkv = K.gemm(y, w16(w_qkv))
+        o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, d, d ** -0.5)
+        branch = torch.empty(T, C, device=x.device, dtype=torch.bfloat16)
+        out = K.gemm(o, w16(w_proj), epilogue=K.EPI_RESIDUAL, bias=b_proj, resid=x, gate=gate, gate_ld=mod.stride(0),
+                     rows_per_batch=N, out2=branch)
+        ctx.save_for_backward(x, mod, ln_w, ln_b, w_qkv, w_proj, mean, rstd, y, qkv, o, lse, branch)
+        ctx.dims = (B, N, H, off)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mod, ln_w, ln_b, w_qkv, w_proj, mean, rstd, y, qkv, o, lse, branch = ctx.saved_tensors
+        B, N, H, off = ctx.dims
+        T, C = x.shape
+        d = C // H
+        dout = dout.contiguous()
+        shift, scale, gate = _mod_views(mod, off, C)
+        dbranch, dgate, db_proj = K.resid_bwd(dout, B, N, branch=branch, gate=gate, gate_ld=mod.stride(0))
+        dw_proj = _wgrad(dbranch, o)
+        d_o = _dgrad(dbranch, w16(w_proj))
+        dqkv = torch.empty(T, 3 * C, device=x.device, dtype=torch.bfloat16)
+        K.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, d_o, B, H, N, N, d, d ** -0.5,
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:])
+        dw_qkv = _wgrad(dqkv, y)
+        dy = _dgrad(dqkv, w16(w_qkv))
+        r = K.ln_bwd(dy, x, mean, rstd, ln_w, ln_b, B, N, scale=scale, mod_ld=mod.stride(0), dx_in=dout, want_mod=True)
+        dmod = torch.zeros_like(mod)
+        dmod[:, off:off + C] = r["dmod"][:, 0]
+        dmod[:, off + C:off + 2 * C] = r["dmod"][:, 1]
+        dmod[:, off + 2 * C:off + 3 * C] = dgate
+        return r["dx"], dmod, r["dw"], r["db"], dw_qkv, dw_proj, db_proj, None, None, None, None
+
+
+# ------------------------------------------------------------------ cross-attention sub-block (a2 inside a5)
+
+class CrossAttnBranch(Function):
+    """x + proj(attn(q(LN2(x)), kv(context)))   hybrid_vit_backbone.py:126-128."""
+
+    @staticmethod
+    def forward(ctx, x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, b_proj, B, N, M, H):
+        T, C = x.shape
+        d = C // H
+        y, mean, rstd = K.ln_fwd(x, ln_w, ln_b)
+        q = K.gemm(y, w16(w_q))
+        kv = K.gemm(ctx16, w16(w_kv))
+        o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5)
+        out = K.gemm(o, w16(w_proj), epilogue=K.EPI_RESIDUAL, bias=b_proj, resid=x)
+        ctx.save_for_backward(x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, mean, rstd, y, q, kv, o, lse)
+        ctx.dims = (B, N, M, H)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, mean, rstd, y, q, kv, o, lse = ctx.saved_tensors
+        B, N, M, H = ctx.dims
+        T, C = x.shape
+        d = C // H
+        dout = dout.contiguous()
+        dbranch, _, db_proj = K.resid_bwd(dout, B, N)
+        dw_proj = _wgrad(dbranch, o)
+        d_o = _dgrad(dbranch, w16(w_proj))
+        dq = torch.empty(T, C, device=x.device, dtype=torch.bfloat16)
+        dkv = torch.empty(B * M, 2 * C, device=x.device, dtype=torch.bfloat16)
+        K.attn_bwd(q, kv[:, :C], kv[:, C:], o, lse, d_o, B, H, N, M, d, d ** -0.5, dq, dkv[:, :C], dkv[:, C:])
+        dw_q = _wgrad(dq, y)
+        dy = _dgrad(dq, w16(w_q))
+        dw_kv = _wgrad(dkv, ctx16)
+        dctx = _dgrad(dkv, w16(w_kv), f32_out=True) if ctx.needs_input_grad[1] else None
+        r = K.ln_bwd(dy, x, mean, rstd, ln_w, ln_b, B, N, dx_in=dout)
+        return r["dx"], dctx, r["dw"], r["db"], dw_q, dw_kv, dw_proj, db_proj, None, None, None, None
+
+
+# ------------------------------------------------------------------ MLP sub-block (inside a5)
+
+class MlpBranch(Function):
+    """x + gate_mlp * W2 gelu(W1 ((1+scale_mlp) * LN3(x) + shift_mlp) + b1) + b2   hybrid_vit_backbone.py:136-139."""
+
+    @staticmethod
+    def forward(ctx, x, mod, ln_w, ln_b, w1, b1, w2, b2, B, N, off):
+        T, C = x.shape
+        shift, scale, gate = _mod_views(mod, off, C)
+        y, mean, rstd = K.ln_fwd(x, ln_w, ln_b, shift, scale, mod.stride(0), N)
+        h = torch.empty(T, w1.shape[0], device=x.device, dtype=torch.bfloat16)
+        g = K.gemm(y, w16(w1), bias=b1, activation=K.ACT_GELU, out2=h)
+        branch = torch.empty(T, C, device=x.device, dtype=torch.bfloat16)
+        out = K.gemm(g, w16(w2), epilogue=K.EPI_RESIDUAL, bias=b2, resid=x, gate=gate, gate_ld=mod.stride(0),
+                     rows_per_batch=N, out2=branch)
+        ctx.save_for_backward(x, mod, ln_w, ln_b, w1, w2, mean, rstd, y, h, g, branch)
+        ctx.dims = (B, N, off)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mod, ln_w, ln_b, w1, w2, mean, rstd, y, h, g, branch = ctx.saved_tensors
+        B, N, off = ctx.dims
+        T, C = x.shape
+        dout = dout.contiguous()
+        shift, scale, gate = _mod_views(mod, off, C)
+        dbranch, dgate, db2 = K.resid_bwd(dout, B, N, branch=branch, gate=gate, gate_ld=mod.stride(0))
+        dw2 = _wgrad(dbranch, g)
+        dh = _dgrad(dbranch, w16(w2), activation=K.ACT_GELU_GRAD, aux=h)
+        db1 = K.colsum_bf16(dh)
+        dw1 = _wgrad(dh, y)
+        dy = _dgrad(dh, w16(w1))
+        r = K.ln_bwd(dy, x, mean, rstd, ln_w, ln_b, B, N, scale=scale, mod_ld=mod.stride(0), dx_in=dout, want_mod=True)
+        dmod = torch.zeros_like(mod)
+        dmod[:, off:off + C] = r["dmod"][:, 0]
+        dmod[:, off + C:off + 2 * C] = r["dmod"][:, 1]
+        dmod[:, off + 2 * C:off + 3 * C] = dgate
+        return r["dx"], dmod, r["dw"], r["db"], dw1, db1, dw2, db2, None, None, None
+
+
+# ------------------------------------------------------------------ standalone attention modules (a1, a2)
+
+class SelfAttention(Function):
+    """proj(attn(qkv(x)))  -- MultiHeadSelfAttention.forward, vit_components.py:31-57 (dropout off)."""
+
+    @staticmethod
+    def forward(ctx, x, w_qkv, w_proj, b_proj, H):
+        B, N, C = x.shape
+        d = C // H
+        x16 = K.cast_tokens(x)
+        qkv = K.gemm(x16, w16(w_qkv))
+        o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, d, d ** -0.5)
+        f32 = x.dtype == torch.float32
+        out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16)
+        ctx.save_for_backward(x16, w_qkv, w_proj, qkv, o, lse)
+        ctx.dims = (B, N, C, H, x.dtype)
+        return out.view(B, N, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x16, w_qkv, w_proj, qkv, o, lse = ctx.saved_tensors
+        B, N, C, H, dt = ctx.dims
+        d = C // H
+        dy16 = K.cast_tokens(dout)
+        db_proj = K.colsum_bf16(dy16)
+        dw_proj = _wgrad(dy16, o)
+        d_o = _dgrad(dy16, w16(w_proj))
+        dqkv = torch.empty(B * N, 3 * C, device=dout.device, dtype=torch.bfloat16)
+        K.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, d_o, B, H, N, N, d, d ** -0.5,
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:])
+        dw_qkv = _wgrad(dqkv, x16)
+        dx = _dgrad(dqkv, w16(w_qkv), f32_out=(dt == torch.float32)).view(B, N, C)
+        return dx, dw_qkv, dw_proj, db_proj, None
+
+
+class CrossAttention(Function):
+    """proj(attn(q(x), kv(context)))  -- MultiHeadCrossAttention.forward, vit_components.py:83-119 (dropout off)."""
+
+    @staticmethod
+    def forward(ctx, x, context, w_q, w_kv, w_proj, b_proj, H):
+        B, N, C = x.shape
+        M, Cc = context.shape[1], context.shape[2]
+        d = C // H
+        x16 = K.cast_tokens(x)
+        c16 = K.cast_tokens(context)
+        q = K.gemm(x16, w16(w_q))
+        kv = K.gemm(c16, w16(w_kv))
+        o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5)
+        f32 = x.dtype == torch.float32
+        out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16)
+        ctx.save_for_backward(x16, c16, w_q, w_kv, w_proj, q, kv, o, lse)
+        ctx.dims = (B, N, M, C, Cc, H, x.dtype, context.dtype)
+        return out.view(B, N, C)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x16, c16, w_q, w_kv, w_proj, q, kv, o, lse = ctx.saved_tensors
+        B, N, M, C, Cc, H, dt, cdt = ctx.dims
+        d = C // H
+        dy16 = K.cast_tokens(dout)
+        db_proj = K.colsum_bf16(dy16)
+        dw_proj = _wgrad(dy16, o)
+        d_o = _dgrad(dy16, w16(w_proj))
+        dq = torch.empty(B * N, C, device=dout.device, dtype=torch.bfloat16)
+        dkv = torch.empty(B * M, 2 * C, device=dout.device, dtype=torch.bfloat16)
+        K.attn_bwd(q, kv[:, :C], kv[:, C:], o, lse, d_o, B, H, N, M, d, d ** -0.5, dq, dkv[:, :C], dkv[:, C:])
+        dw_q = _wgrad(dq, x16)
+        dw_kv = _wgrad(dkv, c16)
+        dx = _dgrad(dq, w16(w_q), f32_out=(dt == torch.float32)).view(B, N, C)
+        dctx = None
+        if ctx.needs_input_grad[1]:
+            dctx = _dgrad(dkv, w16(w_kv), f32_out=(cdt == torch.float32)).view(B, M, Cc)
+        return dx, dctx, dw_q, dw_kv, dw_proj, db_proj, None
+
+
+# ------------------------------------------------------------------ voxel embedding + positional encoding (a7 head of forward)
+
+class VoxelEmbed(Function):
+    """tokens[B*N, C] = flatten(voxel_embed(x)) + pos_embed   hybrid_vit_backbone.py:252-258.
+
+    plan: list of (cin, cout, stride, groups|0); params: for each conv (weight, bias[, gn_weight, gn_bias]).
+    A batch-expanded input (stride(0) == 0, model_direct.py:75) is embedded once and broadcast.
+    """
+
+    @staticmethod
+    def forward(ctx, x, pos_embed, plan, *params):
+        B, Cin, D, H, W = x.shape
+        xB = 1 if (B > 1 and x.stride(0) == 0) else B
+        xin = x[:xB]
+        if xin.dtype not in (torch.float32, torch.bfloat16):
+            xin = xin.float()
+        saved, geoms = [], []
+        a, strides, dims = xin, tuple(xin.stride()), (Cin, D, H, W)
+        z = None
+        pi = 0
+        for (cin, cout, stride, groups) in plan:
+            _, Dc, Hc, Wc = dims
+            weight, bias = params[pi], params[pi + 1]
+            cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides)
+            Do, Ho, Wo = K.conv_out(Dc, stride), K.conv_out(Hc, stride), K.conv_out(Wc, stride)
+            z = K.gemm(cols, w16(weight, pad_to=cols.shape[1]), bias=bias, epilogue=K.EPI_F32)   # [xB*V, cout] channels-last
+            V = Do * Ho * Wo
+            geoms.append((cin, Dc, Hc, Wc, stride, strides, V))
+            if groups:
+                gw, gb = params[pi + 2], params[pi + 3]
+                act, mean, rstd = K.groupnorm_silu_fwd(z, gw, gb, xB, V, cout, groups)
+                saved += [cols, z, mean, rstd]
+                a = act
+                pi += 4
+            else:
+                saved += [cols]
+                a = None
+                pi += 2
+            strides = (V * cout, 1, Ho * Wo * cout, Wo * cout, cout)
+            dims = (cout, Do, Ho, Wo)
+        Cout, Dd, Hd, Wd = dims
+        n = Dd * Hd * Wd * Cout
+        if pos_embed.numel() != n:
+            raise RuntimeError(
+                f"voxel_embed emits a {Dd}x{Hd}x{Wd} token grid x {Cout} channels but pos_embed has "
+                f"{tuple(pos_embed.shape)}: the tensor sizes must match (the committed reference has this "
+                "defect at 128^3; construct HybridViT3D(token_grid='conv') or token_grid=16)")
+        tokens = K.add_pos(z.view(xB, n), pos_embed.contiguous().view(-1), B)
+        ctx.save_for_backward(*saved, *params)
+        ctx.meta = (plan, geoms, xB, B, tuple(x.shape), len(saved), n, Cout)
+        return tokens.view(B * Dd * Hd * Wd, Cout)
+
+    @staticmethod
+    def backward(ctx, dtok):
+        plan, geoms, xB, B, xshape, nsaved, n, Cout = ctx.meta
+        saved, params = ctx.saved_tensors[:nsaved], ctx.saved_tensors[nsaved:]
+        dtok = dtok.contiguous().view(B, n)
+        dpos = K.batch_sum(dtok)
+        dz = dpos.view(1, n) if xB != B else dtok
+        dz = dz.reshape(-1, Cout)
+        grads = [None] * len(params)
+        # walk the stack backwards
+        si, pi = nsaved, len(params)
+        dx = None
+        for li in range(len(plan) - 1, -1, -1):
+            cin, cout, stride, groups = plan[li]
+            cin_, Dc, Hc, Wc, stride_, strides, V = geoms[li]
+            if groups:
+                cols, z, mean, rstd = saved[si - 4:si]
+                si -= 4
+                weight, bias, gw, gb = params[pi - 4:pi]
+                pi -= 4
+                dz, dgw, dgb = K.groupnorm_silu_bwd(dz.contiguous(), z, gw, gb, mean, rstd, xB, V, cout, groups)
+                grads[pi + 2], grads[pi + 3] = dgw, dgb
+            else:
+                cols = saved[si - 1]
+                si -= 1
+                weight, bias = params[pi - 2:pi]
+                pi -= 2
+            dz16 = K.cast_bf16(dz.contiguous())
+            grads[pi + 1] = K.colsum_bf16(dz16)
+            dwp = _wgrad(dz16, cols)                                    # [cout, Kp]
+            grads[pi] = dwp[:, :cin * 27].reshape(weight.shape)
+            need_dx = li > 0 or ctx.needs_input_grad[0]
+            if need_dx:
+                dcols = _dgrad(dz16, w16(weight, pad_to=cols.shape[1]))
+                if li > 0:
+                    prev_c = plan[li - 1][1]
+                    d_act = torch.empty(xB * Dc * Hc * Wc, prev_c, device=dtok.device, dtype=torch.float32)
+                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, d_act, strides)
+                    dz = d_act
+                else:
+                    dx1 = torch.empty((xB,) + tuple(xshape[1:]), device=dtok.device, dtype=torch.float32)
+                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, dx1, tuple(dx1.stride()))
+                    if xB != B:
+                        dx = torch.zeros(xshape, device=dtok.device, dtype=torch.float32)
+                        dx[0] = dx1[0]
+                    else:
+                        dx = dx1
+        return (dx, dpos.view(1, -1, Cout), None) + tuple(grads)
+
+
+# ------------------------------------------------------------------ output head (a7 tail of forward)
+
+class OutputHead(Function):
+    """upsample(reshape(output_proj(LayerNorm(tokens))))   hybrid_vit_backbone.py:265-272."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, wo, bo, B, grid, size):
+        v, mean, rstd = K.head_fwd(x, ln_w, ln_b, wo.reshape(-1), bo)
+        out = K.upsample3d_fwd(v, B, grid, size)
+        ctx.save_for_backward(x, ln_w, ln_b, wo, mean, rstd)
+        ctx.meta = (B, grid, size)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, ln_w, ln_b, wo, mean, rstd = ctx.saved_tensors
+        B, grid, size = ctx.meta
+        dv = K.upsample3d_bwd(dout.float().contiguous(), B, grid, size)
+        N = grid[0] * grid[1] * grid[2]
+        r = K.ln_bwd(dv, x, mean, rstd, ln_w, ln_b, B, N, mult_vec=wo.reshape(-1).contiguous(), head=True)
+        return r["dx"], r["dw"], r["db"], r["dvec"].view_as(wo), r["dscalar"], None, None, None

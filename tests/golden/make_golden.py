@@ -93,6 +93,45 @@ def components():
     torch.save(out, os.path.join(HERE, "components.pt"))
 
 
+def components_d64():
+    """head_dim 64 cases (embed 128 / 2 heads) sized for the CUDA parity tests: ragged N, M."""
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    torch.manual_seed(1)
+    sa = MultiHeadSelfAttention(128, num_heads=2).eval()
+    x = torch.randn(2, 200, 128, generator=g, requires_grad=True)
+    y = sa(x)
+    r = torch.randn(y.shape, generator=g)
+    pg, ig = grads_of(sa, [x], y, r)
+    out["self_attn"] = dict(sd=sa.state_dict(), x=x.detach(), y=y.detach(), r=r, pgrad=pg, xgrad=ig[0], num_heads=2)
+
+    ca = MultiHeadCrossAttention(128, 40, num_heads=2).eval()
+    x = torch.randn(2, 200, 128, generator=g, requires_grad=True)
+    ctx = torch.randn(2, 72, 40, generator=g, requires_grad=True)
+    y = ca(x, ctx)
+    r = torch.randn(y.shape, generator=g)
+    pg, ig = grads_of(ca, [x, ctx], y, r)
+    out["cross_attn"] = dict(sd=ca.state_dict(), x=x.detach(), ctx=ctx.detach(), y=y.detach(), r=r,
+                             pgrad=pg, xgrad=ig[0], ctxgrad=ig[1], num_heads=2)
+
+    for name, prev in (("block", False), ("block_prev", True)):
+        blk = HybridViTBlock3D(64, num_heads=1, context_dim=40, cond_dim=48, use_prev_stage=prev).eval()
+        randomise_adaln(blk, g)
+        x = torch.randn(2, 200, 64, generator=g, requires_grad=True)
+        ctx = torch.randn(2, 72, 40, generator=g, requires_grad=True)
+        cond = torch.randn(2, 48, generator=g, requires_grad=True)
+        prev_e = torch.randn(2, 256, generator=g) if prev else None
+        res = blk(x, ctx, cond, prev_e)
+        r = torch.randn(res.shape, generator=g)
+        pg, ig = grads_of(blk, [x, ctx, cond], res, r)
+        out[name] = dict(sd=blk.state_dict(), x=x.detach(), ctx=ctx.detach(), cond=cond.detach(), prev=prev_e,
+                         y=res.detach(), r=r, pgrad=pg, xgrad=ig[0], ctxgrad=ig[1], condgrad=ig[2],
+                         num_heads=1, use_prev_stage=prev)
+    for c in out.values():      # gradients of the weights in fp16: halves the fixture, ample for cos/3e-2 checks
+        c["pgrad"] = {k: v.half() for k, v in c["pgrad"].items()}
+    torch.save(out, os.path.join(HERE, "components_d64.pt"))
+
+
 BACKBONES = {
     # name: ctor kwargs, context_len, batch
     "vit_s2": (dict(volume_size=(32, 16, 16), in_channels=1, voxel_dim=32, depth=2, num_heads=2,
@@ -101,6 +140,13 @@ BACKBONES = {
                           context_dim=24, cond_dim=48, use_prev_stage=True), 12, 1),
     "vit_s1": (dict(volume_size=(16, 16, 8), in_channels=2, voxel_dim=32, depth=1, num_heads=1,
                     context_dim=16, cond_dim=32), 8, 1),
+    # head_dim 64 cases for the CUDA parity tests
+    "vit_d64": (dict(volume_size=(32, 16, 16), in_channels=1, voxel_dim=64, depth=2, num_heads=1,
+                     context_dim=24, cond_dim=48), 40, 2),
+    "vit_d64_h2": (dict(volume_size=(16, 8, 4), in_channels=1, voxel_dim=128, depth=1, num_heads=2,
+                        context_dim=24, cond_dim=48), 20, 1),
+    "vit_d64_quirk": (dict(volume_size=(64, 8, 8), in_channels=16, voxel_dim=64, depth=1, num_heads=1,
+                           context_dim=24, cond_dim=48, use_prev_stage=True), 12, 1),
 }
 
 
@@ -121,7 +167,10 @@ def backbones():
         out[name] = dict(kwargs=kw, sd=m.state_dict(), x=x.detach(), ctx=ctx.detach(), cond=cond.detach(),
                          prev=prev, y=y.detach(), r=r, pgrad=pg, xgrad=ig[0], ctxgrad=ig[1], condgrad=ig[2],
                          downsampled_size=tuple(m.downsampled_size))
-    torch.save(out, os.path.join(HERE, "backbones.pt"))
+        if "d64" in name:
+            out[name]["pgrad"] = {k: v.half() for k, v in out[name]["pgrad"].items()}
+    torch.save({k: v for k, v in out.items() if "d64" not in k}, os.path.join(HERE, "backbones.pt"))
+    torch.save({k: v for k, v in out.items() if "d64" in k}, os.path.join(HERE, "backbones_d64.pt"))
 
 
 CTOR_CASES = [
@@ -156,7 +205,8 @@ def ctor_table():
 if __name__ == "__main__":
     torch.set_num_threads(8)
     components()
+    components_d64()
     backbones()
     ctor_table()
-    for fn in ("components.pt", "backbones.pt", "ctor_table.json"):
+    for fn in ("components.pt", "components_d64.pt", "backbones.pt", "backbones_d64.pt", "ctor_table.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

@@ -1,0 +1,216 @@
+"""GPU parity: the CUDA path (through the drop-in modules -> C ABI) against the golden fixtures produced by
+the real reference, and against the oracle on seeded inputs.
+
+Tolerances are the north-star ones for the bf16 path: forward max|a-b|/max|b| <= 2e-2 against the fp32
+reference, gradient cosine similarity >= 0.999 per tensor and globally.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import vit_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 2e-2
+COS_TOL = 0.999
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gold(name):
+    return torch.load(os.path.join(ROOT, "tests", "golden", name), weights_only=False)
+
+
+def _dev(t):
+    return None if t is None else t.cuda()
+
+
+def _check_grads(named, ref, what):
+    flat_a, flat_b = [], []
+    for k, g in named.items():
+        assert g is not None, f"{what}: no gradient for {k}"
+        r = ref[k].float().cuda()
+        if float(r.abs().max()) == 0.0:
+            assert float(g.abs().max()) < 1e-6, k
+            continue
+        cs = O.cosine(g, r)
+        assert cs >= COS_TOL, f"{what}: grad cosine {cs:.5f} for {k}"
+        flat_a.append(g.flatten().float())
+        flat_b.append(r.flatten())
+    cs = O.cosine(torch.cat(flat_a), torch.cat(flat_b))
+    assert cs >= COS_TOL, f"{what}: global grad cosine {cs:.5f}"
+
+
+def test_self_attention_golden():
+    import hybrid_vit_cascade_b200 as hvc
+    c = _gold("components_d64.pt")["self_attn"]
+    m = hvc.MultiHeadSelfAttention(128, num_heads=c["num_heads"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x = c["x"].cuda().requires_grad_(True)
+    y = m(x)
+    assert y.dtype == torch.float32 and y.shape == c["y"].shape
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads["x"] = x.grad
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"]), "self_attn")
+
+
+def test_cross_attention_golden():
+    import hybrid_vit_cascade_b200 as hvc
+    c = _gold("components_d64.pt")["cross_attn"]
+    m = hvc.MultiHeadCrossAttention(128, 40, num_heads=c["num_heads"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x = c["x"].cuda().requires_grad_(True)
+    ctx = c["ctx"].cuda().requires_grad_(True)
+    y = m(x, ctx)
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=x.grad, ctx=ctx.grad)
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"]), "cross_attn")
+
+
+def test_cross_attention_transposed_context_view():
+    """model_direct.py:80 passes context as a transposed view of (B, C, H*W); no copy is required of the caller."""
+    import hybrid_vit_cascade_b200 as hvc
+    c = _gold("components_d64.pt")["cross_attn"]
+    m = hvc.MultiHeadCrossAttention(128, 40, num_heads=c["num_heads"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    ctx_nchw = c["ctx"].cuda().transpose(1, 2).contiguous()          # (B, Cc, M)
+    y = m(c["x"].cuda(), ctx_nchw.transpose(1, 2))
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+
+
+@pytest.mark.parametrize("name", ["block", "block_prev"])
+def test_block_golden(name):
+    import hybrid_vit_cascade_b200 as hvc
+    c = _gold("components_d64.pt")[name]
+    m = hvc.HybridViTBlock3D(64, num_heads=c["num_heads"], context_dim=40, cond_dim=48,
+                             use_prev_stage=c["use_prev_stage"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x, ctx, cond = (c[k].cuda().requires_grad_(True) for k in ("x", "ctx", "cond"))
+    y = m(x, ctx, cond, _dev(c["prev"]))
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=x.grad, ctx=ctx.grad, cond=cond.grad)
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"], cond=c["condgrad"]), name)
+
+
+@pytest.mark.parametrize("name", ["vit_d64", "vit_d64_h2", "vit_d64_quirk"])
+def test_backbone_golden(name):
+    import hybrid_vit_cascade_b200 as hvc
+    c = _gold("backbones_d64.pt")[name]
+    m = hvc.HybridViT3D(**c["kwargs"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    assert tuple(m.downsampled_size) == tuple(c["downsampled_size"])
+    x, ctx, cond = (c[k].cuda().requires_grad_(True) for k in ("x", "ctx", "cond"))
+    y = m(x, ctx, cond, _dev(c["prev"]))
+    assert y.shape == c["y"].shape
+    err = O.max_rel(y, c["y"])
+    assert err <= FWD_TOL, err
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=x.grad, ctx=ctx.grad, cond=cond.grad)
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"], cond=c["condgrad"]), name)
+
+
+def _oracle_on_gpu(cfg, sd, x, ctx, cond, r, attn_chunk=None):
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+        xs = [t.detach().clone().requires_grad_(True) for t in (x, ctx, cond)]
+        y = O.backbone(xs[0], xs[1], xs[2], sd, cfg, attn_chunk=attn_chunk)
+        (y * r).sum().backward()
+        return y.detach(), {k: v.grad for k, v in sd.items()}, [t.grad for t in xs]
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("volume,grid", [((64, 64, 64), "reference"), ((128, 128, 128), 16)])
+def test_backbone_direct_config_vs_oracle(volume, grid):
+    """config_direct.json shape (C=256, 4 heads, 4096 tokens) at depth 2, batch 2, against the fp32 oracle on the GPU."""
+    import hybrid_vit_cascade_b200 as hvc
+    kw = dict(volume_size=volume, in_channels=1, voxel_dim=256, depth=2, num_heads=4, context_dim=512, cond_dim=1024)
+    cfg = O.BackboneConfig(token_grid=grid, **kw)
+    sd = {k: v.cuda() for k, v in O.init_state_dict(cfg, seed=3).items()}
+    m = hvc.HybridViT3D(token_grid=grid, **kw).cuda().eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, M = 2, 384
+    x = torch.randn(B, 1, *volume, device="cuda", generator=g) * 0.5
+    ctx = torch.randn(B, M, 512, device="cuda", generator=g)
+    cond = torch.randn(B, 1024, device="cuda", generator=g)
+    r = torch.randn(B, 1, *volume, device="cuda", generator=g)
+    y_ref, pg_ref, ig_ref = _oracle_on_gpu(cfg, sd, x, ctx, cond, r, attn_chunk=1024)
+    xs = [t.clone().requires_grad_(True) for t in (x, ctx, cond)]
+    y = m(*xs)
+    err = O.max_rel(y, y_ref)
+    assert err <= FWD_TOL, err
+    (y * r).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=xs[0].grad, ctx=xs[1].grad, cond=xs[2].grad)
+    _check_grads(grads, dict(pg_ref, x=ig_ref[0], ctx=ig_ref[1], cond=ig_ref[2]), f"direct{volume[0]}")
+
+
+def test_expanded_input_is_embedded_once_and_exact():
+    """model_direct.py:75 feeds initial_volume.expand(B, ...): same result as the materialised batch."""
+    import hybrid_vit_cascade_b200 as hvc
+    torch.manual_seed(0)
+    m = hvc.HybridViT3D(volume_size=(32, 32, 32), in_channels=1, voxel_dim=64, depth=1, num_heads=1,
+                        context_dim=32, cond_dim=64).cuda().eval()
+    with torch.no_grad():
+        for p in m.blocks[0].adaln.parameters():
+            p.normal_(0, 0.02)
+    vol = (torch.randn(1, 1, 32, 32, 32, device="cuda") * 0.1).requires_grad_(True)
+    ctx = torch.randn(3, 40, 32, device="cuda")
+    cond = torch.randn(3, 64, device="cuda")
+    y1 = m(vol.expand(3, -1, -1, -1, -1), ctx, cond)
+    y1.sum().backward()
+    g1 = vol.grad.clone()
+    vol.grad = None
+    y2 = m(vol.expand(3, -1, -1, -1, -1).contiguous(), ctx, cond)
+    y2.sum().backward()
+    assert torch.equal(y1, y2)
+    assert O.cosine(g1, vol.grad) > 0.9999
+
+
+def test_attention_32768_tokens_against_chunked_fp32():
+    """Full-size sequence (the 128^3 / 256^3 token grid): one head, fp32 chunked reference on the GPU."""
+    from hybrid_vit_cascade_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, d = 32768, 64
+    q, k, v = (torch.randn(N, d, device="cuda", generator=g).bfloat16() for _ in range(3))
+    o, lse2 = K.attn_fwd(q, k, v, 1, 1, N, N, d, d ** -0.5)
+    qf, kf, vf = q.float(), k.float(), v.float()
+    worst = 0.0
+    for s in range(0, N, 4096):
+        a = ((qf[s:s + 4096] @ kf.t()) * d ** -0.5).softmax(-1) @ vf
+        worst = max(worst, float((o[s:s + 4096].float() - a).abs().max() / a.abs().max()))
+    assert worst <= FWD_TOL, worst
+    # size-independent property: softmax rows sum to one  <=>  attention over constant V returns the constant
+    ones = torch.ones(N, d, device="cuda", dtype=torch.bfloat16)
+    o1, _ = K.attn_fwd(q, k, ones, 1, 1, N, N, d, d ** -0.5)
+    assert float((o1.float() - 1).abs().max()) < 1e-2
+
+
+def test_gradient_linearity_property():
+    """Backward is linear in the upstream gradient: grad(2r) == 2 grad(r) (size-independent check of the bwd kernels)."""
+    import hybrid_vit_cascade_b200 as hvc
+    torch.manual_seed(0)
+    m = hvc.HybridViTBlock3D(64, num_heads=1, context_dim=32, cond_dim=64).cuda().eval()
+    with torch.no_grad():
+        for p in m.adaln.parameters():
+            p.normal_(0, 0.02)
+    x = torch.randn(2, 384, 64, device="cuda", requires_grad=True)
+    ctx = torch.randn(2, 100, 32, device="cuda")
+    cond = torch.randn(2, 64, device="cuda")
+    r = torch.randn(2, 384, 64, device="cuda")
+    g1, = torch.autograd.grad((m(x, ctx, cond) * r).sum(), x)
+    g2, = torch.autograd.grad((m(x, ctx, cond) * (2 * r)).sum(), x)
+    assert O.cosine(g2, 2 * g1) > 0.9999
+    assert O.max_rel(g2, 2 * g1) < 2e-2
