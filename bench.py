@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- training throughput of the 3D ViT backbone hot path (volumes/sec), B200-native arm and
+reference (CPU) arm.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload direct128|direct64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: HybridViT3D forward (voxel embed, L x (AdaLN
+self-attention, cross-attention to the X-ray tokens, AdaLN MLP), LN/proj/upsample head) + L1 loss +
+backward of every parameter and of the learned input volume + (N>1) bucketed gradient all-reduce
+overlapped with backward + AdamW.  Workload = BASELINE.json configs[2]: direct_regression at 128^3,
+C=256, 4 heads (d=64), depth 4, 32^3 = 32768 volume tokens (what the conv stack emits), 4096 X-ray
+context tokens x 512, batch 8 per GPU, synthetic inputs, random-init weights (AdaLN re-randomised so the
+self-attention and MLP branches are live).  Train-mode dropout is OFF in both arms.
+
+Prints ONE JSON line on stdout (rank 0); diagnostics go to stderr.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "direct128": dict(volume=(128, 128, 128), token_grid="conv", voxel_dim=256, depth=4, heads=4, ctx_hw=64, ctx_dim=512,
+                      cond_dim=1024, batch=8, desc="direct_regression 128^3 (32^3=32768 tokens, 4096 ctx tokens)"),
+    "direct64": dict(volume=(64, 64, 64), token_grid="reference", voxel_dim=256, depth=4, heads=4, ctx_hw=64, ctx_dim=512,
+                     cond_dim=1024, batch=8, desc="direct_regression 64^3 (16^3=4096 tokens, 4096 ctx tokens)"),
+}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def oracle_cfg(w):
+    from oracle import vit_oracle as O
+    return O.BackboneConfig(volume_size=w["volume"], in_channels=1, voxel_dim=w["voxel_dim"], depth=w["depth"],
+                            num_heads=w["heads"], context_dim=w["ctx_dim"], cond_dim=w["cond_dim"],
+                            token_grid=w["token_grid"])
+
+
+def step_flops(w):
+    """Algorithmic FLOPs of one sample, forward+backward (3 x forward)."""
+    from oracle import vit_oracle as O
+    f = O.forward_flops(oracle_cfg(w), w["ctx_hw"] ** 2)
+    return {k: 3.0 * v for k, v in f.items()}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[4:8]):
+                    if v.strip() == "Active":
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_baseline(w, seconds_budget=20.0, rows=2048, steps=None, warmup=1):
+    """Oracle port on the host cores, bounded sample (oracle/cpu_baseline.py)."""
+    from oracle.cpu_baseline import CpuBaseline
+    cb = CpuBaseline(oracle_cfg(w), w["ctx_hw"] ** 2, rows=rows)
+    for _ in range(warmup):
+        cb.step()
+    est, t0 = [], time.perf_counter()
+    while True:
+        est.append(cb.step())
+        if steps is not None:
+            if len(est) >= steps:
+                break
+        elif time.perf_counter() - t0 > seconds_budget or len(est) >= 8:
+            break
+    sec_per_vol = min(est) if steps is None else sum(est) / len(est)
+    return {"value": 1.0 / sec_per_vol, "unit": "volumes/s", "cores": cb.threads, "kind": "port", "sample": cb.describe(),
+            "sec_per_volume": sec_per_vol, "samples": len(est)}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(w, rows=args.cpu_rows, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": "train volumes/sec (3D ViT backbone fwd+bwd)", "value": cb["value"], "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_volume"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "batch_per_gpu": 1, "dropout": 0.0, "note": "CPU arm: one step = one bounded sample of one volume"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, w):
+    import torch.distributed as dist
+    import hybrid_vit_cascade_b200 as hvc
+    from hybrid_vit_cascade_b200 import _lib, kernels as K
+    from hybrid_vit_cascade_b200.dp import GradientBuckets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or w["batch"]
+    D, H, W = w["volume"]
+    hvc.set_dropout_policy("ignore")
+
+    torch.manual_seed(0)
+    model = hvc.HybridViT3D(volume_size=w["volume"], in_channels=1, voxel_dim=w["voxel_dim"], depth=w["depth"],
+                            num_heads=w["heads"], context_dim=w["ctx_dim"], cond_dim=w["cond_dim"],
+                            token_grid=w["token_grid"]).to(dev)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "adaln.linear" in n:
+                p.normal_(0.0, 0.02)
+    initial_volume = torch.nn.Parameter(torch.randn(1, 1, D, H, W, device=dev) * 0.01)   # model_direct.py:57
+    params = list(model.parameters()) + [initial_volume]
+    gb = GradientBuckets(params)
+    gb.broadcast_parameters(params)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    hw = w["ctx_hw"]
+    feat = torch.rand(B, w["ctx_dim"], hw, hw, device=dev, generator=g)          # encoder feature map (B, C, H', W')
+    cond = torch.randn(B, w["cond_dim"], device=dev, generator=g)
+    target = torch.rand(B, 1, D, H, W, device=dev, generator=g) * 2 - 1
+
+    def step(feat_, cond_, target_):
+        gb.reset()
+        ctx = feat_.flatten(2).transpose(1, 2)                                    # model_direct.py:80 (a view, no copy)
+        out = model(initial_volume.expand(B, -1, -1, -1, -1), ctx, cond_)
+        loss = (out - target_).abs().mean()
+        loss.backward()
+        gb.finish()
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        step(feat, cond, target)
+    # ---- device-resident timing
+    prof = {}
+    K.set_profiler(prof)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(lambda: step(feat, cond, target), args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else {}
+    K.set_profiler(None)
+    torch.cuda.synchronize()
+    kern = {}
+    for name, evs in prof.items():
+        t = [a.elapsed_time(b) for a, b, _ in evs]
+        fl = [f for _, _, f in evs]
+        kern[name] = {"calls": len(t), "ms_total": sum(t), "tflops": sum(fl) / (sum(t) * 1e9) if sum(t) > 0 else 0.0,
+                      "ms_max_call": max(t), "tflops_max_call": max(f / (x * 1e9) for f, x in zip(fl, t) if x > 0)}
+    # dominant kernel: self-attention backward launches (the largest calls of attn_bwd)
+    bwd = sorted(((a.elapsed_time(b), f) for a, b, f in prof.get("attn_bwd", [])), key=lambda z: -z[1])
+    big = [z for z in bwd if z[1] == bwd[0][1]] if bwd else []
+
+    # ---- end-to-end: host buffers in, loss out, every step
+    feat_h, cond_h, target_h = (t.cpu().pin_memory() for t in (feat, cond, target))
+    loss_val = [0.0]
+
+    def e2e_step():
+        f = feat_h.to(dev, non_blocking=True)
+        c = cond_h.to(dev, non_blocking=True)
+        t = target_h.to(dev, non_blocking=True)
+        loss_val[0] = float(step(f, c, t).item())
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = sum(t.numel() * t.element_size() for t in (feat_h, cond_h, target_h))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    fl = step_flops(w)
+    vols = world * B * args.steps
+    value = vols / (ms_total / 1e3)
+    roof = None
+    if big:
+        ach = sum(f for _, f in big) / (sum(t for t, _ in big) * 1e9)
+        roof = {"kernel": "attn_bwd_kernel<64> (self-attention; call also includes the delta and dq-convert passes)",
+                "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "peak_source": peak_src, "launches": len(big), "ms_per_launch": sum(t for t, _ in big) / len(big),
+                "frac_of_nominal_2250": ach / 2250.0}
+    line = {
+        "metric": "train volumes/sec (3D ViT backbone fwd+bwd)", "value": value, "unit": "volumes/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": B * world, "voxel_dim": w["voxel_dim"],
+                   "heads": w["heads"], "depth": w["depth"], "tokens": oracle_cfg(w).num_tokens, "context_tokens": hw * hw,
+                   "parallelism": f"dp{world}", "dropout": 0.0, "optimizer": "AdamW(fused)", "loss": "L1",
+                   "l2_note": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush"},
+        "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "loss": loss_val[0]},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "model_tflops": {"algorithmic_tflop_per_volume": fl["total"] / 1e12, "achieved": value * fl["total"] / 1e12 / world,
+                         "frac_of_measured_peak": value * fl["total"] / 1e12 / world / peak_tf,
+                         "attention_share_of_flops": (fl["self_attn"] + fl["cross_attn"]) / fl["total"]},
+        "kernels": kern,
+        "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+    }
+    if world == 1 and not args.skip_cpu_baseline:
+        cb = cpu_baseline(w, rows=args.cpu_rows)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="direct128", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows in the CPU baseline sample")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device (sm_100); there is no CPU fallback")
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

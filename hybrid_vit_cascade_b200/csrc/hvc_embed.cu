@@ -195,7 +195,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                                                        const float* __restrict__ A, const float* __restrict__ Bq, bf16* __restrict__ y,
-                                                       float* __restrict__ dx, int B, int V, int C, int cpg) {
+                                                       float* __restrict__ dx, int B, int V, int C, int cpg, int y_f32) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*V*C/4
   const int tpr = C >> 2;
   const long long total = (long long)B * V * tpr;
@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     }
   }
   if (MODE == 0) {
-    *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_bf16(out[0], out[1]), pack_bf16(out[2], out[3]));
+    if (y_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + off) = make_float4(out[0], out[1], out[2], out[3]);
+    else *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_bf16(out[0], out[1]), pack_bf16(out[2], out[3]));
   } else {
     *reinterpret_cast<float4*>(dx + off) = make_float4(out[0], out[1], out[2], out[3]);
   }
@@ -280,7 +281,7 @@ static int gn_rows_per_block(int B, int V) {
 }
 
 extern "C" int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
-                                      void* y, float* mean, float* rstd, float* scratch, void* stream) {
+                                      void* y, int32_t y_is_bf16, float* mean, float* rstd, float* scratch, void* stream) {
   HVC_CHECK_ARG(x && w && b && y && mean && rstd && scratch, "hvc_groupnorm_silu_fwd: null operand");
   HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_groupnorm_silu_fwd: bad shape C=%d G=%d", C, groups);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -294,7 +295,7 @@ extern "C" int hvc_groupnorm_silu_fwd(const float* x, const float* w, const floa
   HVC_LAUNCH_CHECK();
   const long long total = (long long)B * V * (C / 4);
   gn_apply_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, nullptr, mean, rstd, w, b, nullptr, nullptr, reinterpret_cast<bf16*>(y),
-                                                                      nullptr, B, V, C, a.cpg);
+                                                                      nullptr, B, V, C, a.cpg, y_is_bf16 ? 0 : 1);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
@@ -317,7 +318,7 @@ extern "C" int hvc_groupnorm_silu_bwd(const float* dy, const float* x, const flo
   gn_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(T1, T2, w, dw, db, A, Bq, B, C, a.cpg, V);
   HVC_LAUNCH_CHECK();
   const long long total = (long long)B * V * (C / 4);
-  gn_apply_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, B, V, C, a.cpg);
+  gn_apply_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, B, V, C, a.cpg, 0);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

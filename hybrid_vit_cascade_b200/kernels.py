@@ -13,6 +13,33 @@ EPI_BF16, EPI_RESIDUAL, EPI_F32_ATOMIC, EPI_F32 = 0, 1, 2, 3
 ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 
 
+# Optional per-call device timing (bench.py's live roofline measurement): when set to a dict, the wrappers listed
+# in _timed() bracket their launches with CUDA events on the current stream (the stream the kernels run on).
+_PROF = None
+
+
+def set_profiler(store):
+    global _PROF
+    _PROF = store
+
+
+class _timed:
+    def __init__(self, name, flops):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _PROF is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _PROF is not None:
+            self.e1.record()
+            _PROF.setdefault(self.name, []).append((self.e0, self.e1, self.flops))
+        return False
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -79,7 +106,8 @@ def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epil
         args.aux, args.ldaux = aux.data_ptr(), _row_major_2d(aux, "aux")
     args.alpha = alpha
     args.k_splits = k_splits
-    _lib.check(_lib.lib().hvc_gemm(C.byref(args), _stream()), "hvc_gemm")
+    with _timed("gemm", 2.0 * M * N * K):
+        _lib.check(_lib.lib().hvc_gemm(C.byref(args), _stream()), "hvc_gemm")
     return out
 
 
@@ -111,7 +139,8 @@ def attn_fwd(q, k, v, B, H, nq, nk, d, scale):
     args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
     args.o, args.ldo = o.data_ptr(), o.stride(0)
     args.lse = lse.data_ptr()
-    _lib.check(_lib.lib().hvc_attn_fwd(C.byref(args), _stream()), "hvc_attn_fwd")
+    with _timed("attn_fwd", 4.0 * B * H * nq * nk * d):
+        _lib.check(_lib.lib().hvc_attn_fwd(C.byref(args), _stream()), "hvc_attn_fwd")
     return o, lse
 
 
@@ -131,7 +160,8 @@ def attn_bwd(q, k, v, o, lse, d_o, B, H, nq, nk, d, scale, dq, dk, dv):
     args.dv, args.lddv = dv.data_ptr(), _row_major_2d(dv, "dv")
     args.delta = delta.data_ptr()
     args.dq_accum = dq_accum.data_ptr()
-    _lib.check(_lib.lib().hvc_attn_bwd(C.byref(args), _stream()), "hvc_attn_bwd")
+    with _timed("attn_bwd", 10.0 * B * H * nq * nk * d):
+        _lib.check(_lib.lib().hvc_attn_bwd(C.byref(args), _stream()), "hvc_attn_bwd")
     return dq, dk, dv
 
 
@@ -316,15 +346,16 @@ def col2im3d(dcols, B, Cin, D, H, W, stride, out, strides):
     return out
 
 
-def groupnorm_silu_fwd(x, w, b, B, V, Cc, groups):
-    """x f32 [B*V, C] channels-last -> (y bf16 [B*V, C], mean [B,G], rstd [B,G])."""
+def groupnorm_silu_fwd(x, w, b, B, V, Cc, groups, out_dtype=torch.bfloat16):
+    """x f32 [B*V, C] channels-last -> (y bf16|f32 [B*V, C], mean [B,G], rstd [B,G])."""
     _need_cuda(x, w, b)
     assert x.dtype == torch.float32 and x.is_contiguous()
-    y = torch.empty(B * V, Cc, device=x.device, dtype=torch.bfloat16)
+    y = torch.empty(B * V, Cc, device=x.device, dtype=out_dtype)
     mean = torch.empty(B, groups, device=x.device, dtype=torch.float32)
     rstd = torch.empty(B, groups, device=x.device, dtype=torch.float32)
     scratch = torch.empty(2 * B * Cc, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().hvc_groupnorm_silu_fwd(_ptr(x), _ptr(w), _ptr(b), B, V, Cc, groups, _ptr(y), _ptr(mean), _ptr(rstd),
+    _lib.check(_lib.lib().hvc_groupnorm_silu_fwd(_ptr(x), _ptr(w), _ptr(b), B, V, Cc, groups, _ptr(y),
+                                                 int(out_dtype == torch.bfloat16), _ptr(mean), _ptr(rstd),
                                                  _ptr(scratch), _stream()), "hvc_groupnorm_silu_fwd")
     return y, mean, rstd
 

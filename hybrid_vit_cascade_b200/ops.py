@@ -329,7 +329,7 @@ class VoxelEmbed(Function):
         a, strides, dims = xin, tuple(xin.stride()), (Cin, D, H, W)
         z = None
         pi = 0
-        for (cin, cout, stride, groups) in plan:
+        for li, (cin, cout, stride, groups) in enumerate(plan):
             _, Dc, Hc, Wc = dims
             weight, bias = params[pi], params[pi + 1]
             cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides)
@@ -339,9 +339,13 @@ class VoxelEmbed(Function):
             geoms.append((cin, Dc, Hc, Wc, stride, strides, V))
             if groups:
                 gw, gb = params[pi + 2], params[pi + 3]
-                act, mean, rstd = K.groupnorm_silu_fwd(z, gw, gb, xB, V, cout, groups)
+                last = li == len(plan) - 1          # a stack that ends in GN+SiLU feeds the fp32 token stream
+                act, mean, rstd = K.groupnorm_silu_fwd(z, gw, gb, xB, V, cout, groups,
+                                                       out_dtype=torch.float32 if last else torch.bfloat16)
                 saved += [cols, z, mean, rstd]
                 a = act
+                if last:
+                    z = act
                 pi += 4
             else:
                 saved += [cols]

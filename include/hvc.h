@@ -209,9 +209,11 @@ typedef struct hvc_conv3d_geom {
 int hvc_im2col3d(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream);
 /* dx (f32, layout given by geom strides) = adjoint of im2col applied to dcols (bf16 [M, Kp]). */
 int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream);
-/* y bf16 [B,V,C] = SiLU(GroupNorm(x f32 [B,V,C])); mean/rstd f32 [B,groups] saved; scratch f32 [2*B*C]. */
+/* y [B,V,C] (bf16, or f32 when it feeds the token stream) = SiLU(GroupNorm(x f32 [B,V,C])); mean/rstd f32
+ * [B,groups] saved; scratch f32 [2*B*C]. */
 int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C,
-                           int32_t groups, void* y, float* mean, float* rstd, float* scratch, void* stream);
+                           int32_t groups, void* y, int32_t y_is_bf16, float* mean, float* rstd, float* scratch,
+                           void* stream);
 /* dx f32 [B,V,C], dw/db f32 [C]; scratch f32 [2*B*C + 2*B*groups]. */
 int hvc_groupnorm_silu_bwd(const float* dy, const float* x, const float* w, const float* b, const float* mean,
                            const float* rstd, int32_t B, int32_t V, int32_t C, int32_t groups, float* dx,
