@@ -5,27 +5,31 @@
 //
 // Kernels:
 //   attn_delta_kernel   delta[b,h,q] = sum_d dO * O                       (HBM-bound pre-pass)
-//   attn_bwd_kernel     one CTA = one (batch, head, 128-key tile), loops over 128-query tiles:
-//        S^T  = K Q^T                (SS)            P^T = exp2(S^T*scale2 - lse2)      -> TMEM (bf16, over S^T)
-//        dP^T = V dO^T               (SS)            dS^T = P^T * (dP^T - delta) * scale -> smem (bf16, swizzled)
-//        dV  += P^T  dO              (TS, dO MN-major)
-//        dK  += dS^T Q               (SS, dS^T K-major, Q MN-major)
-//        dQ_i = dS   K               (SS, dS^T read MN-major as A, K MN-major)  -> fp32 atomics into dq_accum
-//      thread == key row == TMEM lane, so the elementwise stage needs no shuffles; the single swizzled
-//      smem copy of dS^T serves both the dK (K-major) and the dQ (MN-major) products.
-//   attn_dq_convert_kernel   dq_accum (f32, per head) -> dq (bf16, packed token-major)
+//   attn_bwd_kernel     one CTA = one (batch, head, 128-key tile), loops over 128-query tiles i:
+//        S^T  = K Q_i^T   (SS)      phase A: P^T = exp2(S^T*scale2 - lse2)          -> TMEM (bf16, own columns)
+//        dP^T = V dO_i^T  (SS)      phase B: dS^T = P^T * (dP^T - delta)            -> smem (bf16, swizzled)
+//        dV  += P^T  dO_i (TS, dO MN-major)
+//        dK  += dS^T Q_i  (SS, dS^T K-major, Q MN-major)          (softmax scale applied in the epilogue)
+//        dQ_i = dS   K    (SS, dS^T read MN-major as A, K MN-major) -> TMA reduce-add (fp32) into dq_accum
+//      320 threads: two elementwise warpgroups (thread == key row == TMEM lane; warpgroup w owns query
+//      columns [64w, 64w+64)), a TMA warp and an MMA warp.  TMEM is used to the last column
+//      (S^T 128 | P^T 64 | dP^T 128 | dV 64 | dK 64 | dQ 64 = 512) so that S^T(i+1) is computed while the
+//      warpgroups are still in phase B of tile i and dP^T(i+1) during phase A of tile i+1: the tensor
+//      pipe, the MUFU pipe (exp2) and the FMA pipe (packed f32x2 math) overlap instead of taking turns.
+//      The single swizzled smem copy of dS^T serves both the dK (K-major) and the dQ (MN-major) products.
+//   attn_dq_convert_kernel   dq_accum (f32, per head) * scale -> dq (bf16, packed token-major)
 #include "hvc_common.cuh"
 #include "hvc_host.h"
 
 namespace hvc {
 
-constexpr int kBwdThreads = 192;
+constexpr int kBwdThreads = 320;
 constexpr int kBT = 128;  // tile edge (queries and keys)
+constexpr int kQStages = 3;
 
 struct AttnBwdKArgs {
   int batch, heads, nq, nk, nq_pad, n_q_tiles;
   const float* lse2; const float* delta;   // [B, H, nq_pad]
-  float* dq_accum;                          // [B, H, nq_pad, HD]
   bf16* dk; long long lddk;
   bf16* dv; long long lddv;
   float scale, scale2;
@@ -36,25 +40,21 @@ struct BwdSmem {
   static constexpr int kTile = kBT * HD * 2;                 // 16 KB
   static constexpr int kK = 0;
   static constexpr int kV = kTile;
-  static constexpr int kQStage = 2 * kTile + 2048;           // Q, dO, lse2[128], delta[128] (+pad to 1 KB multiple)
+  static constexpr int kQStage = 2 * kTile + 2048;           // Q, dO, lse2[128], delta[128] (+pad to a 1 KB multiple)
   static constexpr int kQ = 2 * kTile;
-  static constexpr int kDS = kQ + 2 * kQStage;               // 2 x [128 x 128] bf16
-  static constexpr int kBar = kDS + 2 * (kBT * kBT * 2);
+  static constexpr int kDS = kQ + kQStages * kQStage;        // [128 keys x 128 queries] bf16, two 64-query sub-tiles
+  static constexpr int kDQ = kDS + kBT * kBT * 2;            // dQ staging: two [128 x 32] fp32 halves (swizzled)
+  static constexpr int kBar = kDQ + kBT * HD * 4;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
-enum { BB_KV = 0, BB_QF = 1, BB_QE = 3, BB_ST = 5, BB_DS = 6, BB_DQF = 7, BB_DQE = 8, BB_N = 9 };
-
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
+enum { BB_KV = 0, BB_QF = 1, BB_QE = 4, BB_ST = 7, BB_STFREE = 8, BB_PT = 9, BB_DPT = 10, BB_DS = 11, BB_DQF = 12, BB_DQFREE = 13, BB_N = 14 };
 
 template <int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const AttnBwdKArgs p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ, const AttnBwdKArgs p) {
   static_assert(HD == 64, "head_dim 64 only for now");
   using L = BwdSmem<HD>;
   extern __shared__ uint8_t smem_raw[];
@@ -70,31 +70,34 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nQ = p.n_q_tiles;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
     mbar_init(&bar[BB_KV], 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar[BB_QF + s], 1); mbar_init(&bar[BB_QE + s], 1); }
+    for (int s = 0; s < kQStages; ++s) { mbar_init(&bar[BB_QF + s], 1); mbar_init(&bar[BB_QE + s], 1); }
     mbar_init(&bar[BB_ST], 1);
-    mbar_init(&bar[BB_DS], 128);
+    mbar_init(&bar[BB_STFREE], 256);
+    mbar_init(&bar[BB_PT], 256);
+    mbar_init(&bar[BB_DPT], 1);
+    mbar_init(&bar[BB_DS], 256);
     mbar_init(&bar[BB_DQF], 1);
-    mbar_init(&bar[BB_DQE], 128);
+    mbar_init(&bar[BB_DQFREE], 256);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kColSt = 0, kColDPt = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+  constexpr uint32_t kColSt = 0, kColPt = 128, kColDPt = 192, kColDV = 320, kColDK = 384, kColDQ = 448;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_arrive_expect_tx(&bar[BB_KV], 2 * L::kTile);
       tma_load_2d(smem + L::kK, &tmK, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
       tma_load_2d(smem + L::kV, &tmV, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
       for (int i = 0; i < nQ; ++i) {
-        const int st = i & 1;
-        const uint32_t ph = (i >> 1) & 1;
+        const int st = i % kQStages;
+        const uint32_t ph = (i / kQStages) & 1;
         uint8_t* base = smem + L::kQ + st * L::kQStage;
         mbar_wait(&bar[BB_QE + st], ph ^ 1, 10);
         mbar_arrive_expect_tx(&bar[BB_QF + st], 2 * L::kTile + 2 * kBT * 4);
@@ -104,20 +107,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         bulk_load_1d(base + 2 * L::kTile + kBT * 4, p.delta + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t id_s = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);      // S^T, dP^T
       constexpr uint32_t id_dv = make_idesc_bf16(kBT, HD, kMajorK, kMajorMN);     // dV (A in TMEM), dK (A K-major smem)
       constexpr uint32_t id_dq = make_idesc_bf16(kBT, HD, kMajorMN, kMajorMN);    // dQ
       const uint32_t sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
-      const uint32_t sQ0 = smem_u32(smem + L::kQ), sDS0 = smem_u32(smem + L::kDS);
-      auto issue_s_dp = [&](int st) {
-        const uint32_t sQ = sQ0 + st * L::kQStage, sDO = sQ + L::kTile;
+      const uint32_t sQ0 = smem_u32(smem + L::kQ), sDS = smem_u32(smem + L::kDS);
+      auto issue_st = [&](int st) {
+        const uint32_t sQ = sQ0 + st * L::kQStage;
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
           umma_ss(tmem_base + kColSt, make_sdesc_sw128(sK + k16 * 32, 16, 1024), make_sdesc_sw128(sQ + k16 * 32, 16, 1024), id_s,
                   k16 > 0 ? 1u : 0u);
+      };
+      auto issue_dpt = [&](int st) {
+        const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
           umma_ss(tmem_base + kColDPt, make_sdesc_sw128(sV + k16 * 32, 16, 1024), make_sdesc_sw128(sDO + k16 * 32, 16, 1024), id_s,
@@ -126,31 +132,42 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&bar[BB_KV], 0, 20);
       mbar_wait(&bar[BB_QF + 0], 0, 21);
       tc_fence_after();
-      issue_s_dp(0);
+      issue_st(0);
       tc_commit(&bar[BB_ST]);
+      issue_dpt(0);
+      tc_commit(&bar[BB_DPT]);
       for (int i = 0; i < nQ; ++i) {
-        const int st = i & 1;
+        const int st = i % kQStages;
+        const int st1 = (i + 1) % kQStages;
         const uint32_t sQ = sQ0 + st * L::kQStage, sDO = sQ + L::kTile;
-        const uint32_t sDS = sDS0 + (i & 1) * (kBT * kBT * 2);
-        mbar_wait(&bar[BB_DS], i & 1, 22);
+        // (1) S^T(i+1) as soon as the warpgroups have pulled S^T(i) out of TMEM
+        if (i + 1 < nQ) {
+          mbar_wait(&bar[BB_STFREE], i & 1, 22);
+          mbar_wait(&bar[BB_QF + st1], ((i + 1) / kQStages) & 1, 23);
+          tc_fence_after();
+          issue_st(st1);
+          tc_commit(&bar[BB_ST]);
+        }
+        // (2) dV += P^T dO     (A = P^T in TMEM, 8 columns per K=16 step; B = dO MN-major)
+        mbar_wait(&bar[BB_PT], i & 1, 24);
         tc_fence_after();
-        // dV += P^T dO     (A = P^T in TMEM over S^T, 8 columns per K=16 step; B = dO MN-major)
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
-          umma_ts(tmem_base + kColDV, tmem_base + kColSt + k16 * 8, make_sdesc_sw128(sDO + k16 * 2048, 8192, 1024), id_dv,
+          umma_ts(tmem_base + kColDV, tmem_base + kColPt + k16 * 8, make_sdesc_sw128(sDO + k16 * 2048, 8192, 1024), id_dv,
                   (i > 0 || k16 > 0) ? 1u : 0u);
+        // (3) once dS^T(i) is in smem (and dP^T(i) consumed): dP^T(i+1), dK, dQ
+        mbar_wait(&bar[BB_DS], i & 1, 25);
+        tc_fence_after();
         if (i + 1 < nQ) {
-          mbar_wait(&bar[BB_QF + (st ^ 1)], ((i + 1) >> 1) & 1, 23);
-          tc_fence_after();
-          issue_s_dp(st ^ 1);
-          tc_commit(&bar[BB_ST]);
+          issue_dpt(st1);
+          tc_commit(&bar[BB_DPT]);
         }
         // dK += dS^T Q     (A = dS^T K-major: two 64-query sub-tiles; B = Q MN-major)
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS + (k16 >> 2) * 16384 + (k16 & 3) * 32, 16, 1024),
                   make_sdesc_sw128(sQ + k16 * 2048, 8192, 1024), id_dv, (i > 0 || k16 > 0) ? 1u : 0u);
-        if (i > 0) { mbar_wait(&bar[BB_DQE], (i - 1) & 1, 24); tc_fence_after(); }
+        if (i > 0) { mbar_wait(&bar[BB_DQFREE], (i - 1) & 1, 26); tc_fence_after(); }
         // dQ_i = dS K      (A = dS^T read MN-major: M = queries contiguous, K = key rows; B = K MN-major)
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
@@ -160,109 +177,148 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_commit(&bar[BB_QE + st]);
       }
     }
-  } else if (warp < 4) {
-    // ===================== elementwise warpgroup: thread == key row =====================
-    const int quarter = warp;
+  } else {
+    // ===================== elementwise warpgroups: thread == key row, warpgroup w == 64 query columns =====================
+    const int wg = warp >> 2;
+    const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t tSt = tmem_base + lane_base + kColSt, tDPt = tmem_base + lane_base + kColDPt;
     const bool key_ok = (j * kBT + r) < p.nk;
-    const float scale = p.scale, scale2 = p.scale2;
+    const bool keys_full = (j + 1) * kBT <= p.nk;
+    const float scale2 = p.scale2;
+    const float2 scale2v = make_float2(scale2, scale2);
+    uint8_t* dq_stage = smem + L::kDQ + wg * (kBT * 32 * 4);
 
     auto drain_dq = [&](int i) {
       mbar_wait(&bar[BB_DQF], i & 1, 31);
       tc_fence_after();
-      const int q = i * kBT + r;     // here the lane is a query row of tile i
-      float* dst = p.dq_accum + ((long long)bh * p.nq_pad + q) * HD;
-#pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + lane_base + kColDQ + c, v);
-        tmem_ld_wait();
-        if (q < p.nq) {
-#pragma unroll
-          for (int t = 0; t < 32; t += 4)
-            atomicAdd(reinterpret_cast<float4*>(dst + c + t),
-                      make_float4(__uint_as_float(v[t]), __uint_as_float(v[t + 1]), __uint_as_float(v[t + 2]), __uint_as_float(v[t + 3])));
-        }
-      }
+      if ((threadIdx.x & 127) == 0) bulk_wait_read<0>();      // previous reduce has finished reading the staging tile
+      named_bar_sync(1 + wg, 128);
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + lane_base + kColDQ + wg * 32, v);   // lane = query row of tile i, 32 of the 64 d columns
+      tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bar[BB_DQE]);
+      mbar_arrive(&bar[BB_DQFREE]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<uint4*>(dq_stage + sw128_offset(r, k)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + wg, 128);
+      if ((threadIdx.x & 127) == 0) {
+        tma_reduce_add_2d(&tmDQ, dq_stage, wg * 32, bh * p.nq_pad + i * kBT);
+        bulk_commit();
+      }
     };
 
     for (int i = 0; i < nQ; ++i) {
-      const int st = i & 1;
+      const int st = i % kQStages;
       const uint8_t* stage = smem + L::kQ + st * L::kQStage;
-      const float* s_lse = reinterpret_cast<const float*>(stage + 2 * L::kTile);
+      const float* s_lse = reinterpret_cast<const float*>(stage + 2 * L::kTile) + wg * 64;
       const float* s_delta = s_lse + kBT;
-      uint8_t* dsbuf = smem + L::kDS + (i & 1) * (kBT * kBT * 2);
-      mbar_wait(&bar[BB_QF + st], (i >> 1) & 1, 32);   // lse/delta for this query tile are in smem
+      const int q_valid = p.nq - i * kBT - wg * 64;        // this warpgroup's columns >= q_valid are padding
+      const bool full = keys_full && q_valid >= 64;
+      float2 pv[32];                                       // P^T row slice, fp32, lives across phase A -> B
+
+      // ---------------- phase A: P^T = exp2(S^T * scale2 - lse2)
+      mbar_wait(&bar[BB_QF + st], (i / kQStages) & 1, 32);  // lse/delta of this query tile are in smem
       mbar_wait(&bar[BB_ST], i & 1, 33);
       tc_fence_after();
-      const int q_valid = p.nq - i * kBT;               // columns >= q_valid are padding
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32(tSt + c * 32, sv);
-        tmem_ld_32x32(tDPt + c * 32, dv);
+      {
+        uint32_t sv[64];
+        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+        tmem_ld_32x32(tmem_base + lane_base + kColSt + wg * 64, s0);
+        tmem_ld_32x32(tmem_base + lane_base + kColSt + wg * 64 + 32, s1);
         tmem_ld_wait();
-        uint32_t ppk[16], dpk[16];
+        tc_fence_before();
+        mbar_arrive(&bar[BB_STFREE]);
+        uint32_t ppk[32];
 #pragma unroll
-        for (int t = 0; t < 32; t += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(s_lse + c * 32 + t);
-          const float4 d4 = *reinterpret_cast<const float4*>(s_delta + c * 32 + t);
-          const float lse[4] = {l4.x, l4.y, l4.z, l4.w};
-          const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
-          float pv[4], ds[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const bool ok = key_ok && (c * 32 + t + e) < q_valid;
-            const float pe = ex2_approx(fmaf(__uint_as_float(sv[t + e]), scale2, -lse[e]));
-            pv[e] = ok ? pe : 0.f;
-            ds[e] = ok ? pe * (__uint_as_float(dv[t + e]) - dl[e]) * scale : 0.f;
+        for (int t = 0; t < 64; t += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(s_lse + t);
+          const float2 a = ffma2(make_float2(__uint_as_float(sv[t]), __uint_as_float(sv[t + 1])), scale2v, make_float2(-l4.x, -l4.y));
+          const float2 c = ffma2(make_float2(__uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3])), scale2v, make_float2(-l4.z, -l4.w));
+          float2 e0 = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+          float2 e1 = make_float2(ex2_approx(c.x), ex2_approx(c.y));
+          if (!full) {
+            e0.x = (key_ok && t + 0 < q_valid) ? e0.x : 0.f;
+            e0.y = (key_ok && t + 1 < q_valid) ? e0.y : 0.f;
+            e1.x = (key_ok && t + 2 < q_valid) ? e1.x : 0.f;
+            e1.y = (key_ok && t + 3 < q_valid) ? e1.y : 0.f;
           }
-          ppk[(t >> 1)] = pack_bf16(pv[0], pv[1]);
-          ppk[(t >> 1) + 1] = pack_bf16(pv[2], pv[3]);
-          dpk[(t >> 1)] = pack_bf16(ds[0], ds[1]);
-          dpk[(t >> 1) + 1] = pack_bf16(ds[2], ds[3]);
+          pv[t >> 1] = e0;
+          pv[(t >> 1) + 1] = e1;
+          ppk[t >> 1] = pack_bf16(e0.x, e0.y);
+          ppk[(t >> 1) + 1] = pack_bf16(e1.x, e1.y);
         }
-        tmem_st_32x16(tSt + c * 16, ppk);   // P^T over the S^T columns already consumed
-        uint8_t* sub = dsbuf + (c >> 1) * 16384;
+        tmem_st_32x32(tmem_base + lane_base + kColPt + wg * 32, ppk);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&bar[BB_PT]);
+      }
+
+      // ---------------- drain dQ(i-1) while the tensor pipe works on dV(i) / dP^T(i)
+      if (i > 0) drain_dq(i - 1);      // also guarantees dK(i-1)/dQ(i-1) are done reading the dS^T tile
+
+      // ---------------- phase B: dS^T = P^T * (dP^T - delta)
+      mbar_wait(&bar[BB_DPT], i & 1, 34);
+      tc_fence_after();
+      {
+        uint32_t dv[64];
+        uint32_t(&d0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dv[0]);
+        uint32_t(&d1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dv[32]);
+        tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64, d0);
+        tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64 + 32, d1);
+        tmem_ld_wait();
+        uint8_t* sub = smem + L::kDS + wg * 16384;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t off = sw128_offset(r, (c & 1) * 4 + k);
-          *reinterpret_cast<uint4*>(sub + off) = make_uint4(dpk[4 * k], dpk[4 * k + 1], dpk[4 * k + 2], dpk[4 * k + 3]);
+        for (int k = 0; k < 8; ++k) {       // 8 queries (16 B of bf16) per step
+          uint32_t w4[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int t = 8 * k + 4 * u;
+            const float4 d4 = *reinterpret_cast<const float4*>(s_delta + t);
+            float2 x0 = fadd2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), make_float2(-d4.x, -d4.y));
+            float2 x1 = fadd2(make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])), make_float2(-d4.z, -d4.w));
+            x0 = fmul2(x0, pv[t >> 1]);
+            x1 = fmul2(x1, pv[(t >> 1) + 1]);
+            if (!full) {   // padded delta may be garbage: 0 * NaN must not leak
+              x0.x = (key_ok && t + 0 < q_valid) ? x0.x : 0.f;
+              x0.y = (key_ok && t + 1 < q_valid) ? x0.y : 0.f;
+              x1.x = (key_ok && t + 2 < q_valid) ? x1.x : 0.f;
+              x1.y = (key_ok && t + 3 < q_valid) ? x1.y : 0.f;
+            }
+            w4[2 * u] = pack_bf16(x0.x, x0.y);
+            w4[2 * u + 1] = pack_bf16(x1.x, x1.y);
+          }
+          *reinterpret_cast<uint4*>(sub + sw128_offset(r, k)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
       }
-      tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bar[BB_DS]);
-      if (i > 0) drain_dq(i - 1);
     }
-    drain_dq(nQ - 1);   // also implies dV and dK are complete (commit covers all earlier MMAs)
+    drain_dq(nQ - 1);   // the commit behind BB_DQF covers every earlier MMA: dV and dK are complete too
+    if ((threadIdx.x & 127) == 0) bulk_wait<0>();
 
-    // ---- epilogue: dV, dK -> bf16 -> global
+    // ---- epilogue: dV, dK (x softmax scale) -> bf16 -> global; warpgroup w writes d columns [32w, 32w+32)
     const int key = j * kBT + r;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD;
-      const uint32_t tcol = tmem_base + lane_base + (which == 0 ? kColDV : kColDK);
+      bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD + wg * 32;
+      const float mul = which == 0 ? 1.0f : p.scale;
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 32, v);
+      tmem_ld_wait();
+      if (key_ok) {
 #pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tcol + c, v);
-        tmem_ld_wait();
-        if (key_ok) {
-#pragma unroll
-          for (int t = 0; t < 32; t += 8) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(v[t]), __uint_as_float(v[t + 1]));
-            u.y = pack_bf16(__uint_as_float(v[t + 2]), __uint_as_float(v[t + 3]));
-            u.z = pack_bf16(__uint_as_float(v[t + 4]), __uint_as_float(v[t + 5]));
-            u.w = pack_bf16(__uint_as_float(v[t + 6]), __uint_as_float(v[t + 7]));
-            *reinterpret_cast<uint4*>(dst + c + t) = u;
-          }
+        for (int t = 0; t < 32; t += 8) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[t]) * mul, __uint_as_float(v[t + 1]) * mul);
+          u.y = pack_bf16(__uint_as_float(v[t + 2]) * mul, __uint_as_float(v[t + 3]) * mul);
+          u.z = pack_bf16(__uint_as_float(v[t + 4]) * mul, __uint_as_float(v[t + 5]) * mul);
+          u.w = pack_bf16(__uint_as_float(v[t + 6]) * mul, __uint_as_float(v[t + 7]) * mul);
+          *reinterpret_cast<uint4*>(dst + t) = u;
         }
       }
     }
@@ -270,7 +326,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -295,7 +351,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
 
 // dq_accum f32 [B,H,nq_pad,64] -> dq bf16 [B*nq, lddq] (column h*64 + d); 8 elements per thread
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq,
-                                                              int batch, int heads, int nq, int nq_pad) {
+                                                              int batch, int heads, int nq, int nq_pad, float scale) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*nq*H*8
   const long long total = (long long)batch * nq * heads * 8;
   if (idx >= total) return;
@@ -306,7 +362,8 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
   const int b = (int)(tok / nq), q = (int)(tok - (long long)b * nq);
   const float* src = acc + (((long long)b * heads + h) * nq_pad + q) * 64 + part * 8;
   const float4 x = __ldg(reinterpret_cast<const float4*>(src)), y = __ldg(reinterpret_cast<const float4*>(src + 4));
-  uint4 u = make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+  uint4 u = make_uint4(pack_bf16(x.x * scale, x.y * scale), pack_bf16(x.z * scale, x.w * scale), pack_bf16(y.x * scale, y.y * scale),
+                       pack_bf16(y.z * scale, y.w * scale));
   *reinterpret_cast<uint4*>(dq + tok * lddq + h * 64 + part * 8) = u;
 }
 
@@ -333,8 +390,9 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
                                                                   a->heads, a->nq, nq_pad);
     HVC_LAUNCH_CHECK();
   }
-  CUtensorMap tmQ, tmK, tmV, tmDO;
+  CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int rc;
+  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, 32, kBT, true))) return rc;
   if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kBT, true))) return rc;
   if ((rc = make_tmap_2d(&tmDO, a->d_o, 2, (uint64_t)a->batch * a->nq, width, a->lddo, HD, kBT, true))) return rc;
   if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kBT, true))) return rc;
@@ -342,7 +400,7 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   AttnBwdKArgs ka;
   ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk; ka.nq_pad = nq_pad;
   ka.n_q_tiles = nq_pad / kBT;
-  ka.lse2 = a->lse; ka.delta = a->delta; ka.dq_accum = a->dq_accum;
+  ka.lse2 = a->lse; ka.delta = a->delta;
   ka.dk = reinterpret_cast<bf16*>(a->dk); ka.lddk = a->lddk;
   ka.dv = reinterpret_cast<bf16*>(a->dv); ka.lddv = a->lddv;
   ka.scale = a->scale; ka.scale2 = a->scale * 1.4426950408889634f;
@@ -352,12 +410,12 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
     configured = true;
   }
   dim3 grid((a->nk + kBT - 1) / kBT, a->batch * a->heads);
-  attn_bwd_kernel<HD><<<grid, kBwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, tmDO, ka);
+  attn_bwd_kernel<HD><<<grid, kBwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, ka);
   HVC_LAUNCH_CHECK();
   {
     const long long threads = (long long)a->batch * a->nq * a->heads * 8;
     attn_dq_convert_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a->dq_accum, reinterpret_cast<bf16*>(a->dq), a->lddq,
-                                                                             a->batch, a->heads, a->nq, nq_pad);
+                                                                             a->batch, a->heads, a->nq, nq_pad, a->scale);
     HVC_LAUNCH_CHECK();
   }
   return HVC_OK;

@@ -20,6 +20,8 @@ CASES = {
     "bwd_ragged": (2, 2, 200, 72, 64, False),
     "bwd_self_packed": (2, 4, 1024, 1024, 64, True),
     "bwd_4096": (2, 4, 4096, 4096, 64, True),
+    "perf_32k": (1, 4, 32768, 32768, 64, True),
+    "perf_cross": (2, 4, 32768, 4096, 64, False),
 }
 
 
@@ -29,10 +31,42 @@ def ref_attn(q, k, v, scale):
     return p @ v.float(), torch.logsumexp(s, -1)
 
 
+def run_perf(name):
+    import torch
+    from hybrid_vit_cascade_b200 import kernels as K
+    B, H, nq, nk, d, packed = CASES[name]
+    C = H * d
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(B * nq, C, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B * nk, C, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B * nk, C, device="cuda", generator=g).bfloat16()
+    d_o = torch.randn(B * nq, C, device="cuda", generator=g).bfloat16()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    scale = d ** -0.5
+    o, lse2 = K.attn_fwd(q, k, v, B, H, nq, nk, d, scale)
+    def t(fn, n=5):
+        for _ in range(2):
+            fn()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(n):
+            fn()
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / n
+    mf = t(lambda: K.attn_fwd(q, k, v, B, H, nq, nk, d, scale))
+    mb = t(lambda: K.attn_bwd(q, k, v, o, lse2, d_o, B, H, nq, nk, d, scale, dq, dk, dv))
+    fl = 4.0 * B * H * nq * nk * d
+    print(f"PERF {name}: fwd {mf:.3f} ms {fl/mf/1e9:.1f} TFLOP/s | bwd {mb:.3f} ms {2.5*fl/mb/1e9:.1f} TFLOP/s")
+    return 0
+
+
 def run_case(name, bwd=False):
     global torch
     import torch
     from hybrid_vit_cascade_b200 import kernels as K
+    if name.startswith("perf"):
+        return run_perf(name)
     B, H, nq, nk, d, packed = CASES[name]
     g = torch.Generator(device="cuda").manual_seed(3)
     C = H * d
