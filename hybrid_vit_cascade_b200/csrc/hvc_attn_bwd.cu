@@ -29,7 +29,7 @@ constexpr int kQStages = 3;
 
 struct AttnBwdKArgs {
   int batch, heads, nq, nk, nq_pad, n_q_tiles;
-  const float* lse2; const float* delta;   // [B, H, nq_pad]
+  const float* nlse2; const float* delta;  // [B, H, nq_pad] each: -lse2 (written by the pre-pass) and rowsum(dO*O)
   bf16* dk; long long lddk;
   bf16* dv; long long lddv;
   float scale, scale2;
@@ -49,6 +49,60 @@ struct BwdSmem {
 };
 
 enum { BB_KV = 0, BB_QF = 1, BB_QE = 4, BB_ST = 7, BB_STFREE = 8, BB_PT = 9, BB_DPT = 10, BB_DS = 11, BB_DQF = 12, BB_DQFREE = 13, BB_N = 14 };
+
+// ---- elementwise phases of one (key tile, query tile) pair; thread == key row, 64 query columns per thread.
+// FULL = no padding rows/columns in this pair (the masked variant is a separate code path: selects cost issue slots).
+// Phase A: P^T = exp2(S^T*scale2 - lse2); the pre-pass stores -lse2 so the argument is a single FFMA2.
+template <bool FULL>
+__device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[64], uint32_t lse_saddr, float2 nss, bool key_ok, int q_valid,
+                                            float2 (&pv)[32], uint32_t (&ppk)[32]) {
+#pragma unroll
+  for (int t = 0; t < 64; t += 4) {
+    const float4 l4 = lds_f4(lse_saddr + t * 4);
+    const float2 a = ffma2(make_float2(__uint_as_float(sv[t]), __uint_as_float(sv[t + 1])), nss, make_float2(l4.x, l4.y));
+    const float2 c = ffma2(make_float2(__uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3])), nss, make_float2(l4.z, l4.w));
+    float2 e0 = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    float2 e1 = make_float2(ex2_approx(c.x), ex2_approx(c.y));
+    if (!FULL) {
+      e0.x = (key_ok && t + 0 < q_valid) ? e0.x : 0.f;
+      e0.y = (key_ok && t + 1 < q_valid) ? e0.y : 0.f;
+      e1.x = (key_ok && t + 2 < q_valid) ? e1.x : 0.f;
+      e1.y = (key_ok && t + 3 < q_valid) ? e1.y : 0.f;
+    }
+    pv[t >> 1] = e0;
+    pv[(t >> 1) + 1] = e1;
+    ppk[t >> 1] = pack_bf16(e0.x, e0.y);
+    ppk[(t >> 1) + 1] = pack_bf16(e1.x, e1.y);
+  }
+}
+// Phase B: dS^T = P^T * (dP^T - delta) -> swizzled smem sub-tile (8 x 16-byte chunks of this thread's row)
+template <bool FULL>
+__device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[64], uint32_t delta_saddr, const float2 (&pv)[32], bool key_ok,
+                                            int q_valid, uint32_t sub_saddr, int r) {
+  const float2 neg1 = make_float2(-1.f, -1.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t w4[4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int t = 8 * k + 4 * u;
+      const float4 d4 = lds_f4(delta_saddr + t * 4);
+      float2 x0 = ffma2(make_float2(d4.x, d4.y), neg1, make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])));
+      float2 x1 = ffma2(make_float2(d4.z, d4.w), neg1, make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])));
+      x0 = fmul2(x0, pv[t >> 1]);
+      x1 = fmul2(x1, pv[(t >> 1) + 1]);
+      if (!FULL) {   // padded delta may be garbage: 0 * NaN must not leak
+        x0.x = (key_ok && t + 0 < q_valid) ? x0.x : 0.f;
+        x0.y = (key_ok && t + 1 < q_valid) ? x0.y : 0.f;
+        x1.x = (key_ok && t + 2 < q_valid) ? x1.x : 0.f;
+        x1.y = (key_ok && t + 3 < q_valid) ? x1.y : 0.f;
+      }
+      w4[2 * u] = pack_bf16(x0.x, x0.y);
+      w4[2 * u + 1] = pack_bf16(x1.x, x1.y);
+    }
+    sts_u4(sub_saddr + sw128_offset(r, k), w4[0], w4[1], w4[2], w4[3]);
+  }
+}
 
 template <int HD>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -103,79 +157,89 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive_expect_tx(&bar[BB_QF + st], 2 * L::kTile + 2 * kBT * 4);
         tma_load_2d(base, &tmQ, &bar[BB_QF + st], h * HD, b * p.nq + i * kBT, kEvictLast);
         tma_load_2d(base + L::kTile, &tmDO, &bar[BB_QF + st], h * HD, b * p.nq + i * kBT, kEvictLast);
-        bulk_load_1d(base + 2 * L::kTile, p.lse2 + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
+        bulk_load_1d(base + 2 * L::kTile, p.nlse2 + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
         bulk_load_1d(base + 2 * L::kTile + kBT * 4, p.delta + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
       }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t id_s = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);      // S^T, dP^T
-      constexpr uint32_t id_dv = make_idesc_bf16(kBT, HD, kMajorK, kMajorMN);     // dV (A in TMEM), dK (A K-major smem)
-      constexpr uint32_t id_dq = make_idesc_bf16(kBT, HD, kMajorMN, kMajorMN);    // dQ
-      const uint32_t sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
-      const uint32_t sQ0 = smem_u32(smem + L::kQ), sDS = smem_u32(smem + L::kDS);
-      auto issue_st = [&](int st) {
-        const uint32_t sQ = sQ0 + st * L::kQStage;
+    // ===================== MMA issuer (whole warp runs the loop; only the elected lane issues) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t id_s = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);      // S^T, dP^T
+    constexpr uint32_t id_dv = make_idesc_bf16(kBT, HD, kMajorK, kMajorMN);     // dV (A in TMEM), dK (A K-major smem)
+    constexpr uint32_t id_dq = make_idesc_bf16(kBT, HD, kMajorMN, kMajorMN);    // dQ
+    const uint32_t sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
+    const uint32_t sQ0 = smem_u32(smem + L::kQ), sDS = smem_u32(smem + L::kDS);
+    auto issue_st = [&](int st) {
+      const uint32_t sQ = sQ0 + st * L::kQStage;
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
           umma_ss(tmem_base + kColSt, make_sdesc_sw128(sK + k16 * 32, 16, 1024), make_sdesc_sw128(sQ + k16 * 32, 16, 1024), id_s,
                   k16 > 0 ? 1u : 0u);
-      };
-      auto issue_dpt = [&](int st) {
-        const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
+      }
+    };
+    auto issue_dpt = [&](int st) {
+      const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
           umma_ss(tmem_base + kColDPt, make_sdesc_sw128(sV + k16 * 32, 16, 1024), make_sdesc_sw128(sDO + k16 * 32, 16, 1024), id_s,
                   k16 > 0 ? 1u : 0u);
-      };
-      mbar_wait(&bar[BB_KV], 0, 20);
-      mbar_wait(&bar[BB_QF + 0], 0, 21);
-      tc_fence_after();
-      issue_st(0);
-      tc_commit(&bar[BB_ST]);
-      issue_dpt(0);
-      tc_commit(&bar[BB_DPT]);
-      for (int i = 0; i < nQ; ++i) {
-        const int st = i % kQStages;
-        const int st1 = (i + 1) % kQStages;
-        const uint32_t sQ = sQ0 + st * L::kQStage, sDO = sQ + L::kTile;
-        // (1) S^T(i+1) as soon as the warpgroups have pulled S^T(i) out of TMEM
-        if (i + 1 < nQ) {
-          mbar_wait(&bar[BB_STFREE], i & 1, 22);
-          mbar_wait(&bar[BB_QF + st1], ((i + 1) / kQStages) & 1, 23);
-          tc_fence_after();
-          issue_st(st1);
-          tc_commit(&bar[BB_ST]);
-        }
-        // (2) dV += P^T dO     (A = P^T in TMEM, 8 columns per K=16 step; B = dO MN-major)
-        mbar_wait(&bar[BB_PT], i & 1, 24);
+      }
+    };
+    auto commit = [&](int barrier) { if (leader) tc_commit(&bar[barrier]); };
+    mbar_wait(&bar[BB_KV], 0, 20);
+    mbar_wait(&bar[BB_QF + 0], 0, 21);
+    tc_fence_after();
+    issue_st(0);
+    commit(BB_ST);
+    issue_dpt(0);
+    commit(BB_DPT);
+    for (int i = 0; i < nQ; ++i) {
+      const int st = i % kQStages;
+      const int st1 = (i + 1) % kQStages;
+      const uint32_t sQ = sQ0 + st * L::kQStage, sDO = sQ + L::kTile;
+      // (1) S^T(i+1) as soon as the warpgroups have pulled S^T(i) out of TMEM
+      if (i + 1 < nQ) {
+        mbar_wait(&bar[BB_STFREE], i & 1, 22);
+        mbar_wait(&bar[BB_QF + st1], ((i + 1) / kQStages) & 1, 23);
         tc_fence_after();
+        issue_st(st1);
+        commit(BB_ST);
+      }
+      // (2) dV += P^T dO     (A = P^T in TMEM, 8 columns per K=16 step; B = dO MN-major)
+      mbar_wait(&bar[BB_PT], i & 1, 24);
+      tc_fence_after();
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ts(tmem_base + kColDV, tmem_base + kColPt + k16 * 8, make_sdesc_sw128(sDO + k16 * 2048, 8192, 1024), id_dv,
                   (i > 0 || k16 > 0) ? 1u : 0u);
-        // (3) once dS^T(i) is in smem (and dP^T(i) consumed): dP^T(i+1), dK, dQ
-        mbar_wait(&bar[BB_DS], i & 1, 25);
-        tc_fence_after();
-        if (i + 1 < nQ) {
-          issue_dpt(st1);
-          tc_commit(&bar[BB_DPT]);
-        }
-        // dK += dS^T Q     (A = dS^T K-major: two 64-query sub-tiles; B = Q MN-major)
+      }
+      // (3) once dS^T(i) is in smem (and dP^T(i) consumed): dP^T(i+1), dK, dQ
+      mbar_wait(&bar[BB_DS], i & 1, 25);
+      tc_fence_after();
+      if (i + 1 < nQ) {
+        issue_dpt(st1);
+        commit(BB_DPT);
+      }
+      // dK += dS^T Q     (A = dS^T K-major: two 64-query sub-tiles; B = Q MN-major)
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS + (k16 >> 2) * 16384 + (k16 & 3) * 32, 16, 1024),
                   make_sdesc_sw128(sQ + k16 * 2048, 8192, 1024), id_dv, (i > 0 || k16 > 0) ? 1u : 0u);
-        if (i > 0) { mbar_wait(&bar[BB_DQFREE], (i - 1) & 1, 26); tc_fence_after(); }
-        // dQ_i = dS K      (A = dS^T read MN-major: M = queries contiguous, K = key rows; B = K MN-major)
+      }
+      if (i > 0) { mbar_wait(&bar[BB_DQFREE], (i - 1) & 1, 26); tc_fence_after(); }
+      // dQ_i = dS K      (A = dS^T read MN-major: M = queries contiguous, K = key rows; B = K MN-major)
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ss(tmem_base + kColDQ, make_sdesc_sw128(sDS + k16 * 2048, 16384, 1024),
                   make_sdesc_sw128(sK + k16 * 2048, 8192, 1024), id_dq, k16 > 0 ? 1u : 0u);
-        tc_commit(&bar[BB_DQF]);
-        tc_commit(&bar[BB_QE + st]);
       }
+      commit(BB_DQF);
+      commit(BB_QE + st);
     }
   } else {
     // ===================== elementwise warpgroups: thread == key row, warpgroup w == 64 query columns =====================
@@ -186,8 +250,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool key_ok = (j * kBT + r) < p.nk;
     const bool keys_full = (j + 1) * kBT <= p.nk;
     const float scale2 = p.scale2;
-    const float2 scale2v = make_float2(scale2, scale2);
     uint8_t* dq_stage = smem + L::kDQ + wg * (kBT * 32 * 4);
+    const uint32_t dq_saddr = smem_u32(dq_stage);
 
     auto drain_dq = [&](int i) {
       mbar_wait(&bar[BB_DQF], i & 1, 31);
@@ -200,8 +264,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(&bar[BB_DQFREE]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        *reinterpret_cast<uint4*>(dq_stage + sw128_offset(r, k)) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      for (int k = 0; k < 8; ++k) sts_u4(dq_saddr + sw128_offset(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       fence_proxy_async_smem();
       named_bar_sync(1 + wg, 128);
       if ((threadIdx.x & 127) == 0) {
@@ -210,11 +273,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
 
+    const float2 nss = make_float2(scale2, scale2);
+    const uint32_t sub_saddr = smem_u32(smem + L::kDS + wg * 16384);
     for (int i = 0; i < nQ; ++i) {
       const int st = i % kQStages;
-      const uint8_t* stage = smem + L::kQ + st * L::kQStage;
-      const float* s_lse = reinterpret_cast<const float*>(stage + 2 * L::kTile) + wg * 64;
-      const float* s_delta = s_lse + kBT;
+      const uint32_t lse_saddr = smem_u32(smem + L::kQ + st * L::kQStage + 2 * L::kTile) + wg * 64 * 4;
+      const uint32_t delta_saddr = lse_saddr + kBT * 4;
       const int q_valid = p.nq - i * kBT - wg * 64;        // this warpgroup's columns >= q_valid are padding
       const bool full = keys_full && q_valid >= 64;
       float2 pv[32];                                       // P^T row slice, fp32, lives across phase A -> B
@@ -233,24 +297,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         mbar_arrive(&bar[BB_STFREE]);
         uint32_t ppk[32];
-#pragma unroll
-        for (int t = 0; t < 64; t += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(s_lse + t);
-          const float2 a = ffma2(make_float2(__uint_as_float(sv[t]), __uint_as_float(sv[t + 1])), scale2v, make_float2(-l4.x, -l4.y));
-          const float2 c = ffma2(make_float2(__uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3])), scale2v, make_float2(-l4.z, -l4.w));
-          float2 e0 = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-          float2 e1 = make_float2(ex2_approx(c.x), ex2_approx(c.y));
-          if (!full) {
-            e0.x = (key_ok && t + 0 < q_valid) ? e0.x : 0.f;
-            e0.y = (key_ok && t + 1 < q_valid) ? e0.y : 0.f;
-            e1.x = (key_ok && t + 2 < q_valid) ? e1.x : 0.f;
-            e1.y = (key_ok && t + 3 < q_valid) ? e1.y : 0.f;
-          }
-          pv[t >> 1] = e0;
-          pv[(t >> 1) + 1] = e1;
-          ppk[t >> 1] = pack_bf16(e0.x, e0.y);
-          ppk[(t >> 1) + 1] = pack_bf16(e1.x, e1.y);
-        }
+        if (full) bwd_phase_a<true>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk);
+        else      bwd_phase_a<false>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk);
         tmem_st_32x32(tmem_base + lane_base + kColPt + wg * 32, ppk);
         tmem_st_wait();
         tc_fence_before();
@@ -270,29 +318,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64, d0);
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64 + 32, d1);
         tmem_ld_wait();
-        uint8_t* sub = smem + L::kDS + wg * 16384;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {       // 8 queries (16 B of bf16) per step
-          uint32_t w4[4];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int t = 8 * k + 4 * u;
-            const float4 d4 = *reinterpret_cast<const float4*>(s_delta + t);
-            float2 x0 = fadd2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), make_float2(-d4.x, -d4.y));
-            float2 x1 = fadd2(make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])), make_float2(-d4.z, -d4.w));
-            x0 = fmul2(x0, pv[t >> 1]);
-            x1 = fmul2(x1, pv[(t >> 1) + 1]);
-            if (!full) {   // padded delta may be garbage: 0 * NaN must not leak
-              x0.x = (key_ok && t + 0 < q_valid) ? x0.x : 0.f;
-              x0.y = (key_ok && t + 1 < q_valid) ? x0.y : 0.f;
-              x1.x = (key_ok && t + 2 < q_valid) ? x1.x : 0.f;
-              x1.y = (key_ok && t + 3 < q_valid) ? x1.y : 0.f;
-            }
-            w4[2 * u] = pack_bf16(x0.x, x0.y);
-            w4[2 * u + 1] = pack_bf16(x1.x, x1.y);
-          }
-          *reinterpret_cast<uint4*>(sub + sw128_offset(r, k)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        }
+        if (full) bwd_phase_b<true>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r);
+        else      bwd_phase_b<false>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -334,8 +361,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]; one warp per (token, head), HD = 64 -> 2 elements per lane
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o,
-                                                         long long lddo, float* __restrict__ delta, int batch, int heads, int nq,
-                                                         int nq_pad) {
+                                                         long long lddo, const float* __restrict__ lse2, float* __restrict__ delta,
+                                                         float* __restrict__ nlse2, int batch, int heads, int nq, int nq_pad) {
   const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = (long long)batch * nq * heads;
@@ -346,7 +373,11 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   const float2 a = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(o + tok * ldo + h * 64 + 2 * lane)));
   const float2 g = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(d_o + tok * lddo + h * 64 + 2 * lane)));
   const float s = warp_sum(a.x * g.x + a.y * g.y);
-  if (lane == 0) delta[((long long)b * heads + h) * nq_pad + q] = s;
+  if (lane == 0) {
+    const long long idx = ((long long)b * heads + h) * nq_pad + q;
+    delta[idx] = s;
+    nlse2[idx] = -lse2[idx];
+  }
 }
 
 // dq_accum f32 [B,H,nq_pad,64] -> dq bf16 [B*nq, lddq] (column h*64 + d); 8 elements per thread
@@ -386,8 +417,9 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   {
     const long long warps = (long long)a->batch * a->nq * a->heads;
     attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->ldo,
-                                                                  reinterpret_cast<const bf16*>(a->d_o), a->lddo, a->delta, a->batch,
-                                                                  a->heads, a->nq, nq_pad);
+                                                                  reinterpret_cast<const bf16*>(a->d_o), a->lddo, a->lse, a->delta,
+                                                                  a->delta + (long long)a->batch * a->heads * nq_pad, a->batch, a->heads,
+                                                                  a->nq, nq_pad);
     HVC_LAUNCH_CHECK();
   }
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
@@ -400,7 +432,7 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   AttnBwdKArgs ka;
   ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk; ka.nq_pad = nq_pad;
   ka.n_q_tiles = nq_pad / kBT;
-  ka.lse2 = a->lse; ka.delta = a->delta;
+  ka.nlse2 = a->delta + (long long)a->batch * a->heads * nq_pad; ka.delta = a->delta;
   ka.dk = reinterpret_cast<bf16*>(a->dk); ka.lddk = a->lddk;
   ka.dv = reinterpret_cast<bf16*>(a->dv); ka.lddv = a->lddv;
   ka.scale = a->scale; ka.scale2 = a->scale * 1.4426950408889634f;

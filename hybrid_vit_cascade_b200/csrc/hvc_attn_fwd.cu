@@ -45,6 +45,75 @@ struct FwdSmem {
 
 enum { BAR_Q = 0, BAR_KF = 1, BAR_KE = 4, BAR_VF = 7, BAR_VE = 10, BAR_SF = 13, BAR_PF = 15, BAR_OD = 17, BAR_N = 19 };
 
+// ---- softmax passes over one 128-column S tile held in TMEM (thread == row).  MASKED = last, partial key tile.
+template <bool MASKED>
+__device__ __forceinline__ float softmax_rowmax(uint32_t tS, int tail) {
+  float a0 = -INFINITY, a1 = -INFINITY;
+  uint32_t u0[32], u1[32];
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    tmem_ld_32x32(tS + half * 64, u0);
+    tmem_ld_32x32(tS + half * 64 + 32, u1);
+    tmem_ld_wait();
+    if (MASKED) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        a0 = fmaxf(a0, half * 64 + c < tail ? __uint_as_float(u0[c]) : -INFINITY);
+        a1 = fmaxf(a1, half * 64 + 32 + c < tail ? __uint_as_float(u1[c]) : -INFINITY);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        a0 = fmax3(a0, __uint_as_float(u0[c]), __uint_as_float(u0[c + 1]));
+        a1 = fmax3(a1, __uint_as_float(u1[c]), __uint_as_float(u1[c + 1]));
+      }
+    }
+  }
+  return fmaxf(a0, a1);
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint32_t tP, int c0, int tail, float2 scale2v, float2 neg_m,
+                                                  float2& sum) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int c = 0; c < 32; c += 2) {
+    const float2 a = ffma2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), scale2v, neg_m);
+    float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    if (MASKED) {
+      e.x = (c0 + c < tail) ? e.x : 0.f;
+      e.y = (c0 + c + 1 < tail) ? e.y : 0.f;
+    }
+    sum = fadd2(sum, e);
+    pk[c >> 1] = pack_bf16(e.x, e.y);
+  }
+  tmem_st_32x16(tP + (c0 >> 1), pk);   // P (bf16 pairs) over S columns that were already consumed
+}
+
+// P = exp2(S*scale2 - m): chunk c+1 is fetched from TMEM while chunk c is exponentiated.  The section between the
+// named-barrier sync and arrive is the warpgroup's turn on the MUFU pipe.
+template <bool MASKED>
+__device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2, float m, int turn_bar, int next_bar, bool hand_over) {
+  const float2 scale2v = make_float2(scale2, scale2), neg_m = make_float2(-m, -m);
+  float2 sum = make_float2(0.f, 0.f);
+  uint32_t bufa[32], bufb[32];
+  tmem_ld_32x32(tS, bufa);
+  named_bar_sync(turn_bar, 256);
+  tmem_ld_wait();
+  tmem_ld_32x32(tS + 32, bufb);
+  softmax_exp_chunk<MASKED>(bufa, tS, 0, tail, scale2v, neg_m, sum);
+  tmem_ld_wait();
+  tmem_ld_32x32(tS + 64, bufa);
+  softmax_exp_chunk<MASKED>(bufb, tS, 32, tail, scale2v, neg_m, sum);
+  tmem_ld_wait();
+  tmem_ld_32x32(tS + 96, bufb);
+  softmax_exp_chunk<MASKED>(bufa, tS, 64, tail, scale2v, neg_m, sum);
+  tmem_ld_wait();
+  softmax_exp_chunk<MASKED>(bufb, tS, 96, tail, scale2v, neg_m, sum);
+  if (hand_over) named_bar_arrive(next_bar, 256);
+  return sum.x + sum.y;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -106,48 +175,54 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKTile, kMajorK, kMajorK);
-      constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, HD, kMajorK, kMajorMN);
-      const uint32_t sQ = smem_u32(smem + L::kQ), sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
-      auto issue_s = [&](int x, int st) {   // S_x = Q_x K^T
+    // ===================== MMA issuer (whole warp runs the loop so address math stays on the uniform datapath;
+    // only the elected lane issues tcgen05.mma / commit) =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(kQTile, kKTile, kMajorK, kMajorK);
+    constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, HD, kMajorK, kMajorMN);
+    const uint32_t sQ = smem_u32(smem + L::kQ), sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
+    auto issue_s = [&](int x, int st) {   // S_x = Q_x K^T
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
           umma_ss(tmem_base + kColS + x * kKTile, make_sdesc_sw128(sQ + x * L::kTile + k16 * 32, 16, 1024),
                   make_sdesc_sw128(sK + st * L::kTile + k16 * 32, 16, 1024), idesc_s, k16 > 0 ? 1u : 0u);
-      };
-      auto issue_pv = [&](int x, int st, bool acc) {   // O_x (+)= P_x V   (P: TMEM, 8 columns per K=16 step)
+      }
+    };
+    auto issue_pv = [&](int x, int st, bool acc) {   // O_x (+)= P_x V   (P: TMEM, 8 columns per K=16 step)
+      if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < kKTile / 16; ++k16)
           umma_ts(tmem_base + kColO + x * HD, tmem_base + kColS + x * kKTile + k16 * 8,
                   make_sdesc_sw128(sV + st * L::kTile + k16 * 2048, 8192, 1024), idesc_o, (acc || k16 > 0) ? 1u : 0u);
-      };
-      mbar_wait(&bar[BAR_Q], 0, 20);
-      mbar_wait(&bar[BAR_KF + 0], 0, 21);
-      tc_fence_after();
-      issue_s(0, 0); tc_commit(&bar[BAR_SF + 0]);
-      issue_s(1, 0); tc_commit(&bar[BAR_SF + 1]);
-      tc_commit(&bar[BAR_KE + 0]);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
-        const int st1 = (j + 1) % kKvStages;
-        const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
-        const bool more = (j + 1 < n_tiles);
-        mbar_wait(&bar[BAR_VF + st], ph, 22);
-        for (int x = 0; x < 2; ++x) {
-          mbar_wait(&bar[BAR_PF + x], j & 1, 23);
-          tc_fence_after();
-          issue_pv(x, st, j > 0);
-          tc_commit(&bar[BAR_OD + x]);
-          if (x == 1) tc_commit(&bar[BAR_VE + st]);
-          if (more) {
-            if (x == 0) { mbar_wait(&bar[BAR_KF + st1], ph1, 24); tc_fence_after(); }
-            issue_s(x, st1);
-            tc_commit(&bar[BAR_SF + x]);
-            if (x == 1) tc_commit(&bar[BAR_KE + st1]);
-          }
+      }
+    };
+    auto commit = [&](int barrier) { if (leader) tc_commit(&bar[barrier]); };
+    mbar_wait(&bar[BAR_Q], 0, 20);
+    mbar_wait(&bar[BAR_KF + 0], 0, 21);
+    tc_fence_after();
+    issue_s(0, 0); commit(BAR_SF + 0);
+    issue_s(1, 0); commit(BAR_SF + 1);
+    commit(BAR_KE + 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
+      const int st1 = (j + 1) % kKvStages;
+      const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
+      const bool more = (j + 1 < n_tiles);
+      mbar_wait(&bar[BAR_VF + st], ph, 22);
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(&bar[BAR_PF + x], j & 1, 23);
+        tc_fence_after();
+        issue_pv(x, st, j > 0);
+        commit(BAR_OD + x);
+        if (x == 1) commit(BAR_VE + st);
+        if (more) {
+          if (x == 0) { mbar_wait(&bar[BAR_KF + st1], ph1, 24); tc_fence_after(); }
+          issue_s(x, st1);
+          commit(BAR_SF + x);
+          if (x == 1) commit(BAR_KE + st1);
         }
       }
     }
@@ -161,37 +236,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float scale2 = p.scale2;
     float m = -INFINITY, l = 0.f;
     const int tail = p.nk - (n_tiles - 1) * kKTile;   // valid keys in the last tile (1..128)
+    // The two warpgroups take turns in the MUFU-bound exp section (named barriers 1 and 2): while one runs
+    // exp2 the other waits for its next S tile, loads it and finds the row maximum.
+    if (x == 1) named_bar_arrive(1, 256);             // warpgroup A goes first
 
     for (int j = 0; j < n_tiles; ++j) {
+      const bool masked = (j == n_tiles - 1) && (tail < kKTile);
       mbar_wait(&bar[BAR_SF + x], j & 1, 30);
       tc_fence_after();
-      uint32_t s[128];
-      {
-        uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[0]);
-        uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[32]);
-        uint32_t(&s2)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[64]);
-        uint32_t(&s3)[32] = *reinterpret_cast<uint32_t(*)[32]>(&s[96]);
-        tmem_ld_32x32(tS, s0);
-        tmem_ld_32x32(tS + 32, s1);
-        tmem_ld_32x32(tS + 64, s2);
-        tmem_ld_32x32(tS + 96, s3);
-        tmem_ld_wait();
-      }
-      if (j == n_tiles - 1 && tail < kKTile) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c >= tail) s[c] = 0xff800000u;  // -inf
-      }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]), mx2 = __uint_as_float(s[2]),
-            mx3 = __uint_as_float(s[3]);
-#pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(s[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(s[c + 3]));
-      }
-      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale2);
+      // ---- pass 1: row maximum (S stays in TMEM; TMEM reads are cheap)
+      const float mx = masked ? softmax_rowmax<true>(tS, tail) : softmax_rowmax<false>(tS, tail);
+      const float m_new = fmaxf(m, mx * scale2);
       if (j == 0) {
         m = m_new;
       } else {
@@ -214,22 +269,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (need) { l *= f; m = m_new; }
         }
       }
-      const float neg_m = -m;
-      float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + c]), scale2, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + c + 1]), scale2, neg_m));
-          sum0 += p0;
-          sum1 += p1;
-          pk[c >> 1] = pack_bf16(p0, p1);
-        }
-        tmem_st_32x32(tS + hh * 32, pk);   // P (bf16 pairs) overwrites S columns already held in registers
-      }
-      l += sum0 + sum1;
+      // ---- pass 2 (my turn on the MUFU pipe): P = exp2(S*scale2 - m) -> TMEM, row sum
+      const bool hand_over = !(x == 1 && j == n_tiles - 1);
+      l += masked ? softmax_exp<true>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over)
+                  : softmax_exp<false>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar[BAR_PF + x]);

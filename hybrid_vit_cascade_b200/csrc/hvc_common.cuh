@@ -249,6 +249,18 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// explicit shared-space vector load (keeps LDS even when the pointer's provenance is lost to the compiler)
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 // ------------------------------------------------------------------ math
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -262,6 +274,12 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^(-x): the negation is folded into the MUFU source modifier by ptxas
+__device__ __forceinline__ float ex2_neg_approx(float x) {
+  float y;
+  asm("{\n\t.reg .f32 t;\n\tneg.ftz.f32 t, %1;\n\tex2.approx.ftz.f32 %0, t;\n\t}" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }

@@ -149,7 +149,7 @@ def attn_bwd(q, k, v, o, lse, d_o, B, H, nq, nk, d, scale, dq, dk, dv):
     _need_cuda(q, k, v, o, d_o)
     assert d_o.dtype == torch.bfloat16 and o.dtype == torch.bfloat16
     nq_pad = _pad128(nq)
-    delta = torch.empty(B, H, nq_pad, device=q.device, dtype=torch.float32)
+    delta = torch.empty(2, B, H, nq_pad, device=q.device, dtype=torch.float32)
     dq_accum = torch.zeros(B, H, nq_pad, d, device=q.device, dtype=torch.float32)
     args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
     args.o, args.ldo = o.data_ptr(), _row_major_2d(o, "o")

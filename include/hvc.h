@@ -99,8 +99,8 @@ int hvc_gemm(const hvc_gemm_args* args, void* stream);
  * columns are [head*head_dim, (head+1)*head_dim) starting at the given base pointer (so q, k, v may
  * all point into one [T, 3C] qkv projection output; ld* are the row pitches in elements).
  * lse: f32 [batch, heads, nq_pad] base-2 logsumexp of the scaled scores (forward output, backward
- * input), nq_pad = nq rounded up to 128.  delta: f32 [batch, heads, nq_pad] = rowsum(dO * O)
- * (scratch, written by hvc_attn_bwd).  dq_accum: f32 [batch, heads, nq_pad, head_dim] zero-filled
+ * input), nq_pad = nq rounded up to 128.  delta: f32 [2, batch, heads, nq_pad] scratch written by
+ * hvc_attn_bwd (plane 0 = rowsum(dO * O), plane 1 = -lse).  dq_accum: f32 [batch, heads, nq_pad, head_dim] zero-filled
  * scratch for the cross-CTA dQ reduction.
  * head_dim: 64.
  * ---------------------------------------------------------------------------------------------- */
