@@ -175,7 +175,9 @@ def test_expanded_input_is_embedded_once_and_exact():
     vol.grad = None
     y2 = m(vol.expand(3, -1, -1, -1, -1).contiguous(), ctx, cond)
     y2.sum().backward()
-    assert O.max_rel(y1, y2) < 1e-5      # not bit-equal: GroupNorm statistics are reduced with float atomics
+    # not bit-equal: GroupNorm statistics are reduced with float atomics whose grouping depends on the batch, and a
+    # last-bit difference there can flip the bf16 rounding of a few activations (1 bf16 ulp = 4e-3 of one element)
+    assert O.max_rel(y1, y2) < 2e-3
     assert O.cosine(g1, vol.grad) > 0.9999
 
 
