@@ -43,7 +43,7 @@ struct BwdSmem {
   static constexpr int kQStage = 2 * kTile + 2048;           // Q, dO, lse2[128], delta[128] (+pad to a 1 KB multiple)
   static constexpr int kQ = 2 * kTile;
   static constexpr int kDS = kQ + kQStages * kQStage;        // [128 keys x 128 queries] bf16, two 64-query sub-tiles
-  static constexpr int kDQ = kDS + kBT * kBT * 2;            // dQ staging: two [128 x 32] fp32 halves (swizzled)
+  static constexpr int kDQ = kDS + kBT * kBT * 2;            // dQ staging: two [128 x HD/2] fp32 halves (swizzled)
   static constexpr int kBar = kDQ + kBT * HD * 4;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwdKArgs p) {
-  static_assert(HD == 64, "head_dim 64 only for now");
+  static_assert(HD == 64 || HD == 32, "head_dim 64 (SWIZZLE_128B tiles) or 32 (SWIZZLE_64B tiles)");
   using L = BwdSmem<HD>;
+  using SW = Swz<HD * 2>;        // Q / K / V / dO tiles and the fp32 dQ staging halves: rows of HD*2 bytes
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
@@ -141,7 +142,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t kColSt = 0, kColPt = 128, kColDPt = 192, kColDV = 320, kColDK = 384, kColDQ = 448;
+  constexpr uint32_t kColSt = 0, kColPt = 128, kColDPt = 192, kColDV = 320, kColDK = 320 + HD, kColDQ = 320 + 2 * HD;
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -174,8 +175,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
-          umma_ss(tmem_base + kColSt, make_sdesc_sw128(sK + k16 * 32, 16, 1024), make_sdesc_sw128(sQ + k16 * 32, 16, 1024), id_s,
-                  k16 > 0 ? 1u : 0u);
+          umma_ss(tmem_base + kColSt, SW::desc(sK + k16 * 32), SW::desc(sQ + k16 * 32), id_s, k16 > 0 ? 1u : 0u);
       }
     };
     auto issue_dpt = [&](int st) {
@@ -183,8 +183,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
-          umma_ss(tmem_base + kColDPt, make_sdesc_sw128(sV + k16 * 32, 16, 1024), make_sdesc_sw128(sDO + k16 * 32, 16, 1024), id_s,
-                  k16 > 0 ? 1u : 0u);
+          umma_ss(tmem_base + kColDPt, SW::desc(sV + k16 * 32), SW::desc(sDO + k16 * 32), id_s, k16 > 0 ? 1u : 0u);
       }
     };
     auto commit = [&](int barrier) { if (leader) tc_commit(&bar[barrier]); };
@@ -213,7 +212,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
-          umma_ts(tmem_base + kColDV, tmem_base + kColPt + k16 * 8, make_sdesc_sw128(sDO + k16 * 2048, 8192, 1024), id_dv,
+          umma_ts(tmem_base + kColDV, tmem_base + kColPt + k16 * 8, SW::desc(sDO + k16 * SW::kMnStep, 8192), id_dv,
                   (i > 0 || k16 > 0) ? 1u : 0u);
       }
       // (3) once dS^T(i) is in smem (and dP^T(i) consumed): dP^T(i+1), dK, dQ
@@ -228,7 +227,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS + (k16 >> 2) * 16384 + (k16 & 3) * 32, 16, 1024),
-                  make_sdesc_sw128(sQ + k16 * 2048, 8192, 1024), id_dv, (i > 0 || k16 > 0) ? 1u : 0u);
+                  SW::desc(sQ + k16 * SW::kMnStep, 8192), id_dv, (i > 0 || k16 > 0) ? 1u : 0u);
       }
       if (i > 0) { mbar_wait(&bar[BB_DQFREE], (i - 1) & 1, 26); tc_fence_after(); }
       // dQ_i = dS K      (A = dS^T read MN-major: M = queries contiguous, K = key rows; B = K MN-major)
@@ -236,7 +235,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ss(tmem_base + kColDQ, make_sdesc_sw128(sDS + k16 * 2048, 16384, 1024),
-                  make_sdesc_sw128(sK + k16 * 2048, 8192, 1024), id_dq, k16 > 0 ? 1u : 0u);
+                  SW::desc(sK + k16 * SW::kMnStep, 8192), id_dq, k16 > 0 ? 1u : 0u);
       }
       commit(BB_DQF);
       commit(BB_QE + st);
@@ -250,7 +249,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool key_ok = (j * kBT + r) < p.nk;
     const bool keys_full = (j + 1) * kBT <= p.nk;
     const float scale2 = p.scale2;
-    uint8_t* dq_stage = smem + L::kDQ + wg * (kBT * 32 * 4);
+    uint8_t* dq_stage = smem + L::kDQ + wg * (kBT * (HD / 2) * 4);
     const uint32_t dq_saddr = smem_u32(dq_stage);
 
     auto drain_dq = [&](int i) {
@@ -258,17 +257,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_after();
       if ((threadIdx.x & 127) == 0) bulk_wait_read<0>();      // previous reduce has finished reading the staging tile
       named_bar_sync(1 + wg, 128);
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + lane_base + kColDQ + wg * 32, v);   // lane = query row of tile i, 32 of the 64 d columns
+      uint32_t v[HD / 2];
+      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + kColDQ + wg * 32, v);   // lane = query row of tile i,
+      else                    tmem_ld_32x16(tmem_base + lane_base + kColDQ + wg * 16, v);   // this warpgroup's half of the d columns
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bar[BB_DQFREE]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) sts_u4(dq_saddr + sw128_offset(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      for (int k = 0; k < HD / 8; ++k) sts_u4(dq_saddr + SW::offset(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       fence_proxy_async_smem();
       named_bar_sync(1 + wg, 128);
       if ((threadIdx.x & 127) == 0) {
-        tma_reduce_add_2d(&tmDQ, dq_stage, wg * 32, bh * p.nq_pad + i * kBT);
+        tma_reduce_add_2d(&tmDQ, dq_stage, wg * (HD / 2), bh * p.nq_pad + i * kBT);
         bulk_commit();
       }
     };
@@ -328,18 +328,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     drain_dq(nQ - 1);   // the commit behind BB_DQF covers every earlier MMA: dV and dK are complete too
     if ((threadIdx.x & 127) == 0) bulk_wait<0>();
 
-    // ---- epilogue: dV, dK (x softmax scale) -> bf16 -> global; warpgroup w writes d columns [32w, 32w+32)
+    // ---- epilogue: dV, dK (x softmax scale) -> bf16 -> global; warpgroup w writes d columns [HD/2 w, HD/2 (w+1))
     const int key = j * kBT + r;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD + wg * 32;
+      bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD + wg * (HD / 2);
       const float mul = which == 0 ? 1.0f : p.scale;
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 32, v);
+      uint32_t v[HD / 2];
+      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 32, v);
+      else                    tmem_ld_32x16(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 16, v);
       tmem_ld_wait();
       if (key_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 8) {
+        for (int t = 0; t < HD / 2; t += 8) {
           uint4 u;
           u.x = pack_bf16(__uint_as_float(v[t]) * mul, __uint_as_float(v[t + 1]) * mul);
           u.y = pack_bf16(__uint_as_float(v[t + 2]) * mul, __uint_as_float(v[t + 3]) * mul);
@@ -359,7 +360,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]; one warp per (token, head), HD = 64 -> 2 elements per lane
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]; one warp per (token, head): 2 elements per lane (HD 64) or 1 (HD 32)
+template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o,
                                                          long long lddo, const float* __restrict__ lse2, float* __restrict__ delta,
                                                          float* __restrict__ nlse2, int batch, int heads, int nq, int nq_pad) {
@@ -370,9 +372,15 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   const int h = (int)(gw % heads);
   const long long tok = gw / heads;
   const int b = (int)(tok / nq), q = (int)(tok - (long long)b * nq);
-  const float2 a = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(o + tok * ldo + h * 64 + 2 * lane)));
-  const float2 g = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(d_o + tok * lddo + h * 64 + 2 * lane)));
-  const float s = warp_sum(a.x * g.x + a.y * g.y);
+  float part;
+  if constexpr (HD == 64) {
+    const float2 a = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(o + tok * ldo + h * 64 + 2 * lane)));
+    const float2 g = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(d_o + tok * lddo + h * 64 + 2 * lane)));
+    part = a.x * g.x + a.y * g.y;
+  } else {
+    part = __bfloat162float(o[tok * ldo + h * 32 + lane]) * __bfloat162float(d_o[tok * lddo + h * 32 + lane]);
+  }
+  const float s = warp_sum(part);
   if (lane == 0) {
     const long long idx = ((long long)b * heads + h) * nq_pad + q;
     delta[idx] = s;
@@ -380,55 +388,50 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
 }
 
-// dq_accum f32 [B,H,nq_pad,64] -> dq bf16 [B*nq, lddq] (column h*64 + d); 8 elements per thread
+// dq_accum f32 [B,H,nq_pad,HD] -> dq bf16 [B*nq, lddq] (column h*HD + d); 8 elements per thread
+template <int HD>
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, long long lddq,
                                                               int batch, int heads, int nq, int nq_pad, float scale) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*nq*H*8
-  const long long total = (long long)batch * nq * heads * 8;
+  constexpr int kParts = HD / 8;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*nq*H*kParts
+  const long long total = (long long)batch * nq * heads * kParts;
   if (idx >= total) return;
-  const int part = (int)(idx & 7);
-  const long long t = idx >> 3;
+  const int part = (int)(idx % kParts);
+  const long long t = idx / kParts;
   const int h = (int)(t % heads);
   const long long tok = t / heads;
   const int b = (int)(tok / nq), q = (int)(tok - (long long)b * nq);
-  const float* src = acc + (((long long)b * heads + h) * nq_pad + q) * 64 + part * 8;
+  const float* src = acc + (((long long)b * heads + h) * nq_pad + q) * HD + part * 8;
   const float4 x = __ldg(reinterpret_cast<const float4*>(src)), y = __ldg(reinterpret_cast<const float4*>(src + 4));
   uint4 u = make_uint4(pack_bf16(x.x * scale, x.y * scale), pack_bf16(x.z * scale, x.w * scale), pack_bf16(y.x * scale, y.y * scale),
                        pack_bf16(y.z * scale, y.w * scale));
-  *reinterpret_cast<uint4*>(dq + tok * lddq + h * 64 + part * 8) = u;
+  *reinterpret_cast<uint4*>(dq + tok * lddq + h * HD + part * 8) = u;
 }
 
 }  // namespace hvc
 
-extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
-  using namespace hvc;
-  HVC_CHECK_ARG(a != nullptr && a->size == sizeof(hvc_attn_args), "hvc_attn_bwd: bad args struct");
-  HVC_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->nq > 0 && a->nk > 0, "hvc_attn_bwd: empty problem");
-  HVC_CHECK_ARG(a->head_dim == 64, "hvc_attn_bwd: head_dim %d not supported (64 only)", a->head_dim);
-  HVC_CHECK_ARG(a->q && a->k && a->v && a->o && a->d_o && a->lse && a->delta && a->dq_accum && a->dq && a->dk && a->dv,
-                "hvc_attn_bwd: null operand");
-  HVC_CHECK_ARG(((a->lddq | a->lddk | a->lddv) & 7) == 0, "hvc_attn_bwd: gradient row pitches must be multiples of 8");
-  constexpr int HD = 64;
+namespace hvc {
+template <int HD>
+static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   using L = BwdSmem<HD>;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nq_pad = (a->nq + 127) / 128 * 128;
   const uint64_t width = (uint64_t)a->heads * HD;
-
+  const int swz = HD == 64 ? 1 : 2;
   {
     const long long warps = (long long)a->batch * a->nq * a->heads;
-    attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->ldo,
-                                                                  reinterpret_cast<const bf16*>(a->d_o), a->lddo, a->lse, a->delta,
-                                                                  a->delta + (long long)a->batch * a->heads * nq_pad, a->batch, a->heads,
-                                                                  a->nq, nq_pad);
+    attn_delta_kernel<HD><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->ldo,
+                                                                      reinterpret_cast<const bf16*>(a->d_o), a->lddo, a->lse, a->delta,
+                                                                      a->delta + (long long)a->batch * a->heads * nq_pad, a->batch,
+                                                                      a->heads, a->nq, nq_pad);
     HVC_LAUNCH_CHECK();
   }
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int rc;
-  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, 32, kBT, true))) return rc;
-  if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kBT, true))) return rc;
-  if ((rc = make_tmap_2d(&tmDO, a->d_o, 2, (uint64_t)a->batch * a->nq, width, a->lddo, HD, kBT, true))) return rc;
-  if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kBT, true))) return rc;
-  if ((rc = make_tmap_2d(&tmV, a->v, 2, (uint64_t)a->batch * a->nk, width, a->ldv, HD, kBT, true))) return rc;
+  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, HD / 2, kBT, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kBT, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmDO, a->d_o, 2, (uint64_t)a->batch * a->nq, width, a->lddo, HD, kBT, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kBT, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmV, a->v, 2, (uint64_t)a->batch * a->nk, width, a->ldv, HD, kBT, swz))) return rc;
   AttnBwdKArgs ka;
   ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk; ka.nq_pad = nq_pad;
   ka.n_q_tiles = nq_pad / kBT;
@@ -445,10 +448,23 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   attn_bwd_kernel<HD><<<grid, kBwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, ka);
   HVC_LAUNCH_CHECK();
   {
-    const long long threads = (long long)a->batch * a->nq * a->heads * 8;
-    attn_dq_convert_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a->dq_accum, reinterpret_cast<bf16*>(a->dq), a->lddq,
-                                                                             a->batch, a->heads, a->nq, nq_pad, a->scale);
+    const long long threads = (long long)a->batch * a->nq * a->heads * (HD / 8);
+    attn_dq_convert_kernel<HD><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a->dq_accum, reinterpret_cast<bf16*>(a->dq), a->lddq,
+                                                                                 a->batch, a->heads, a->nq, nq_pad, a->scale);
     HVC_LAUNCH_CHECK();
   }
   return HVC_OK;
+}
+}  // namespace hvc
+
+extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
+  using namespace hvc;
+  HVC_CHECK_ARG(a != nullptr && a->size == sizeof(hvc_attn_args), "hvc_attn_bwd: bad args struct");
+  HVC_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->nq > 0 && a->nk > 0, "hvc_attn_bwd: empty problem");
+  HVC_CHECK_ARG(a->head_dim == 64 || a->head_dim == 32, "hvc_attn_bwd: head_dim %d not supported (32 or 64)", a->head_dim);
+  HVC_CHECK_ARG(a->q && a->k && a->v && a->o && a->d_o && a->lse && a->delta && a->dq_accum && a->dq && a->dk && a->dv,
+                "hvc_attn_bwd: null operand");
+  HVC_CHECK_ARG(((a->lddq | a->lddk | a->lddv) & 7) == 0, "hvc_attn_bwd: gradient row pitches must be multiples of 8");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return a->head_dim == 64 ? launch_attn_bwd<64>(a, st) : launch_attn_bwd<32>(a, st);
 }

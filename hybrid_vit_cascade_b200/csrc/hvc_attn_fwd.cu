@@ -118,8 +118,9 @@ template <int HD>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdKArgs p) {
-  static_assert(HD == 64, "head_dim 64 (128-byte rows, SWIZZLE_128B) only for now");
+  static_assert(HD == 64 || HD == 32, "head_dim 64 (128-byte rows, SWIZZLE_128B) or 32 (64-byte rows, SWIZZLE_64B)");
   using L = FwdSmem<HD>;
+  using SW = Swz<HD * 2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
@@ -185,8 +186,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
-          umma_ss(tmem_base + kColS + x * kKTile, make_sdesc_sw128(sQ + x * L::kTile + k16 * 32, 16, 1024),
-                  make_sdesc_sw128(sK + st * L::kTile + k16 * 32, 16, 1024), idesc_s, k16 > 0 ? 1u : 0u);
+          umma_ss(tmem_base + kColS + x * kKTile, SW::desc(sQ + x * L::kTile + k16 * 32),
+                  SW::desc(sK + st * L::kTile + k16 * 32), idesc_s, k16 > 0 ? 1u : 0u);
       }
     };
     auto issue_pv = [&](int x, int st, bool acc) {   // O_x (+)= P_x V   (P: TMEM, 8 columns per K=16 step)
@@ -194,7 +195,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k16 = 0; k16 < kKTile / 16; ++k16)
           umma_ts(tmem_base + kColO + x * HD, tmem_base + kColS + x * kKTile + k16 * 8,
-                  make_sdesc_sw128(sV + st * L::kTile + k16 * 2048, 8192, 1024), idesc_o, (acc || k16 > 0) ? 1u : 0u);
+                  SW::desc(sV + st * L::kTile + k16 * SW::kMnStep, 8192), idesc_o, (acc || k16 > 0) ? 1u : 0u);
       }
     };
     auto commit = [&](int barrier) { if (leader) tc_commit(&bar[barrier]); };
@@ -314,21 +315,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 }  // namespace hvc
 
-extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
-  using namespace hvc;
-  HVC_CHECK_ARG(a != nullptr && a->size == sizeof(hvc_attn_args), "hvc_attn_fwd: bad args struct");
-  HVC_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->nq > 0 && a->nk > 0, "hvc_attn_fwd: empty problem");
-  HVC_CHECK_ARG(a->head_dim == 64, "hvc_attn_fwd: head_dim %d not supported (64 only)", a->head_dim);
-  HVC_CHECK_ARG(a->q && a->k && a->v && a->o, "hvc_attn_fwd: null operand");
-  HVC_CHECK_ARG((a->ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "hvc_attn_fwd: o must be 16-byte aligned rows");
-  constexpr int HD = 64;
+namespace hvc {
+template <int HD>
+static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   using L = FwdSmem<HD>;
   const uint64_t width = (uint64_t)a->heads * HD;
+  const int swz = HD == 64 ? 1 : 2;
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kQTile, true))) return rc;
-  if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kKTile, true))) return rc;
-  if ((rc = make_tmap_2d(&tmV, a->v, 2, (uint64_t)a->batch * a->nk, width, a->ldv, HD, kKTile, true))) return rc;
+  if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kQTile, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kKTile, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmV, a->v, 2, (uint64_t)a->batch * a->nk, width, a->ldv, HD, kKTile, swz))) return rc;
   AttnFwdKArgs ka;
   ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk;
   ka.n_kv_tiles = (a->nk + kKTile - 1) / kKTile;
@@ -342,7 +339,19 @@ extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
     configured = true;
   }
   dim3 grid((a->nq + 2 * kQTile - 1) / (2 * kQTile), a->batch * a->heads);
-  attn_fwd_kernel<HD><<<grid, kFwdThreads, L::kTotal, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, ka);
+  attn_fwd_kernel<HD><<<grid, kFwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, ka);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
+}
+}  // namespace hvc
+
+extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
+  using namespace hvc;
+  HVC_CHECK_ARG(a != nullptr && a->size == sizeof(hvc_attn_args), "hvc_attn_fwd: bad args struct");
+  HVC_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->nq > 0 && a->nk > 0, "hvc_attn_fwd: empty problem");
+  HVC_CHECK_ARG(a->head_dim == 64 || a->head_dim == 32, "hvc_attn_fwd: head_dim %d not supported (32 or 64)", a->head_dim);
+  HVC_CHECK_ARG(a->q && a->k && a->v && a->o, "hvc_attn_fwd: null operand");
+  HVC_CHECK_ARG((a->ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "hvc_attn_fwd: o must be 16-byte aligned rows");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return a->head_dim == 64 ? launch_attn_fwd<64>(a, st) : launch_attn_fwd<32>(a, st);
 }

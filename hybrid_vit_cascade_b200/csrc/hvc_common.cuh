@@ -195,15 +195,34 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
 // a K=16 step advances the start address by 32 B inside the swizzle atom.  MN-major: rows are K
 // indices holding 64 contiguous MN elements; SBO = 1024 B between 8-row K groups, LBO = byte distance
 // between 64-element MN chunks; a K=16 step advances the start address by 16 rows = 2048 B.
-__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout type (bits [61,64)): 2 = SWIZZLE_128B, 4 = SWIZZLE_64B (rows of 64 B = head_dim 32 tiles: 8-row groups are
+// 512 B apart, a K=16 step of an MN-major operand advances 16 rows = 1024 B)
+template <uint32_t LAYOUT>
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;  // descriptor version (Blackwell)
-  d |= 2ull << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(LAYOUT) << 61;
   return d;
 }
+__device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_sdesc<2>(smem_addr, lbo_bytes, sbo_bytes);
+}
+// Swizzled operand tiles whose rows are ROWB bytes (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B).
+template <int ROWB>
+struct Swz {
+  static_assert(ROWB == 128 || ROWB == 64, "row bytes");
+  static constexpr uint32_t kLayout = ROWB == 128 ? 2u : 4u;
+  static constexpr uint32_t kGroup = 8u * ROWB;        // SBO: 8-row group pitch
+  static constexpr uint32_t kMnStep = 16u * ROWB;      // MN-major operand: one K=16 step = 16 rows
+  __device__ static __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo = 16) { return make_sdesc<kLayout>(addr, lbo, kGroup); }
+  // byte offset of 16-byte chunk `chunk` of row `row`
+  __device__ static __forceinline__ uint32_t offset(uint32_t row, uint32_t chunk) {
+    return ROWB == 128 ? row * 128u + ((chunk ^ (row & 7u)) << 4) : row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+  }
+};
 
 #define HVC_R4(v, i) "=r"(v[i]), "=r"(v[i + 1]), "=r"(v[i + 2]), "=r"(v[i + 3])
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (taddr.lane + t).

@@ -37,10 +37,10 @@ def _check_dropout(module, p):
 
 def _check_heads(embed_dim, num_heads):
     assert embed_dim % num_heads == 0
-    if embed_dim // num_heads != 64:
+    if embed_dim // num_heads not in (32, 64):
         raise NotImplementedError(
-            f"head_dim {embed_dim // num_heads} is not built yet: the sm_100a attention kernels cover head_dim 64 "
-            "(direct_regression / cascade stage 1); head_dim 32 is the next kernel variant")
+            f"head_dim {embed_dim // num_heads} is not built: the sm_100a attention kernels cover head_dim 64 "
+            "(direct_regression / cascade stage 1) and 32 (cascade stages 2-3, the H200 variants)")
 
 
 class MultiHeadSelfAttention(nn.Module):

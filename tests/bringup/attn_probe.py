@@ -20,7 +20,16 @@ CASES = {
     "bwd_ragged": (2, 2, 200, 72, 64, False),
     "bwd_self_packed": (2, 4, 1024, 1024, 64, True),
     "bwd_4096": (2, 4, 4096, 4096, 64, True),
+    "fwd32_1tile": (1, 1, 256, 128, 32, False),
+    "fwd32_multi": (1, 2, 512, 640, 32, False),
+    "fwd32_ragged": (2, 2, 200, 72, 32, False),
+    "bwd32_1tile": (1, 1, 128, 128, 32, False),
+    "bwd32_multi": (1, 2, 384, 256, 32, False),
+    "bwd32_ragged": (2, 2, 200, 72, 32, False),
+    "bwd32_self_packed": (2, 8, 1024, 1024, 32, True),
     "perf_32k": (1, 4, 32768, 32768, 64, True),
+    "perf32_32k": (1, 8, 32768, 32768, 32, True),
+    "perf32_cross": (2, 8, 32768, 4096, 32, False),
     "perf_cross": (2, 4, 32768, 4096, 64, False),
 }
 
@@ -90,7 +99,7 @@ def run_case(name, bwd=False):
     lerr = float((lse2[:, :, :nq] * math.log(2.0) - rlse).abs().max())
     ok = err < 2e-2 and lerr < 2e-2
     print(f"CASE {name}: out relerr {err:.3e} lse abserr {lerr:.3e} {'OK' if ok else 'FAIL'}")
-    if name.startswith("bwd"):
+    if name.startswith("bwd"):  # bwd / bwd32
         d_o = torch.randn(B * nq, C, device="cuda", generator=g).bfloat16()
         if packed:
             dqkv = torch.full((B * nq, 3 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
