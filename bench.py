@@ -2,7 +2,7 @@
 """bench.py -- training throughput of the 3D ViT backbone hot path (volumes/sec), B200-native arm and
 reference (CPU) arm.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload direct128|direct64]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload direct128|direct64|stage2|stage3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch: HybridViT3D forward (voxel embed, L x (AdaLN
@@ -34,6 +34,15 @@ WORKLOADS = {
                       cond_dim=1024, batch=8, desc="direct_regression 128^3 (32^3=32768 tokens, 4096 ctx tokens)"),
     "direct64": dict(volume=(64, 64, 64), token_grid="reference", voxel_dim=256, depth=4, heads=4, ctx_hw=64, ctx_dim=512,
                      cond_dim=1024, batch=8, desc="direct_regression 64^3 (16^3=4096 tokens, 4096 ctx tokens)"),
+    # progressive cascade refiners (model_progressive.py:177-186, :247-256): 32-channel input volume from the
+    # upsample conv, 8 heads (d=32); batch 2 per GPU (config_progressive.json:27,35); stage 3 runs the ViT under
+    # torch.utils.checkpoint (model_progressive.py:286-291)
+    "stage2": dict(volume=(128, 128, 128), token_grid="conv", in_channels=32, voxel_dim=256, depth=6, heads=8, ctx_hw=32,
+                   ctx_dim=512, cond_dim=1024, batch=2,
+                   desc="progressive_cascade stage 2 ViT 128^3 (32 ch in, 32768 tokens, 1024 ctx tokens, d=32)"),
+    "stage3": dict(volume=(256, 256, 256), token_grid="reference", in_channels=32, voxel_dim=256, depth=8, heads=8, ctx_hw=64,
+                   ctx_dim=512, cond_dim=1024, batch=2, checkpoint=True,
+                   desc="progressive_cascade stage 3 ViT 256^3 (32 ch in, 32768 tokens, 4096 ctx tokens, d=32, checkpointed)"),
 }
 
 
@@ -43,7 +52,7 @@ def log(*a):
 
 def oracle_cfg(w):
     from oracle import vit_oracle as O
-    return O.BackboneConfig(volume_size=w["volume"], in_channels=1, voxel_dim=w["voxel_dim"], depth=w["depth"],
+    return O.BackboneConfig(volume_size=w["volume"], in_channels=w.get("in_channels", 1), voxel_dim=w["voxel_dim"], depth=w["depth"],
                             num_heads=w["heads"], context_dim=w["ctx_dim"], cond_dim=w["cond_dim"],
                             token_grid=w["token_grid"])
 
@@ -158,15 +167,20 @@ def run_b200(args, w):
     hvc.set_dropout_policy("ignore")
 
     torch.manual_seed(0)
-    model = hvc.HybridViT3D(volume_size=w["volume"], in_channels=1, voxel_dim=w["voxel_dim"], depth=w["depth"],
+    cin = w.get("in_channels", 1)
+    model = hvc.HybridViT3D(volume_size=w["volume"], in_channels=cin, voxel_dim=w["voxel_dim"], depth=w["depth"],
                             num_heads=w["heads"], context_dim=w["ctx_dim"], cond_dim=w["cond_dim"],
                             token_grid=w["token_grid"]).to(dev)
     with torch.no_grad():
         for n, p in model.named_parameters():
             if "adaln.linear" in n:
                 p.normal_(0.0, 0.02)
-    initial_volume = torch.nn.Parameter(torch.randn(1, 1, D, H, W, device=dev) * 0.01)   # model_direct.py:57
-    params = list(model.parameters()) + [initial_volume]
+    direct = cin == 1
+    if direct:
+        initial_volume = torch.nn.Parameter(torch.randn(1, 1, D, H, W, device=dev) * 0.01)   # model_direct.py:57
+        params = list(model.parameters()) + [initial_volume]
+    else:
+        params = list(model.parameters())
     gb = GradientBuckets(params)
     gb.broadcast_parameters(params)
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
@@ -176,11 +190,23 @@ def run_b200(args, w):
     feat = torch.rand(B, w["ctx_dim"], hw, hw, device=dev, generator=g)          # encoder feature map (B, C, H', W')
     cond = torch.randn(B, w["cond_dim"], device=dev, generator=g)
     target = torch.rand(B, 1, D, H, W, device=dev, generator=g) * 2 - 1
+    # cascade refiners: the ViT input is the (B, 32, D, H, W) output of the stage's upsample conv; its gradient is needed
+    vol_in = None if direct else (torch.randn(B, cin, D, H, W, device=dev, generator=g) * 0.5).requires_grad_(True)
+    use_ckpt = bool(w.get("checkpoint"))
+    if use_ckpt:
+        from torch.utils.checkpoint import checkpoint
 
     def step(feat_, cond_, target_):
         gb.reset()
         ctx = feat_.flatten(2).transpose(1, 2)                                    # model_direct.py:80 (a view, no copy)
-        out = model(initial_volume.expand(B, -1, -1, -1, -1), ctx, cond_)
+        if direct:
+            out = model(initial_volume.expand(B, -1, -1, -1, -1), ctx, cond_)
+        elif use_ckpt:
+            vol_in.grad = None
+            out = checkpoint(model, vol_in, ctx, cond_, use_reentrant=False)
+        else:
+            vol_in.grad = None
+            out = model(vol_in, ctx, cond_)
         loss = (out - target_).abs().mean()
         loss.backward()
         gb.finish()
@@ -255,12 +281,14 @@ def run_b200(args, w):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     fl = step_flops(w)
+    if use_ckpt:    # the forward runs twice (x4 instead of x3)
+        fl = {k: v * 4.0 / 3.0 for k, v in fl.items()}
     vols = world * B * args.steps
     value = vols / (ms_total / 1e3)
     roof = None
     if big:
         ach = sum(f for _, f in big) / (sum(t for t, _ in big) * 1e9)
-        roof = {"kernel": "attn_bwd_kernel<64> (self-attention; call also includes the delta and dq-convert passes)",
+        roof = {"kernel": f"attn_bwd_kernel<{w['voxel_dim'] // w['heads']}> (self-attention; call also includes the delta and dq-convert passes)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": None, "peak_source": peak_src, "launches": len(big), "ms_per_launch": sum(t for t, _ in big) / len(big),
                 "frac_of_nominal_2250": ach / 2250.0}
@@ -296,7 +324,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="direct128", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="direct128", choices=sorted(WORKLOADS),
+                    help="direct128 = BASELINE.json's metric configuration (default); the others are the remaining configs")
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")

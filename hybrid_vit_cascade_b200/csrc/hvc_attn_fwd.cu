@@ -343,6 +343,44 @@ static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
+
+// store_attention slow path (vit_components.py:106-108): probs[b,h,i,j] = exp2(s2[i,j] - lse2[b,h,i]) in place, where the
+// buffer holds s2 = q k^T * scale * log2(e) written by hvc_gemm (one GEMM per (b, h) on the head's column slice).
+__global__ void __launch_bounds__(256) attn_probs_finalize_kernel(float* __restrict__ probs, const float* __restrict__ lse2, long long rows,
+                                                                  int nq, int nk, int nq_pad) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);     // one warp per (b, h, i) row
+  if (row >= rows) return;
+  const long long bh = row / nq;
+  const float l = lse2[bh * nq_pad + (row - bh * nq)];
+  float* r = probs + row * nk;
+  for (int j = threadIdx.x & 31; j < nk; j += 32) r[j] = ex2_approx(r[j] - l);
+}
+
+static int attn_store_probs(const hvc_attn_args* a, cudaStream_t st) {
+  const int d = a->head_dim;
+  const int nq_pad = (a->nq + 127) / 128 * 128;
+  float* probs = reinterpret_cast<float*>(a->probs);
+  for (int b = 0; b < a->batch; ++b) {
+    for (int h = 0; h < a->heads; ++h) {
+      hvc_gemm_args g;
+      memset(&g, 0, sizeof(g));
+      g.size = sizeof(g);
+      g.M = a->nq; g.N = a->nk; g.K = d;
+      g.A = reinterpret_cast<const bf16*>(a->q) + (long long)b * a->nq * a->ldq + h * d; g.lda = a->ldq; g.a_major = 0;
+      g.B = reinterpret_cast<const bf16*>(a->k) + (long long)b * a->nk * a->ldk + h * d; g.ldb = a->ldk; g.b_major = 0;
+      g.epilogue = HVC_EPI_F32; g.activation = HVC_ACT_NONE;
+      g.out = probs + ((long long)b * a->heads + h) * a->nq * a->nk; g.ldo = a->nk;
+      g.alpha = a->scale * 1.4426950408889634f;
+      g.k_splits = 1;
+      int rc = hvc_gemm(&g, st);
+      if (rc) return rc;
+    }
+  }
+  const long long rows = (long long)a->batch * a->heads * a->nq;
+  attn_probs_finalize_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(probs, a->lse, rows, a->nq, a->nk, nq_pad);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
 }  // namespace hvc
 
 extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
@@ -352,6 +390,9 @@ extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
   HVC_CHECK_ARG(a->head_dim == 64 || a->head_dim == 32, "hvc_attn_fwd: head_dim %d not supported (32 or 64)", a->head_dim);
   HVC_CHECK_ARG(a->q && a->k && a->v && a->o, "hvc_attn_fwd: null operand");
   HVC_CHECK_ARG((a->ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "hvc_attn_fwd: o must be 16-byte aligned rows");
+  HVC_CHECK_ARG(a->probs == nullptr || a->lse != nullptr, "hvc_attn_fwd: probs needs lse");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return a->head_dim == 64 ? launch_attn_fwd<64>(a, st) : launch_attn_fwd<32>(a, st);
+  const int rc = a->head_dim == 64 ? launch_attn_fwd<64>(a, st) : launch_attn_fwd<32>(a, st);
+  if (rc != HVC_OK || a->probs == nullptr) return rc;
+  return attn_store_probs(a, st);
 }

@@ -58,8 +58,13 @@ class HybridViTBlock3D(nn.Module):
         mod = self.adaln.params(cond)                                   # (B, 6C)
         x = ops.SelfAttnBranch.apply(x, mod, self.norm1.weight, self.norm1.bias, sa.qkv.weight, sa.proj.weight,
                                      sa.proj.bias, B, N, H, 0)
-        x = ops.CrossAttnBranch.apply(x, ctx16, self.norm2.weight, self.norm2.bias, ca.q.weight, ca.kv.weight,
-                                      ca.proj.weight, ca.proj.bias, B, N, M, H)
+        if ca.store_attention:      # reference :130-133 reads it back from the cross-attention module
+            x, probs = ops.CrossAttnBranch.apply(x, ctx16, self.norm2.weight, self.norm2.bias, ca.q.weight, ca.kv.weight,
+                                                 ca.proj.weight, ca.proj.bias, B, N, M, H, True)
+            ca.attention_weights = probs.detach()
+        else:
+            x = ops.CrossAttnBranch.apply(x, ctx16, self.norm2.weight, self.norm2.bias, ca.q.weight, ca.kv.weight,
+                                          ca.proj.weight, ca.proj.bias, B, N, M, H)
         x = ops.MlpBranch.apply(x, mod, self.norm3.weight, self.norm3.bias, self.mlp[0].weight, self.mlp[0].bias,
                                 self.mlp[3].weight, self.mlp[3].bias, B, N, 3 * C)
         return x
@@ -68,15 +73,16 @@ class HybridViTBlock3D(nn.Module):
                 prev_stage_embed: Optional[torch.Tensor] = None):
         _check_heads(self.voxel_dim, self.self_attn.num_heads)
         _check_dropout(self, self.self_attn.attn_drop.p)
-        if self.return_attention:
-            raise NotImplementedError("return_attention=True needs the materialised attention map (not built yet)")
         B, N, C = voxel_features.shape
         M = xray_context.shape[1]
         cond = self._combined_cond(cond, prev_stage_embed, B)
         x = voxel_features.float().contiguous().view(B * N, C)
         ctx16 = ops.CastTokens.apply(xray_context)
         x = self._forward_tokens(x, ctx16, cond, B, N, M)
-        return x.view(B, N, C).to(voxel_features.dtype)
+        out = x.view(B, N, C).to(voxel_features.dtype)
+        if self.return_attention:   # reference :130-143: (features, cross-attention map (B, heads, N, M))
+            return out, self.cross_attn.attention_weights
+        return out
 
 
 class HybridViT3D(nn.Module):

@@ -126,10 +126,11 @@ def _attn_args(q, k, v, B, H, nq, nk, d, scale):
     return args
 
 
-def attn_fwd(q, k, v, B, H, nq, nk, d, scale):
+def attn_fwd(q, k, v, B, H, nq, nk, d, scale, want_probs=False):
     """q: bf16 view [B*nq, H*d] (may be a column slice of a packed projection output), k/v: [B*nk, H*d].
 
-    Returns (o bf16 [B*nq, H*d], lse2 f32 [B, H, pad128(nq)]).
+    Returns (o bf16 [B*nq, H*d], lse2 f32 [B, H, pad128(nq)]) and, with want_probs (the store_attention slow
+    path), the materialised softmax f32 [B, H, nq, nk] as a third element.
     """
     _need_cuda(q, k, v)
     assert q.dtype == k.dtype == v.dtype == torch.bfloat16
@@ -139,8 +140,14 @@ def attn_fwd(q, k, v, B, H, nq, nk, d, scale):
     args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
     args.o, args.ldo = o.data_ptr(), o.stride(0)
     args.lse = lse.data_ptr()
+    probs = None
+    if want_probs:
+        probs = torch.empty(B, H, nq, nk, device=q.device, dtype=torch.float32)
+        args.probs = probs.data_ptr()
     with _timed("attn_fwd", 4.0 * B * H * nq * nk * d):
         _lib.check(_lib.lib().hvc_attn_fwd(C.byref(args), _stream()), "hvc_attn_fwd")
+    if want_probs:
+        return o, lse, probs
     return o, lse
 
 

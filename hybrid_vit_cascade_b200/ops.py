@@ -161,20 +161,24 @@ class CrossAttnBranch(Function):
     """x + proj(attn(q(LN2(x)), kv(context)))   hybrid_vit_backbone.py:126-128."""
 
     @staticmethod
-    def forward(ctx, x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, b_proj, B, N, M, H):
+    def forward(ctx, x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, b_proj, B, N, M, H, store_probs=False):
         T, C = x.shape
         d = C // H
         y, mean, rstd = K.ln_fwd(x, ln_w, ln_b)
         q = K.gemm(y, w16(w_q))
         kv = K.gemm(ctx16, w16(w_kv))
-        o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5)
+        res = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5, want_probs=store_probs)
+        o, lse = res[0], res[1]
         out = K.gemm(o, w16(w_proj), epilogue=K.EPI_RESIDUAL, bias=b_proj, resid=x)
         ctx.save_for_backward(x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, mean, rstd, y, q, kv, o, lse)
         ctx.dims = (B, N, M, H)
+        if store_probs:      # attention map (B, H, N, M): a detached diagnostic output (vit_components.py:106-108)
+            ctx.mark_non_differentiable(res[2])
+            return out, res[2]
         return out
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, *unused):
         x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, mean, rstd, y, q, kv, o, lse = ctx.saved_tensors
         B, N, M, H = ctx.dims
         T, C = x.shape
@@ -191,7 +195,7 @@ class CrossAttnBranch(Function):
         dw_kv = _wgrad(dkv, ctx16)
         dctx = _dgrad(dkv, w16(w_kv), f32_out=True) if ctx.needs_input_grad[1] else None
         r = K.ln_bwd(dy, x, mean, rstd, ln_w, ln_b, B, N, dx_in=dout)
-        return r["dx"], dctx, r["dw"], r["db"], dw_q, dw_kv, dw_proj, db_proj, None, None, None, None
+        return r["dx"], dctx, r["dw"], r["db"], dw_q, dw_kv, dw_proj, db_proj, None, None, None, None, None
 
 
 # ------------------------------------------------------------------ MLP sub-block (inside a5)
@@ -273,7 +277,7 @@ class CrossAttention(Function):
     """proj(attn(q(x), kv(context)))  -- MultiHeadCrossAttention.forward, vit_components.py:83-119 (dropout off)."""
 
     @staticmethod
-    def forward(ctx, x, context, w_q, w_kv, w_proj, b_proj, H):
+    def forward(ctx, x, context, w_q, w_kv, w_proj, b_proj, H, store_probs=False):
         B, N, C = x.shape
         M, Cc = context.shape[1], context.shape[2]
         d = C // H
@@ -281,15 +285,19 @@ class CrossAttention(Function):
         c16 = K.cast_tokens(context)
         q = K.gemm(x16, w16(w_q))
         kv = K.gemm(c16, w16(w_kv))
-        o, lse = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5)
+        res = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5, want_probs=store_probs)
+        o, lse = res[0], res[1]
         f32 = x.dtype == torch.float32
         out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16)
         ctx.save_for_backward(x16, c16, w_q, w_kv, w_proj, q, kv, o, lse)
         ctx.dims = (B, N, M, C, Cc, H, x.dtype, context.dtype)
+        if store_probs:
+            ctx.mark_non_differentiable(res[2])
+            return out.view(B, N, C), res[2]
         return out.view(B, N, C)
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, *unused):
         x16, c16, w_q, w_kv, w_proj, q, kv, o, lse = ctx.saved_tensors
         B, N, M, C, Cc, H, dt, cdt = ctx.dims
         d = C // H
@@ -306,7 +314,7 @@ class CrossAttention(Function):
         dctx = None
         if ctx.needs_input_grad[1]:
             dctx = _dgrad(dkv, w16(w_kv), f32_out=(cdt == torch.float32)).view(B, M, Cc)
-        return dx, dctx, dw_q, dw_kv, dw_proj, db_proj, None
+        return dx, dctx, dw_q, dw_kv, dw_proj, db_proj, None, None
 
 
 # ------------------------------------------------------------------ voxel embedding + positional encoding (a7 head of forward)
@@ -368,7 +376,8 @@ class VoxelEmbed(Function):
     @staticmethod
     def backward(ctx, dtok):
         plan, geoms, xB, B, xshape, nsaved, n, Cout = ctx.meta
-        saved, params = ctx.saved_tensors[:nsaved], ctx.saved_tensors[nsaved:]
+        tensors = ctx.saved_tensors          # read once: torch.utils.checkpoint allows a single unpack per tensor
+        saved, params = tensors[:nsaved], tensors[nsaved:]
         dtok = dtok.contiguous().view(B, n)
         dpos = K.batch_sum(dtok)
         dz = dpos.view(1, n) if xB != B else dtok

@@ -88,9 +88,11 @@ class MultiHeadCrossAttention(nn.Module):
         _check_heads(self.embed_dim, self.num_heads)
         _check_dropout(self, self.attn_drop.p)
         if self.store_attention:
-            raise NotImplementedError(
-                "store_attention=True (materialised (B,h,N,M) attention map, vit_components.py:106-108) is the "
-                "diagnostic slow path and is not built yet")
+            # diagnostic slow path: the (B,h,N,M) softmax is materialised by an extra GEMM + exp pass (reference :106-108)
+            out, probs = ops.CrossAttention.apply(x, context, self.q.weight, self.kv.weight, self.proj.weight,
+                                                  self.proj.bias, self.num_heads, True)
+            self.attention_weights = probs.detach()
+            return out
         return ops.CrossAttention.apply(x, context, self.q.weight, self.kv.weight, self.proj.weight, self.proj.bias,
                                         self.num_heads)
 

@@ -132,6 +132,45 @@ def components_d64():
     torch.save(out, os.path.join(HERE, "components_d64.pt"))
 
 
+def components_d32():
+    """head_dim 32 cases (cascade stages 2/3: C=256, 8 heads) incl. the materialised attention map
+    (store_attention / return_attention, vit_components.py:106-108, hybrid_vit_backbone.py:130-143)."""
+    g = torch.Generator().manual_seed(9876)
+    out = {}
+    torch.manual_seed(2)
+    sa = MultiHeadSelfAttention(64, num_heads=2).eval()
+    x = torch.randn(2, 200, 64, generator=g, requires_grad=True)
+    y = sa(x)
+    r = torch.randn(y.shape, generator=g)
+    pg, ig = grads_of(sa, [x], y, r)
+    out["self_attn"] = dict(sd=sa.state_dict(), x=x.detach(), y=y.detach(), r=r, pgrad=pg, xgrad=ig[0], num_heads=2)
+
+    ca = MultiHeadCrossAttention(96, 40, num_heads=3, store_attention=True).eval()
+    x = torch.randn(2, 200, 96, generator=g, requires_grad=True)
+    ctx = torch.randn(2, 72, 40, generator=g, requires_grad=True)
+    y = ca(x, ctx)
+    r = torch.randn(y.shape, generator=g)
+    pg, ig = grads_of(ca, [x, ctx], y, r)
+    out["cross_attn"] = dict(sd=ca.state_dict(), x=x.detach(), ctx=ctx.detach(), y=y.detach(), r=r,
+                             pgrad=pg, xgrad=ig[0], ctxgrad=ig[1], probs=ca.attention_weights.clone().half(),
+                             num_heads=3)
+
+    blk = HybridViTBlock3D(64, num_heads=2, context_dim=40, cond_dim=48, return_attention=True).eval()
+    randomise_adaln(blk, g)
+    x = torch.randn(2, 200, 64, generator=g, requires_grad=True)
+    ctx = torch.randn(2, 72, 40, generator=g, requires_grad=True)
+    cond = torch.randn(2, 48, generator=g, requires_grad=True)
+    res, attn_map = blk(x, ctx, cond, None)
+    r = torch.randn(res.shape, generator=g)
+    pg, ig = grads_of(blk, [x, ctx, cond], res, r)
+    out["block_attn"] = dict(sd=blk.state_dict(), x=x.detach(), ctx=ctx.detach(), cond=cond.detach(), prev=None,
+                             y=res.detach(), r=r, pgrad=pg, xgrad=ig[0], ctxgrad=ig[1], condgrad=ig[2],
+                             attn_map=attn_map.half(), num_heads=2, use_prev_stage=False)
+    for c in out.values():
+        c["pgrad"] = {k: v.half() for k, v in c["pgrad"].items()}
+    torch.save(out, os.path.join(HERE, "components_d32.pt"))
+
+
 BACKBONES = {
     # name: ctor kwargs, context_len, batch
     "vit_s2": (dict(volume_size=(32, 16, 16), in_channels=1, voxel_dim=32, depth=2, num_heads=2,
@@ -147,6 +186,11 @@ BACKBONES = {
                         context_dim=24, cond_dim=48), 20, 1),
     "vit_d64_quirk": (dict(volume_size=(64, 8, 8), in_channels=16, voxel_dim=64, depth=1, num_heads=1,
                            context_dim=24, cond_dim=48, use_prev_stage=True), 12, 1),
+    # head_dim 32 cases (cascade stage 2/3 style: multi-channel input, 8 heads at C=256)
+    "vit_d32": (dict(volume_size=(32, 16, 16), in_channels=4, voxel_dim=64, depth=2, num_heads=2,
+                     context_dim=24, cond_dim=48), 40, 2),
+    "vit_d32_h4": (dict(volume_size=(16, 16, 16), in_channels=2, voxel_dim=128, depth=1, num_heads=4,
+                        context_dim=32, cond_dim=48), 24, 1),
 }
 
 
@@ -167,10 +211,11 @@ def backbones():
         out[name] = dict(kwargs=kw, sd=m.state_dict(), x=x.detach(), ctx=ctx.detach(), cond=cond.detach(),
                          prev=prev, y=y.detach(), r=r, pgrad=pg, xgrad=ig[0], ctxgrad=ig[1], condgrad=ig[2],
                          downsampled_size=tuple(m.downsampled_size))
-        if "d64" in name:
+        if "d64" in name or "d32" in name:
             out[name]["pgrad"] = {k: v.half() for k, v in out[name]["pgrad"].items()}
-    torch.save({k: v for k, v in out.items() if "d64" not in k}, os.path.join(HERE, "backbones.pt"))
+    torch.save({k: v for k, v in out.items() if "d64" not in k and "d32" not in k}, os.path.join(HERE, "backbones.pt"))
     torch.save({k: v for k, v in out.items() if "d64" in k}, os.path.join(HERE, "backbones_d64.pt"))
+    torch.save({k: v for k, v in out.items() if "d32" in k}, os.path.join(HERE, "backbones_d32.pt"))
 
 
 CTOR_CASES = [
@@ -206,7 +251,9 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     components()
     components_d64()
+    components_d32()
     backbones()
     ctor_table()
-    for fn in ("components.pt", "components_d64.pt", "backbones.pt", "backbones_d64.pt", "ctor_table.json"):
+    for fn in ("components.pt", "components_d64.pt", "components_d32.pt", "backbones.pt", "backbones_d64.pt",
+               "backbones_d32.pt", "ctor_table.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)))

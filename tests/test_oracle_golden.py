@@ -108,6 +108,30 @@ def test_backbone(bb, name):
         _close(sd[k].grad, g, 1e-5)
 
 
+def test_head_dim_32_fixtures(golden_dir):
+    """head_dim 32 fixtures (cascade stage 2/3 heads) incl. the stored attention maps; gradients/maps are kept in fp16."""
+    comp32 = torch.load(os.path.join(golden_dir, "components_d32.pt"), weights_only=False)
+    c = comp32["cross_attn"]
+    y, probs = O.cross_attention(c["x"], c["ctx"], c["sd"], "", c["num_heads"], return_probs=True)
+    _close(y, c["y"])
+    _close(probs, c["probs"].float(), 1e-3)
+    c = comp32["block_attn"]
+    res, amap = O.block(c["x"], c["ctx"], c["cond"], c["sd"], "", c["num_heads"], return_attention=True)
+    _close(res, c["y"])
+    _close(amap, c["attn_map"].float(), 1e-3)
+    c = comp32["self_attn"]
+    _close(O.self_attention(c["x"], c["sd"], "", c["num_heads"]), c["y"])
+    bb32 = torch.load(os.path.join(golden_dir, "backbones_d32.pt"), weights_only=False)
+    for name, c in bb32.items():
+        cfg = O.BackboneConfig(**c["kwargs"])
+        sd = {k: _leaf(v) for k, v in c["sd"].items()}
+        y = O.backbone(c["x"], c["ctx"], c["cond"], sd, cfg, prev_stage_embed=c["prev"])
+        _close(y, c["y"])
+        (y * c["r"]).sum().backward()
+        for k, g in c["pgrad"].items():
+            _close(sd[k].grad, g.float(), 2e-3)
+
+
 def test_constructor_table(golden_dir):
     """Token-grid rule, conv plan (incl. the in_channels==C//4 quirk) and every state_dict shape."""
     rows = json.load(open(os.path.join(golden_dir, "ctor_table.json")))

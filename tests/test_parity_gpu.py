@@ -117,6 +117,66 @@ def test_backbone_golden(name):
     _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"], cond=c["condgrad"]), name)
 
 
+def test_head_dim_32_components_golden():
+    """cascade stage 2/3 heads (d=32): self-attention, cross-attention with the stored attention map, block + map."""
+    import hybrid_vit_cascade_b200 as hvc
+    g32 = _gold("components_d32.pt")
+    c = g32["self_attn"]
+    m = hvc.MultiHeadSelfAttention(64, num_heads=c["num_heads"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x = c["x"].cuda().requires_grad_(True)
+    y = m(x)
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads["x"] = x.grad
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"]), "self_attn_d32")
+
+    c = g32["cross_attn"]
+    m = hvc.MultiHeadCrossAttention(96, 40, num_heads=c["num_heads"], store_attention=True).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x = c["x"].cuda().requires_grad_(True)
+    ctx = c["ctx"].cuda().requires_grad_(True)
+    y = m(x, ctx)
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+    probs = m.attention_weights
+    assert probs.shape == c["probs"].shape and probs.dtype == torch.float32 and not probs.requires_grad
+    assert O.max_rel(probs, c["probs"].float()) <= FWD_TOL
+    assert float((probs.sum(-1) - 1).abs().max()) < 1e-3
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=x.grad, ctx=ctx.grad)
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"]), "cross_attn_d32")
+
+    c = g32["block_attn"]
+    m = hvc.HybridViTBlock3D(64, num_heads=c["num_heads"], context_dim=40, cond_dim=48, return_attention=True).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x, ctx, cond = (c[k].cuda().requires_grad_(True) for k in ("x", "ctx", "cond"))
+    y, amap = m(x, ctx, cond)
+    assert O.max_rel(y, c["y"]) <= FWD_TOL
+    assert O.max_rel(amap, c["attn_map"].float()) <= FWD_TOL
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=x.grad, ctx=ctx.grad, cond=cond.grad)
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"], cond=c["condgrad"]), "block_attn_d32")
+
+
+@pytest.mark.parametrize("name", ["vit_d32", "vit_d32_h4"])
+def test_backbone_golden_head_dim_32(name):
+    import hybrid_vit_cascade_b200 as hvc
+    c = _gold("backbones_d32.pt")[name]
+    m = hvc.HybridViT3D(**c["kwargs"]).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    x, ctx, cond = (c[k].cuda().requires_grad_(True) for k in ("x", "ctx", "cond"))
+    y = m(x, ctx, cond, _dev(c["prev"]))
+    err = O.max_rel(y, c["y"])
+    assert err <= FWD_TOL, err
+    (y * c["r"].cuda()).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=x.grad, ctx=ctx.grad, cond=cond.grad)
+    _check_grads(grads, dict(c["pgrad"], x=c["xgrad"], ctx=c["ctxgrad"], cond=c["condgrad"]), name)
+
+
 def _oracle_on_gpu(cfg, sd, x, ctx, cond, r, attn_chunk=None):
     old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -155,6 +215,33 @@ def test_backbone_direct_config_vs_oracle(volume, grid):
     grads = {k: p.grad for k, p in m.named_parameters()}
     grads.update(x=xs[0].grad, ctx=xs[1].grad, cond=xs[2].grad)
     _check_grads(grads, dict(pg_ref, x=ig_ref[0], ctx=ig_ref[1], cond=ig_ref[2]), f"direct{volume[0]}")
+
+
+def test_cascade_stage2_config_vs_oracle():
+    """Stage2Refiner128's ViT (model_progressive.py:177-186: in_channels=32, C=256, 8 heads -> d=32, 1024 context tokens)
+    at the author's 16^3 token grid, depth 2, batch 1, against the fp32 oracle on the GPU."""
+    import hybrid_vit_cascade_b200 as hvc
+    volume = (128, 128, 128)
+    kw = dict(volume_size=volume, in_channels=32, voxel_dim=256, depth=2, num_heads=8, context_dim=512, cond_dim=1024)
+    cfg = O.BackboneConfig(token_grid=16, **kw)
+    sd = {k: v.cuda() for k, v in O.init_state_dict(cfg, seed=5).items()}
+    m = hvc.HybridViT3D(token_grid=16, **kw).cuda().eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator(device="cuda").manual_seed(13)
+    B, M = 1, 1024
+    x = torch.randn(B, 32, *volume, device="cuda", generator=g) * 0.5
+    ctx = torch.randn(B, M, 512, device="cuda", generator=g)
+    cond = torch.randn(B, 1024, device="cuda", generator=g)
+    r = torch.randn(B, 1, *volume, device="cuda", generator=g)
+    y_ref, pg_ref, ig_ref = _oracle_on_gpu(cfg, sd, x, ctx, cond, r, attn_chunk=1024)
+    xs = [t.clone().requires_grad_(True) for t in (x, ctx, cond)]
+    y = m(*xs)
+    err = O.max_rel(y, y_ref)
+    assert err <= FWD_TOL, err
+    (y * r).sum().backward()
+    grads = {k: p.grad for k, p in m.named_parameters()}
+    grads.update(x=xs[0].grad, ctx=xs[1].grad, cond=xs[2].grad)
+    _check_grads(grads, dict(pg_ref, x=ig_ref[0], ctx=ig_ref[1], cond=ig_ref[2]), "stage2")
 
 
 def test_expanded_input_is_embedded_once_and_exact():
@@ -198,6 +285,56 @@ def test_attention_32768_tokens_against_chunked_fp32():
     ones = torch.ones(N, d, device="cuda", dtype=torch.bfloat16)
     o1, _ = K.attn_fwd(q, k, ones, 1, 1, N, N, d, d ** -0.5)
     assert float((o1.float() - 1).abs().max()) < 1e-2
+
+
+def test_attention_head_dim_32_full_length_properties():
+    """d=32 at the 32768-token length of cascade stages 2/3 (8 heads): rows of the softmax sum to one, and the
+    backward kernel satisfies sum_j dS_ij = 0  <=>  dq is orthogonal to ... checked through dv = P^T dO with dO = 1:
+    column sums of P, whose total must equal the number of queries."""
+    from hybrid_vit_cascade_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(6)
+    N, H, d = 32768, 2, 32
+    qkv = torch.randn(N, 3 * H * d, device="cuda", generator=g).bfloat16()
+    q, k = qkv[:, :H * d], qkv[:, H * d:2 * H * d]
+    ones = torch.ones(N, H * d, device="cuda", dtype=torch.bfloat16)
+    o, lse2 = K.attn_fwd(q, k, ones, 1, H, N, N, d, d ** -0.5)
+    assert float((o.float() - 1).abs().max()) < 1e-2
+    dq, dk, dv = (torch.empty(N, H * d, device="cuda", dtype=torch.bfloat16) for _ in range(3))
+    K.attn_bwd(q, k, ones, o, lse2, ones, 1, H, N, N, d, d ** -0.5, dq, dk, dv)
+    # dv[j, :] = sum_i P_ij (same for every d column); summed over keys it counts the queries
+    tot = dv.float().sum(0)
+    assert float((tot / N - 1).abs().max()) < 2e-2
+    # with V = const, dP = dO V^T is constant per row, so dS = P (dP - delta) = 0: dq = dk = 0
+    assert float(dq.float().abs().max()) < 1e-2 and float(dk.float().abs().max()) < 1e-2
+
+
+def test_works_under_activation_checkpointing():
+    """Stage3Refiner256 wraps the ViT in torch.utils.checkpoint(use_reentrant=False) (model_progressive.py:286-291):
+    same output and gradients as the plain call."""
+    import hybrid_vit_cascade_b200 as hvc
+    from torch.utils.checkpoint import checkpoint
+    torch.manual_seed(0)
+    m = hvc.HybridViT3D(volume_size=(32, 32, 32), in_channels=4, voxel_dim=64, depth=2, num_heads=2,
+                        context_dim=32, cond_dim=64).cuda().eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "adaln.linear" in n:
+                p.normal_(0, 0.02)
+    x = (torch.randn(2, 4, 32, 32, 32, device="cuda") * 0.3).requires_grad_(True)
+    ctx = torch.randn(2, 40, 32, device="cuda")
+    cond = torch.randn(2, 64, device="cuda")
+    y1 = m(x, ctx, cond)
+    y1.square().sum().backward()
+    g1 = {k: p.grad.clone() for k, p in m.named_parameters()}
+    gx1 = x.grad.clone()
+    m.zero_grad(set_to_none=True)
+    x.grad = None
+    y2 = checkpoint(m, x, ctx, cond, use_reentrant=False)
+    y2.square().sum().backward()
+    assert O.max_rel(y2, y1) < 2e-3
+    assert O.cosine(x.grad, gx1) > 0.9999
+    for k, p in m.named_parameters():
+        assert O.cosine(p.grad, g1[k]) > 0.9999, k
 
 
 def test_gradient_linearity_property():
