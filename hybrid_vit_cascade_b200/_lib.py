@@ -19,6 +19,10 @@ class HvcError(RuntimeError):
     pass
 
 
+class Dropout(C.Structure):
+    _fields_ = [("seed", C.c_void_p), ("site", C.c_uint32), ("p", C.c_float)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("size", C.c_uint32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
@@ -33,6 +37,7 @@ class GemmArgs(C.Structure):
         ("rows_per_batch", C.c_int32),
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
         ("alpha", C.c_float), ("k_splits", C.c_int32),
+        ("drop", Dropout),
     ]
 
 
@@ -53,6 +58,7 @@ class AttnArgs(C.Structure):
         ("dq_accum", C.c_void_p),
         ("probs", C.c_void_p),
         ("scale", C.c_float),
+        ("drop", Dropout),
     ]
 
 
@@ -93,6 +99,7 @@ class ResidBwdArgs(C.Structure):
         ("gate", C.c_void_p), ("gate_ld", C.c_int64),
         ("dbranch", C.c_void_p), ("lddbranch", C.c_int64),
         ("dgate", C.c_void_p), ("dbias", C.c_void_p), ("D1", C.c_void_p),
+        ("drop", Dropout),
     ]
 
 

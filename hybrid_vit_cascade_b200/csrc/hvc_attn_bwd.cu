@@ -33,6 +33,8 @@ struct AttnBwdKArgs {
   bf16* dk; long long lddk;
   bf16* dv; long long lddv;
   float scale, scale2;
+  const uint32_t* rowkeys;   // [B, H, nq_pad] dropout row keys (DROP instantiations; written by the pre-pass)
+  DropArg drop;
 };
 
 template <int HD>
@@ -40,7 +42,7 @@ struct BwdSmem {
   static constexpr int kTile = kBT * HD * 2;                 // 16 KB
   static constexpr int kK = 0;
   static constexpr int kV = kTile;
-  static constexpr int kQStage = 2 * kTile + 2048;           // Q, dO, lse2[128], delta[128] (+pad to a 1 KB multiple)
+  static constexpr int kQStage = 2 * kTile + 2048;           // Q, dO, lse2[128], delta[128], dropout row keys[128] (+pad to 1 KB)
   static constexpr int kQ = 2 * kTile;
   static constexpr int kDS = kQ + kQStages * kQStage;        // [128 keys x 128 queries] bf16, two 64-query sub-tiles
   static constexpr int kDQ = kDS + kBT * kBT * 2;            // dQ staging: two [128 x HD/2] fp32 halves (swizzled)
@@ -53,9 +55,12 @@ enum { BB_KV = 0, BB_QF = 1, BB_QE = 4, BB_ST = 7, BB_STFREE = 8, BB_PT = 9, BB_
 // ---- elementwise phases of one (key tile, query tile) pair; thread == key row, 64 query columns per thread.
 // FULL = no padding rows/columns in this pair (the masked variant is a separate code path: selects cost issue slots).
 // Phase A: P^T = exp2(S^T*scale2 - lse2); the pre-pass stores -lse2 so the argument is a single FFMA2.
-template <bool FULL>
+// DROP: attn_drop on P.  The keep decision of element (query, key) is regenerated from the query's row key (smem,
+// written by the pre-pass) and this thread's key column; it is carried to phase B in the SIGN of the fp32 P value
+// (P >= 0): dropped entries are stored negated, and the bf16 P^T that feeds dV is packed with relu (dropped -> 0).
+template <bool FULL, bool DROP>
 __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[64], uint32_t lse_saddr, float2 nss, bool key_ok, int q_valid,
-                                            float2 (&pv)[32], uint32_t (&ppk)[32]) {
+                                            float2 (&pv)[32], uint32_t (&ppk)[32], uint32_t rk_saddr, uint32_t colkey, uint32_t thr) {
 #pragma unroll
   for (int t = 0; t < 64; t += 4) {
     const float4 l4 = lds_f4(lse_saddr + t * 4);
@@ -69,17 +74,26 @@ __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[64], uint32_t l
       e1.x = (key_ok && t + 2 < q_valid) ? e1.x : 0.f;
       e1.y = (key_ok && t + 3 < q_valid) ? e1.y : 0.f;
     }
+    if (DROP) {
+      const uint4 rk = lds_u4(rk_saddr + t * 4);
+      e0.x = mum32(rk.x ^ colkey, 0x2545F491u) >= thr ? e0.x : -e0.x;
+      e0.y = mum32(rk.y ^ colkey, 0x2545F491u) >= thr ? e0.y : -e0.y;
+      e1.x = mum32(rk.z ^ colkey, 0x2545F491u) >= thr ? e1.x : -e1.x;
+      e1.y = mum32(rk.w ^ colkey, 0x2545F491u) >= thr ? e1.y : -e1.y;
+    }
     pv[t >> 1] = e0;
     pv[(t >> 1) + 1] = e1;
-    ppk[t >> 1] = pack_bf16(e0.x, e0.y);
-    ppk[(t >> 1) + 1] = pack_bf16(e1.x, e1.y);
+    ppk[t >> 1] = DROP ? pack_bf16_relu(e0.x, e0.y) : pack_bf16(e0.x, e0.y);
+    ppk[(t >> 1) + 1] = DROP ? pack_bf16_relu(e1.x, e1.y) : pack_bf16(e1.x, e1.y);
   }
 }
 // Phase B: dS^T = P^T * (dP^T - delta) -> swizzled smem sub-tile (8 x 16-byte chunks of this thread's row)
-template <bool FULL>
+// DROP: dS = P * (keep ? dP / (1-p) : 0  -  delta), keep = sign of the stored P value.
+template <bool FULL, bool DROP>
 __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[64], uint32_t delta_saddr, const float2 (&pv)[32], bool key_ok,
-                                            int q_valid, uint32_t sub_saddr, int r) {
+                                            int q_valid, uint32_t sub_saddr, int r, float inv_keep) {
   const float2 neg1 = make_float2(-1.f, -1.f);
+  const float2 rp2 = make_float2(inv_keep, inv_keep);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     uint32_t w4[4];
@@ -87,10 +101,21 @@ __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[64], uint32_t d
     for (int u = 0; u < 2; ++u) {
       const int t = 8 * k + 4 * u;
       const float4 d4 = lds_f4(delta_saddr + t * 4);
-      float2 x0 = ffma2(make_float2(d4.x, d4.y), neg1, make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])));
-      float2 x1 = ffma2(make_float2(d4.z, d4.w), neg1, make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])));
-      x0 = fmul2(x0, pv[t >> 1]);
-      x1 = fmul2(x1, pv[(t >> 1) + 1]);
+      float2 x0, x1;
+      if (DROP) {
+        const float2 p0 = pv[t >> 1], p1 = pv[(t >> 1) + 1];
+        const float2 a0 = ffma2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), rp2, make_float2(-d4.x, -d4.y));
+        const float2 a1 = ffma2(make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])), rp2, make_float2(-d4.z, -d4.w));
+        x0.x = (p0.x > 0.f ? a0.x : -d4.x) * fabsf(p0.x);
+        x0.y = (p0.y > 0.f ? a0.y : -d4.y) * fabsf(p0.y);
+        x1.x = (p1.x > 0.f ? a1.x : -d4.z) * fabsf(p1.x);
+        x1.y = (p1.y > 0.f ? a1.y : -d4.w) * fabsf(p1.y);
+      } else {
+        x0 = ffma2(make_float2(d4.x, d4.y), neg1, make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])));
+        x1 = ffma2(make_float2(d4.z, d4.w), neg1, make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])));
+        x0 = fmul2(x0, pv[t >> 1]);
+        x1 = fmul2(x1, pv[(t >> 1) + 1]);
+      }
       if (!FULL) {   // padded delta may be garbage: 0 * NaN must not leak
         x0.x = (key_ok && t + 0 < q_valid) ? x0.x : 0.f;
         x0.y = (key_ok && t + 1 < q_valid) ? x0.y : 0.f;
@@ -104,7 +129,7 @@ __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[64], uint32_t d
   }
 }
 
-template <int HD>
+template <int HD, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -155,11 +180,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t ph = (i / kQStages) & 1;
         uint8_t* base = smem + L::kQ + st * L::kQStage;
         mbar_wait(&bar[BB_QE + st], ph ^ 1, 10);
-        mbar_arrive_expect_tx(&bar[BB_QF + st], 2 * L::kTile + 2 * kBT * 4);
+        mbar_arrive_expect_tx(&bar[BB_QF + st], 2 * L::kTile + (DROP ? 3 : 2) * kBT * 4);
         tma_load_2d(base, &tmQ, &bar[BB_QF + st], h * HD, b * p.nq + i * kBT, kEvictLast);
         tma_load_2d(base + L::kTile, &tmDO, &bar[BB_QF + st], h * HD, b * p.nq + i * kBT, kEvictLast);
         bulk_load_1d(base + 2 * L::kTile, p.nlse2 + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
         bulk_load_1d(base + 2 * L::kTile + kBT * 4, p.delta + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
+        if (DROP) bulk_load_1d(base + 2 * L::kTile + 2 * kBT * 4, p.rowkeys + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
       }
     }
   } else if (warp == 9) {
@@ -275,10 +301,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     const float2 nss = make_float2(scale2, scale2);
     const uint32_t sub_saddr = smem_u32(smem + L::kDS + wg * 16384);
+    uint32_t colkey = 0, thr = 0;
+    float inv_keep = 1.f;
+    if (DROP) {
+      colkey = static_cast<uint32_t>(j * kBT + r) * kDropColMul;
+      thr = p.drop.thr;
+      inv_keep = p.drop.inv_keep;
+    }
     for (int i = 0; i < nQ; ++i) {
       const int st = i % kQStages;
       const uint32_t lse_saddr = smem_u32(smem + L::kQ + st * L::kQStage + 2 * L::kTile) + wg * 64 * 4;
       const uint32_t delta_saddr = lse_saddr + kBT * 4;
+      const uint32_t rk_saddr = lse_saddr + 2 * kBT * 4;
       const int q_valid = p.nq - i * kBT - wg * 64;        // this warpgroup's columns >= q_valid are padding
       const bool full = keys_full && q_valid >= 64;
       float2 pv[32];                                       // P^T row slice, fp32, lives across phase A -> B
@@ -297,8 +331,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         mbar_arrive(&bar[BB_STFREE]);
         uint32_t ppk[32];
-        if (full) bwd_phase_a<true>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk);
-        else      bwd_phase_a<false>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk);
+        if (full) bwd_phase_a<true, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
+        else      bwd_phase_a<false, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
         tmem_st_32x32(tmem_base + lane_base + kColPt + wg * 32, ppk);
         tmem_st_wait();
         tc_fence_before();
@@ -318,8 +352,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64, d0);
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64 + 32, d1);
         tmem_ld_wait();
-        if (full) bwd_phase_b<true>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r);
-        else      bwd_phase_b<false>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r);
+        if (full) bwd_phase_b<true, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, inv_keep);
+        else      bwd_phase_b<false, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, inv_keep);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -333,7 +367,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD + wg * (HD / 2);
-      const float mul = which == 0 ? 1.0f : p.scale;
+      const float mul = which == 0 ? inv_keep : p.scale;     // dV = (drop(P))^T dO carries the 1/(1-p) of the kept entries
       uint32_t v[HD / 2];
       if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 32, v);
       else                    tmem_ld_32x16(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 16, v);
@@ -364,7 +398,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o,
                                                          long long lddo, const float* __restrict__ lse2, float* __restrict__ delta,
-                                                         float* __restrict__ nlse2, int batch, int heads, int nq, int nq_pad) {
+                                                         float* __restrict__ nlse2, int batch, int heads, int nq, int nq_pad,
+                                                         uint32_t* __restrict__ rowkeys, const DropArg drop) {
   const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const long long total = (long long)batch * nq * heads;
@@ -385,6 +420,7 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
     const long long idx = ((long long)b * heads + h) * nq_pad + q;
     delta[idx] = s;
     nlse2[idx] = -lse2[idx];
+    if (drop.seed != nullptr) rowkeys[idx] = drop_rowkey(drop_load(drop), static_cast<uint32_t>((b * heads + h) * nq + q));
   }
 }
 
@@ -411,18 +447,20 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
 }  // namespace hvc
 
 namespace hvc {
-template <int HD>
+template <int HD, bool DROP>
 static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   using L = BwdSmem<HD>;
   const int nq_pad = (a->nq + 127) / 128 * 128;
   const uint64_t width = (uint64_t)a->heads * HD;
   const int swz = HD == 64 ? 1 : 2;
+  const long long plane = (long long)a->batch * a->heads * nq_pad;
+  const DropArg drop = make_drop(a->drop);
   {
     const long long warps = (long long)a->batch * a->nq * a->heads;
     attn_delta_kernel<HD><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->ldo,
                                                                       reinterpret_cast<const bf16*>(a->d_o), a->lddo, a->lse, a->delta,
-                                                                      a->delta + (long long)a->batch * a->heads * nq_pad, a->batch,
-                                                                      a->heads, a->nq, nq_pad);
+                                                                      a->delta + plane, a->batch, a->heads, a->nq, nq_pad,
+                                                                      reinterpret_cast<uint32_t*>(a->delta + 2 * plane), drop);
     HVC_LAUNCH_CHECK();
   }
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
@@ -435,17 +473,18 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   AttnBwdKArgs ka;
   ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk; ka.nq_pad = nq_pad;
   ka.n_q_tiles = nq_pad / kBT;
-  ka.nlse2 = a->delta + (long long)a->batch * a->heads * nq_pad; ka.delta = a->delta;
+  ka.nlse2 = a->delta + plane; ka.delta = a->delta;
+  ka.rowkeys = reinterpret_cast<const uint32_t*>(a->delta + 2 * plane); ka.drop = drop;
   ka.dk = reinterpret_cast<bf16*>(a->dk); ka.lddk = a->lddk;
   ka.dv = reinterpret_cast<bf16*>(a->dv); ka.lddv = a->lddv;
   ka.scale = a->scale; ka.scale2 = a->scale * 1.4426950408889634f;
   static bool configured = false;
   if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    HVC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   dim3 grid((a->nk + kBT - 1) / kBT, a->batch * a->heads);
-  attn_bwd_kernel<HD><<<grid, kBwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, ka);
+  attn_bwd_kernel<HD, DROP><<<grid, kBwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, ka);
   HVC_LAUNCH_CHECK();
   {
     const long long threads = (long long)a->batch * a->nq * a->heads * (HD / 8);
@@ -466,5 +505,8 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
                 "hvc_attn_bwd: null operand");
   HVC_CHECK_ARG(((a->lddq | a->lddk | a->lddv) & 7) == 0, "hvc_attn_bwd: gradient row pitches must be multiples of 8");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return a->head_dim == 64 ? launch_attn_bwd<64>(a, st) : launch_attn_bwd<32>(a, st);
+  const bool drop = a->drop.seed != nullptr && a->drop.p > 0.f;
+  HVC_CHECK_ARG(!drop || a->drop.p < 1.f, "hvc_attn_bwd: dropout p must be < 1");
+  return a->head_dim == 64 ? (drop ? launch_attn_bwd<64, true>(a, st) : launch_attn_bwd<64, false>(a, st))
+                           : (drop ? launch_attn_bwd<32, true>(a, st) : launch_attn_bwd<32, false>(a, st));
 }

@@ -31,6 +31,7 @@ struct AttnFwdKArgs {
   float* lse2;      // [B, H, nq_pad]  log2-domain logsumexp of the scaled scores
   int nq_pad;
   float scale2;     // softmax scale * log2(e)
+  DropArg drop;     // attn_drop on P (vit_components.py:49,110); used by the DROP instantiations only
 };
 
 template <int HD>
@@ -72,9 +73,11 @@ __device__ __forceinline__ float softmax_rowmax(uint32_t tS, int tail) {
   return fmaxf(a0, a1);
 }
 
-template <bool MASKED>
+// rowkey/col0/thr: dropout on P (DROP): the row sum uses the undropped probabilities (softmax normalisation comes
+// before nn.Dropout in the reference), the P that feeds P V has the dropped entries zeroed; 1/(1-p) is applied to O.
+template <bool MASKED, bool DROP>
 __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint32_t tP, int c0, int tail, float2 scale2v, float2 neg_m,
-                                                  float2& sum) {
+                                                  float2& sum, uint32_t rowkey, uint32_t col0, uint32_t thr) {
   uint32_t pk[16];
 #pragma unroll
   for (int c = 0; c < 32; c += 2) {
@@ -85,6 +88,10 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
       e.y = (c0 + c + 1 < tail) ? e.y : 0.f;
     }
     sum = fadd2(sum, e);
+    if (DROP) {
+      e.x = drop_keep(rowkey, col0 + c0 + c, thr) ? e.x : 0.f;
+      e.y = drop_keep(rowkey, col0 + c0 + c + 1, thr) ? e.y : 0.f;
+    }
     pk[c >> 1] = pack_bf16(e.x, e.y);
   }
   tmem_st_32x16(tP + (c0 >> 1), pk);   // P (bf16 pairs) over S columns that were already consumed
@@ -92,8 +99,9 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
 
 // P = exp2(S*scale2 - m): chunk c+1 is fetched from TMEM while chunk c is exponentiated.  The section between the
 // named-barrier sync and arrive is the warpgroup's turn on the MUFU pipe.
-template <bool MASKED>
-__device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2, float m, int turn_bar, int next_bar, bool hand_over) {
+template <bool MASKED, bool DROP>
+__device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2, float m, int turn_bar, int next_bar, bool hand_over,
+                                             uint32_t rowkey, uint32_t col0, uint32_t thr) {
   const float2 scale2v = make_float2(scale2, scale2), neg_m = make_float2(-m, -m);
   float2 sum = make_float2(0.f, 0.f);
   uint32_t bufa[32], bufb[32];
@@ -101,20 +109,20 @@ __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2
   named_bar_sync(turn_bar, 256);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 32, bufb);
-  softmax_exp_chunk<MASKED>(bufa, tS, 0, tail, scale2v, neg_m, sum);
+  softmax_exp_chunk<MASKED, DROP>(bufa, tS, 0, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 64, bufa);
-  softmax_exp_chunk<MASKED>(bufb, tS, 32, tail, scale2v, neg_m, sum);
+  softmax_exp_chunk<MASKED, DROP>(bufb, tS, 32, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 96, bufb);
-  softmax_exp_chunk<MASKED>(bufa, tS, 64, tail, scale2v, neg_m, sum);
+  softmax_exp_chunk<MASKED, DROP>(bufa, tS, 64, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
-  softmax_exp_chunk<MASKED>(bufb, tS, 96, tail, scale2v, neg_m, sum);
+  softmax_exp_chunk<MASKED, DROP>(bufb, tS, 96, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   if (hand_over) named_bar_arrive(next_bar, 256);
   return sum.x + sum.y;
 }
 
-template <int HD>
+template <int HD, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdKArgs p) {
@@ -237,6 +245,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float scale2 = p.scale2;
     float m = -INFINITY, l = 0.f;
     const int tail = p.nk - (n_tiles - 1) * kKTile;   // valid keys in the last tile (1..128)
+    uint32_t rowkey = 0, thr = 0;
+    float inv_keep = 1.f;
+    if (DROP) {
+      const DropCfg dc = drop_load(p.drop);
+      rowkey = drop_rowkey(dc, static_cast<uint32_t>(bh * p.nq + q0 + x * kQTile + row));
+      thr = dc.thr;
+      inv_keep = dc.inv_keep;
+    }
     // The two warpgroups take turns in the MUFU-bound exp section (named barriers 1 and 2): while one runs
     // exp2 the other waits for its next S tile, loads it and finds the row maximum.
     if (x == 1) named_bar_arrive(1, 256);             // warpgroup A goes first
@@ -272,8 +288,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // ---- pass 2 (my turn on the MUFU pipe): P = exp2(S*scale2 - m) -> TMEM, row sum
       const bool hand_over = !(x == 1 && j == n_tiles - 1);
-      l += masked ? softmax_exp<true>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over)
-                  : softmax_exp<false>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over);
+      l += masked ? softmax_exp<true, DROP>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr)
+                  : softmax_exp<false, DROP>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar[BAR_PF + x]);
@@ -283,7 +299,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bar[BAR_OD + x], (n_tiles - 1) & 1, 32);
     tc_fence_after();
     const int q = q0 + x * kQTile + row;
-    const float inv = 1.0f / l;
+    const float inv = inv_keep / l;
     bf16* optr = p.o + (long long)(b * p.nq + q) * p.ldo + h * HD;
 #pragma unroll
     for (int c = 0; c < HD; c += 32) {
@@ -316,7 +332,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace hvc
 
 namespace hvc {
-template <int HD>
+template <int HD, bool DROP>
 static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   using L = FwdSmem<HD>;
   const uint64_t width = (uint64_t)a->heads * HD;
@@ -333,13 +349,14 @@ static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   ka.lse2 = reinterpret_cast<float*>(a->lse);
   ka.nq_pad = (a->nq + 127) / 128 * 128;
   ka.scale2 = a->scale * 1.4426950408889634f;
+  ka.drop = make_drop(a->drop);
   static bool configured = false;
   if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    HVC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   dim3 grid((a->nq + 2 * kQTile - 1) / (2 * kQTile), a->batch * a->heads);
-  attn_fwd_kernel<HD><<<grid, kFwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, ka);
+  attn_fwd_kernel<HD, DROP><<<grid, kFwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, ka);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
@@ -392,7 +409,10 @@ extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
   HVC_CHECK_ARG((a->ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(a->o) & 15) == 0, "hvc_attn_fwd: o must be 16-byte aligned rows");
   HVC_CHECK_ARG(a->probs == nullptr || a->lse != nullptr, "hvc_attn_fwd: probs needs lse");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int rc = a->head_dim == 64 ? launch_attn_fwd<64>(a, st) : launch_attn_fwd<32>(a, st);
+  const bool drop = a->drop.seed != nullptr && a->drop.p > 0.f;
+  HVC_CHECK_ARG(!drop || a->drop.p < 1.f, "hvc_attn_fwd: dropout p must be < 1");
+  const int rc = a->head_dim == 64 ? (drop ? launch_attn_fwd<64, true>(a, st) : launch_attn_fwd<64, false>(a, st))
+                                   : (drop ? launch_attn_fwd<32, true>(a, st) : launch_attn_fwd<32, false>(a, st));
   if (rc != HVC_OK || a->probs == nullptr) return rc;
   return attn_store_probs(a, st);
 }

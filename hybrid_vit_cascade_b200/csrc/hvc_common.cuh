@@ -14,6 +14,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include "../../include/hvc.h"
+
 namespace hvc {
 
 typedef __nv_bfloat16 bf16;
@@ -286,6 +288,17 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   bf162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// same, negative inputs clamp to +0 (the sign bit carries the dropout decision in the attention backward)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   bf162 v = *reinterpret_cast<bf162*>(&u);
   return __bfloat1622float2(v);
@@ -320,6 +333,51 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ------------------------------------------------------------------ dropout masks (counter-based, layout-free)
+// nn.Dropout on the hot path (vit_components.py:27-29,76-78; hybrid_vit_backbone.py:78,80) is applied inside the
+// kernels.  keep(row, col) is a pure function of (seed words, site, row, col), so forward and backward kernels with
+// different thread layouts regenerate the same mask and nothing of mask size is stored.  The seed is two 32-bit
+// words drawn by the caller from torch's CUDA generator (replayed by torch.utils.checkpoint) and read from device
+// memory, so no host synchronisation is needed.  Mixer: 32x32->64 multiply folded by xor ("mum"); three rounds for
+// the per-row key, one per element.  oracle/dropout_mask.py restates it for the parity tests.
+struct DropCfg {
+  uint32_t k0, k1, site, thr;   // drop element iff hash < thr (thr = p * 2^32)
+  float inv_keep;               // 1 / (1 - p)
+};
+__device__ __forceinline__ uint32_t mum32(uint32_t a, uint32_t b) {
+  const uint64_t w = static_cast<uint64_t>(a) * b;
+  return static_cast<uint32_t>(w) ^ static_cast<uint32_t>(w >> 32);
+}
+__device__ __forceinline__ uint32_t drop_rowkey(const DropCfg& c, uint32_t row) {
+  uint32_t h = mum32(row ^ c.k0, 0x9E3779B1u);
+  h = mum32(h ^ c.site ^ c.k1, 0x85EBCA77u);
+  return mum32(h + 0x6A09E667u, 0xC2B2AE3Du);
+}
+constexpr uint32_t kDropColMul = 0x9E3779B1u;
+__device__ __forceinline__ uint32_t drop_hash(uint32_t rowkey, uint32_t col) { return mum32(rowkey ^ (col * kDropColMul), 0x2545F491u); }
+__device__ __forceinline__ bool drop_keep(uint32_t rowkey, uint32_t col, uint32_t thr) { return drop_hash(rowkey, col) >= thr; }
+// host-side description -> kernel config (reads the seed words on the device)
+struct DropArg {
+  const uint32_t* seed; uint32_t site; uint32_t thr; float inv_keep;   // seed == nullptr: disabled
+};
+// hvc_dropout (C ABI) -> DropArg; disabled when seed is NULL or p <= 0
+inline DropArg make_drop(const hvc_dropout& d) {
+  DropArg r;
+  const bool on = d.seed != nullptr && d.p > 0.f;
+  r.seed = on ? d.seed : nullptr;
+  r.site = d.site;
+  double t = on ? (double)d.p * 4294967296.0 : 0.0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  r.thr = (uint32_t)t;
+  r.inv_keep = on ? (float)(1.0 / (1.0 - (double)r.thr / 4294967296.0)) : 1.f;
+  return r;
+}
+__device__ __forceinline__ DropCfg drop_load(const DropArg& a) {
+  DropCfg c;
+  c.k0 = __ldg(a.seed); c.k1 = __ldg(a.seed + 1); c.site = a.site; c.thr = a.thr; c.inv_keep = a.inv_keep;
+  return c;
 }
 
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled tile whose rows are 128 B

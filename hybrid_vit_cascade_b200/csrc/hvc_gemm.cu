@@ -40,6 +40,7 @@ struct GemmKArgs {
   int rows_per_batch;
   const bf16* aux; long long ldaux;
   float alpha;
+  DropArg drop;   // fused nn.Dropout on the epilogue value (seed == nullptr: off)
 };
 
 struct WorkItem {
@@ -54,6 +55,14 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKArgs& p, int w) {
   it.kb0 = split * p.kb_per_split;
   it.kb1 = min(it.kb0 + p.kb_per_split, p.k_blocks);
   return it;
+}
+
+// nn.Dropout on the 32 values of one row chunk: element (row, col) of this site, see hvc_common.cuh
+__device__ __forceinline__ void epilogue_dropout(const GemmKArgs& p, float (&v)[32], int row, int col0) {
+  const DropCfg dc = drop_load(p.drop);
+  const uint32_t rk = drop_rowkey(dc, static_cast<uint32_t>(row));
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = drop_keep(rk, static_cast<uint32_t>(col0 + j), dc.thr) ? v[j] * dc.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------- epilogue for one 32-column chunk
@@ -75,6 +84,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_
     }
   }
   const bool vec = (ncols == 32);
+  const bool drop = p.drop.seed != nullptr;
+  if (drop && p.epilogue != HVC_EPI_BF16) epilogue_dropout(p, v, row, col0);   // residual / f32: the value before gate + residual
 
   if (p.epilogue == HVC_EPI_BF16) {
     if (p.out2 != nullptr) {
@@ -109,6 +120,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_
         _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) v[j] *= gelu_erf_grad(__bfloat162float(ax[j]));
       }
     }
+    if (drop) epilogue_dropout(p, v, row, col0);   // after the activation (mlp: Linear -> GELU -> Dropout); out2 stays pre-activation
     bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0;
     if (vec && (p.ldo & 7) == 0) {
 #pragma unroll
@@ -347,6 +359,8 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   ka.gate = a->gate; ka.gate_ld = a->gate_ld; ka.rows_per_batch = a->rows_per_batch > 0 ? a->rows_per_batch : 1;
   ka.aux = reinterpret_cast<const bf16*>(a->aux); ka.ldaux = a->ldaux;
   ka.alpha = a->alpha;
+  ka.drop = make_drop(a->drop);
+  HVC_CHECK_ARG(ka.drop.seed == nullptr || (a->epilogue != HVC_EPI_F32_ATOMIC && a->drop.p < 1.f), "hvc_gemm: dropout needs p < 1 and a non-atomic epilogue");
 
   const long long num_work = (long long)ka.m_blocks * ka.n_blocks * ka.k_splits;
   const int sms = device_sm_count();

@@ -258,6 +258,7 @@ struct ResidBwdArgs {
   bf16* dbranch; long long lddb;
   float* D1; float* D2;
   int rows_per_batch, rows_per_block, C;
+  DropArg drop;   // the dropout applied to branch in the forward epilogue (seed == nullptr: none)
 };
 template <int VPL>
 __global__ void __launch_bounds__(256) resid_bwd_kernel(const ResidBwdArgs a) {
@@ -277,14 +278,22 @@ __global__ void __launch_bounds__(256) resid_bwd_kernel(const ResidBwdArgs a) {
     float4 d[VPL], br[VPL];
     load_row_f32<VPL>(a.dout + row * a.lddo, a.C, lane, d);
     if (a.branch) load_row_bf16<VPL>(a.branch + row * a.ldbr, a.C, lane, br);
+    uint32_t rk = 0;
+    if (a.drop.seed != nullptr) rk = drop_rowkey(drop_load(a.drop), static_cast<uint32_t>(row));
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int c = 4 * (lane + 32 * i);
-      s1[i].x += d[i].x; s1[i].y += d[i].y; s1[i].z += d[i].z; s1[i].w += d[i].w;
-      if (a.branch) {
+      if (a.branch) {     // dgate: branch already is the dropped (and rescaled) value, so the raw gradient is used here
         s2[i].x += d[i].x * br[i].x; s2[i].y += d[i].y * br[i].y;
         s2[i].z += d[i].z * br[i].z; s2[i].w += d[i].w * br[i].w;
       }
+      if (a.drop.seed != nullptr) {   // d(pre-dropout branch) = mask / (1-p) * gate * dout
+        d[i].x = drop_keep(rk, c, a.drop.thr) ? d[i].x * a.drop.inv_keep : 0.f;
+        d[i].y = drop_keep(rk, c + 1, a.drop.thr) ? d[i].y * a.drop.inv_keep : 0.f;
+        d[i].z = drop_keep(rk, c + 2, a.drop.thr) ? d[i].z * a.drop.inv_keep : 0.f;
+        d[i].w = drop_keep(rk, c + 3, a.drop.thr) ? d[i].w * a.drop.inv_keep : 0.f;
+      }
+      s1[i].x += d[i].x; s1[i].y += d[i].y; s1[i].z += d[i].z; s1[i].w += d[i].w;
       if (c < a.C) {
         uint2 u = make_uint2(pack_bf16(d[i].x * gv[i].x, d[i].y * gv[i].y), pack_bf16(d[i].z * gv[i].z, d[i].w * gv[i].w));
         *reinterpret_cast<uint2*>(a.dbranch + row * a.lddb + c) = u;
@@ -494,6 +503,8 @@ extern "C" int hvc_resid_bwd(const hvc_resid_bwd_args* a, void* stream) {
   k.dout = a->dout; k.lddo = a->lddout; k.branch = a->dgate ? reinterpret_cast<const bf16*>(a->branch) : nullptr; k.ldbr = a->ldbranch;
   k.gate = a->gate; k.gate_ld = a->gate_ld; k.dbranch = reinterpret_cast<bf16*>(a->dbranch); k.lddb = a->lddbranch;
   k.D1 = a->D1; k.D2 = a->dgate; k.rows_per_batch = a->rows_per_batch; k.C = a->C;
+  k.drop = make_drop(a->drop);
+  HVC_CHECK_ARG(k.drop.seed == nullptr || a->drop.p < 1.f, "hvc_resid_bwd: dropout p must be < 1");
   int rpb = 64;
   while (rpb > 8 && (long long)a->batch * ((a->rows_per_batch + rpb - 1) / rpb) < 4LL * device_sm_count()) rpb >>= 1;
   k.rows_per_block = rpb;

@@ -16,9 +16,10 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
+from . import kernels as K
 from . import ops
 from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHeadSelfAttention,
-                             SinusoidalTimeEmbedding, _check_dropout, _check_heads)  # noqa: F401
+                             SinusoidalTimeEmbedding, _check_heads, _drop_cfg, _p)  # noqa: F401
 
 
 class HybridViTBlock3D(nn.Module):
@@ -50,29 +51,41 @@ class HybridViTBlock3D(nn.Module):
             prev_stage_embed = torch.zeros(batch, 256, device=cond.device, dtype=cond.dtype)
         return torch.cat([cond, prev_stage_embed], dim=-1)
 
-    def _forward_tokens(self, x, ctx16, cond, B, N, M):
-        """x: fp32 [B*N, C] residual stream; ctx16: bf16 [B*M, Cc]; cond already combined."""
+    def dropout_probs(self):
+        """Effective p of the six nn.Dropout sites of the block (all 0 in eval mode), reference :75-81 and
+        vit_components.py:27-29,76-78."""
+        sa, ca = self.self_attn, self.cross_attn
+        return (_p(sa.attn_drop), _p(sa.proj_drop), _p(ca.attn_drop), _p(ca.proj_drop), _p(self.mlp[2]), _p(self.mlp[4]))
+
+    def _forward_tokens(self, x, ctx16, cond, B, N, M, seed=None, site_base=0):
+        """x: fp32 [B*N, C] residual stream; ctx16: bf16 [B*M, Cc]; cond already combined.
+        seed/site_base: dropout seed words shared by the whole backbone call and this block's first site id."""
         C = self.voxel_dim
         H = self.self_attn.num_heads
         sa, ca = self.self_attn, self.cross_attn
+        ps = self.dropout_probs()
+        if seed is None and any(p > 0.0 for p in ps):
+            seed = K.new_seed(x.device)
+        d_sa = _drop_cfg(x.device, ps[0], ps[1], seed, site_base)
+        d_ca = _drop_cfg(x.device, ps[2], ps[3], seed, site_base + 2)
+        d_mlp = _drop_cfg(x.device, ps[4], ps[5], seed, site_base + 4)
         mod = self.adaln.params(cond)                                   # (B, 6C)
         x = ops.SelfAttnBranch.apply(x, mod, self.norm1.weight, self.norm1.bias, sa.qkv.weight, sa.proj.weight,
-                                     sa.proj.bias, B, N, H, 0)
+                                     sa.proj.bias, B, N, H, 0, d_sa)
         if ca.store_attention:      # reference :130-133 reads it back from the cross-attention module
             x, probs = ops.CrossAttnBranch.apply(x, ctx16, self.norm2.weight, self.norm2.bias, ca.q.weight, ca.kv.weight,
-                                                 ca.proj.weight, ca.proj.bias, B, N, M, H, True)
+                                                 ca.proj.weight, ca.proj.bias, B, N, M, H, True, d_ca)
             ca.attention_weights = probs.detach()
         else:
             x = ops.CrossAttnBranch.apply(x, ctx16, self.norm2.weight, self.norm2.bias, ca.q.weight, ca.kv.weight,
-                                          ca.proj.weight, ca.proj.bias, B, N, M, H)
+                                          ca.proj.weight, ca.proj.bias, B, N, M, H, False, d_ca)
         x = ops.MlpBranch.apply(x, mod, self.norm3.weight, self.norm3.bias, self.mlp[0].weight, self.mlp[0].bias,
-                                self.mlp[3].weight, self.mlp[3].bias, B, N, 3 * C)
+                                self.mlp[3].weight, self.mlp[3].bias, B, N, 3 * C, d_mlp)
         return x
 
     def forward(self, voxel_features: torch.Tensor, xray_context: torch.Tensor, cond: torch.Tensor,
                 prev_stage_embed: Optional[torch.Tensor] = None):
         _check_heads(self.voxel_dim, self.self_attn.num_heads)
-        _check_dropout(self, self.self_attn.attn_drop.p)
         B, N, C = voxel_features.shape
         M = xray_context.shape[1]
         cond = self._combined_cond(cond, prev_stage_embed, B)
@@ -155,13 +168,15 @@ class HybridViT3D(nn.Module):
         N, M = Dd * Hd * Wd, context.shape[1]
         if len(self.blocks):
             _check_heads(self.voxel_dim, self.blocks[0].self_attn.num_heads)
-            _check_dropout(self, self.blocks[0].self_attn.attn_drop.p)
         if not self._plan:
             raise NotImplementedError("in_channels == voxel_dim with no downsampling leaves voxel_embed empty")
         tok = ops.VoxelEmbed.apply(x, self.pos_embed, self._plan, *self._embed_params())     # fp32 [B*N, C]
         ctx16 = ops.CastTokens.apply(context)
-        for blk in self.blocks:
+        seed = None
+        if any(p > 0.0 for blk in self.blocks for p in blk.dropout_probs()):
+            seed = K.new_seed(tok.device)      # one draw per forward; every dropout site of every block derives from it
+        for i, blk in enumerate(self.blocks):
             c = blk._combined_cond(cond, prev_stage_embed, B)
-            tok = blk._forward_tokens(tok, ctx16, c, B, N, M)
+            tok = blk._forward_tokens(tok, ctx16, c, B, N, M, seed, 8 * i)
         return ops.OutputHead.apply(tok, self.norm.weight, self.norm.bias, self.output_proj.weight,
                                     self.output_proj.bias, B, (Dd, Hd, Wd), (D, H, W))

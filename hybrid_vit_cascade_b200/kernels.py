@@ -40,6 +40,27 @@ class _timed:
         return False
 
 
+class Drop:
+    """One dropout site: (seed, site, p).  seed = int32[2] device tensor drawn from torch's CUDA generator (new_seed),
+    site separates the sites sharing it, p the drop probability.  None / p == 0 means no dropout."""
+    __slots__ = ("seed", "site", "p")
+
+    def __init__(self, seed, site, p):
+        self.seed, self.site, self.p = seed, int(site), float(p)
+
+
+def new_seed(device):
+    """Two random 32-bit words on the device, taken from torch's CUDA generator: no host sync, and
+    torch.utils.checkpoint (which restores the generator state before recomputing) replays the same words."""
+    return torch.randint(-2 ** 31, 2 ** 31 - 1, (2,), dtype=torch.int32, device=device)
+
+
+def _set_drop(args, drop):
+    if drop is not None and drop.p > 0.0:
+        assert drop.seed.is_cuda and drop.seed.dtype == torch.int32 and drop.seed.numel() == 2
+        args.drop.seed, args.drop.site, args.drop.p = drop.seed.data_ptr(), drop.site, drop.p
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -65,7 +86,7 @@ def _row_major_2d(t, name):
 
 def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epilogue=EPI_BF16,
          activation=ACT_NONE, bias=None, out2=None, resid=None, gate=None, gate_ld=0, rows_per_batch=0,
-         aux=None, alpha=1.0, k_splits=1):
+         aux=None, alpha=1.0, k_splits=1, drop=None):
     """D[M,N] = alpha * sum_k A(m,k) B(n,k) with a fused epilogue (see include/hvc.h).
 
     a: bf16, stored [M,K] (a_major=0) or [K,M] (a_major=1); b: bf16, stored [N,K] or [K,N].
@@ -106,6 +127,7 @@ def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epil
         args.aux, args.ldaux = aux.data_ptr(), _row_major_2d(aux, "aux")
     args.alpha = alpha
     args.k_splits = k_splits
+    _set_drop(args, drop)
     with _timed("gemm", 2.0 * M * N * K):
         _lib.check(_lib.lib().hvc_gemm(C.byref(args), _stream()), "hvc_gemm")
     return out
@@ -126,7 +148,7 @@ def _attn_args(q, k, v, B, H, nq, nk, d, scale):
     return args
 
 
-def attn_fwd(q, k, v, B, H, nq, nk, d, scale, want_probs=False):
+def attn_fwd(q, k, v, B, H, nq, nk, d, scale, want_probs=False, drop=None):
     """q: bf16 view [B*nq, H*d] (may be a column slice of a packed projection output), k/v: [B*nk, H*d].
 
     Returns (o bf16 [B*nq, H*d], lse2 f32 [B, H, pad128(nq)]) and, with want_probs (the store_attention slow
@@ -140,6 +162,7 @@ def attn_fwd(q, k, v, B, H, nq, nk, d, scale, want_probs=False):
     args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
     args.o, args.ldo = o.data_ptr(), o.stride(0)
     args.lse = lse.data_ptr()
+    _set_drop(args, drop)
     probs = None
     if want_probs:
         probs = torch.empty(B, H, nq, nk, device=q.device, dtype=torch.float32)
@@ -151,12 +174,12 @@ def attn_fwd(q, k, v, B, H, nq, nk, d, scale, want_probs=False):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, lse, d_o, B, H, nq, nk, d, scale, dq, dk, dv):
+def attn_bwd(q, k, v, o, lse, d_o, B, H, nq, nk, d, scale, dq, dk, dv, drop=None):
     """Backward of attn_fwd.  dq/dk/dv: bf16 views [B*n, H*d] (column slices of packed gradient buffers)."""
     _need_cuda(q, k, v, o, d_o)
     assert d_o.dtype == torch.bfloat16 and o.dtype == torch.bfloat16
     nq_pad = _pad128(nq)
-    delta = torch.empty(2, B, H, nq_pad, device=q.device, dtype=torch.float32)
+    delta = torch.empty(3, B, H, nq_pad, device=q.device, dtype=torch.float32)
     dq_accum = torch.zeros(B, H, nq_pad, d, device=q.device, dtype=torch.float32)
     args = _attn_args(q, k, v, B, H, nq, nk, d, scale)
     args.o, args.ldo = o.data_ptr(), _row_major_2d(o, "o")
@@ -167,6 +190,7 @@ def attn_bwd(q, k, v, o, lse, d_o, B, H, nq, nk, d, scale, dq, dk, dv):
     args.dv, args.lddv = dv.data_ptr(), _row_major_2d(dv, "dv")
     args.delta = delta.data_ptr()
     args.dq_accum = dq_accum.data_ptr()
+    _set_drop(args, drop)
     with _timed("attn_bwd", 10.0 * B * H * nq * nk * d):
         _lib.check(_lib.lib().hvc_attn_bwd(C.byref(args), _stream()), "hvc_attn_bwd")
     return dq, dk, dv
@@ -238,7 +262,7 @@ def ln_bwd(dz, x, mean, rstd, w, b, batch, rows_per_batch, scale=None, mod_ld=0,
     return out
 
 
-def resid_bwd(dout, batch, rows_per_batch, branch=None, gate=None, gate_ld=0, want_dbias=True):
+def resid_bwd(dout, batch, rows_per_batch, branch=None, gate=None, gate_ld=0, want_dbias=True, drop=None):
     """dout f32 [T,C] -> (dbranch bf16 [T,C], dgate f32 [batch,C] | None, dbias f32 [C] | None)."""
     _need_cuda(dout)
     T, Cc = dout.shape
@@ -260,6 +284,7 @@ def resid_bwd(dout, batch, rows_per_batch, branch=None, gate=None, gate_ld=0, wa
     a.dbias = _ptr(dbias)
     d1 = torch.empty(batch, Cc, device=dev, dtype=torch.float32)
     a.D1 = d1.data_ptr()
+    _set_drop(a, drop)
     _lib.check(_lib.lib().hvc_resid_bwd(C.byref(a), _stream()), "hvc_resid_bwd")
     return dbranch, dgate, dbias
 

@@ -70,6 +70,15 @@ def _dgrad(dy16, w_16, f32_out=False, **kw):
     return K.gemm(dy16, w_16, b_major=1, **kw)
 
 
+def _drops(drop):
+    """drop = None | (seed, site_base, p_first, p_second) -> the two kernel-level dropout sites of a sub-block
+    (attention probabilities / projection output, or MLP activation / MLP output)."""
+    if drop is None:
+        return None, None
+    seed, base, pa, pb = drop
+    return (K.Drop(seed, base, pa) if pa > 0 else None), (K.Drop(seed, base + 1, pb) if pb > 0 else None)
+
+
 def _mod_views(mod, off, C):
     return mod[:, off:off + C], mod[:, off + C:off + 2 * C], mod[:, off + 2 * C:off + 3 * C]
 
@@ -117,18 +126,20 @@ class SelfAttnBranch(Function):
     """x + gate_sa * proj(attn(qkv((1+scale_sa) * LN1(x) + shift_sa)))   hybrid_vit_backbone.py:120-123."""
 
     @staticmethod
-    def forward(ctx, x, mod, ln_w, ln_b, w_qkv, w_proj, b_proj, B, N, H, off):
+    def forward(ctx, x, mod, ln_w, ln_b, w_qkv, w_proj, b_proj, B, N, H, off, drop=None):
         T, C = x.shape
         d = C // H
         shift, scale, gate = _mod_views(mod, off, C)
+        d_attn, d_proj = _drops(drop)
         y, mean, rstd = K.ln_fwd(x, ln_w, ln_b, shift, scale, mod.stride(0), N)
         qkv = K.gemm(y, w16(w_qkv))
-        o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, d, d ** -0.5)
+        o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, d, d ** -0.5, drop=d_attn)
         branch = torch.empty(T, C, device=x.device, dtype=torch.bfloat16)
         out = K.gemm(o, w16(w_proj), epilogue=K.EPI_RESIDUAL, bias=b_proj, resid=x, gate=gate, gate_ld=mod.stride(0),
-                     rows_per_batch=N, out2=branch)
+                     rows_per_batch=N, out2=branch, drop=d_proj)
         ctx.save_for_backward(x, mod, ln_w, ln_b, w_qkv, w_proj, mean, rstd, y, qkv, o, lse, branch)
         ctx.dims = (B, N, H, off)
+        ctx.drop = drop
         return out
 
     @staticmethod
@@ -139,12 +150,13 @@ class SelfAttnBranch(Function):
         d = C // H
         dout = dout.contiguous()
         shift, scale, gate = _mod_views(mod, off, C)
-        dbranch, dgate, db_proj = K.resid_bwd(dout, B, N, branch=branch, gate=gate, gate_ld=mod.stride(0))
+        d_attn, d_proj = _drops(ctx.drop)
+        dbranch, dgate, db_proj = K.resid_bwd(dout, B, N, branch=branch, gate=gate, gate_ld=mod.stride(0), drop=d_proj)
         dw_proj = _wgrad(dbranch, o)
         d_o = _dgrad(dbranch, w16(w_proj))
         dqkv = torch.empty(T, 3 * C, device=x.device, dtype=torch.bfloat16)
         K.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, d_o, B, H, N, N, d, d ** -0.5,
-                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:])
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], drop=d_attn)
         dw_qkv = _wgrad(dqkv, y)
         dy = _dgrad(dqkv, w16(w_qkv))
         r = K.ln_bwd(dy, x, mean, rstd, ln_w, ln_b, B, N, scale=scale, mod_ld=mod.stride(0), dx_in=dout, want_mod=True)
@@ -152,7 +164,7 @@ class SelfAttnBranch(Function):
         dmod[:, off:off + C] = r["dmod"][:, 0]
         dmod[:, off + C:off + 2 * C] = r["dmod"][:, 1]
         dmod[:, off + 2 * C:off + 3 * C] = dgate
-        return r["dx"], dmod, r["dw"], r["db"], dw_qkv, dw_proj, db_proj, None, None, None, None
+        return r["dx"], dmod, r["dw"], r["db"], dw_qkv, dw_proj, db_proj, None, None, None, None, None
 
 
 # ------------------------------------------------------------------ cross-attention sub-block (a2 inside a5)
@@ -161,17 +173,19 @@ class CrossAttnBranch(Function):
     """x + proj(attn(q(LN2(x)), kv(context)))   hybrid_vit_backbone.py:126-128."""
 
     @staticmethod
-    def forward(ctx, x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, b_proj, B, N, M, H, store_probs=False):
+    def forward(ctx, x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, b_proj, B, N, M, H, store_probs=False, drop=None):
         T, C = x.shape
         d = C // H
+        d_attn, d_proj = _drops(drop)
         y, mean, rstd = K.ln_fwd(x, ln_w, ln_b)
         q = K.gemm(y, w16(w_q))
         kv = K.gemm(ctx16, w16(w_kv))
-        res = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5, want_probs=store_probs)
+        res = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5, want_probs=store_probs, drop=d_attn)
         o, lse = res[0], res[1]
-        out = K.gemm(o, w16(w_proj), epilogue=K.EPI_RESIDUAL, bias=b_proj, resid=x)
+        out = K.gemm(o, w16(w_proj), epilogue=K.EPI_RESIDUAL, bias=b_proj, resid=x, drop=d_proj)
         ctx.save_for_backward(x, ctx16, ln_w, ln_b, w_q, w_kv, w_proj, mean, rstd, y, q, kv, o, lse)
         ctx.dims = (B, N, M, H)
+        ctx.drop = drop
         if store_probs:      # attention map (B, H, N, M): a detached diagnostic output (vit_components.py:106-108)
             ctx.mark_non_differentiable(res[2])
             return out, res[2]
@@ -184,18 +198,19 @@ class CrossAttnBranch(Function):
         T, C = x.shape
         d = C // H
         dout = dout.contiguous()
-        dbranch, _, db_proj = K.resid_bwd(dout, B, N)
+        d_attn, d_proj = _drops(ctx.drop)
+        dbranch, _, db_proj = K.resid_bwd(dout, B, N, drop=d_proj)
         dw_proj = _wgrad(dbranch, o)
         d_o = _dgrad(dbranch, w16(w_proj))
         dq = torch.empty(T, C, device=x.device, dtype=torch.bfloat16)
         dkv = torch.empty(B * M, 2 * C, device=x.device, dtype=torch.bfloat16)
-        K.attn_bwd(q, kv[:, :C], kv[:, C:], o, lse, d_o, B, H, N, M, d, d ** -0.5, dq, dkv[:, :C], dkv[:, C:])
+        K.attn_bwd(q, kv[:, :C], kv[:, C:], o, lse, d_o, B, H, N, M, d, d ** -0.5, dq, dkv[:, :C], dkv[:, C:], drop=d_attn)
         dw_q = _wgrad(dq, y)
         dy = _dgrad(dq, w16(w_q))
         dw_kv = _wgrad(dkv, ctx16)
         dctx = _dgrad(dkv, w16(w_kv), f32_out=True) if ctx.needs_input_grad[1] else None
         r = K.ln_bwd(dy, x, mean, rstd, ln_w, ln_b, B, N, dx_in=dout)
-        return r["dx"], dctx, r["dw"], r["db"], dw_q, dw_kv, dw_proj, db_proj, None, None, None, None, None
+        return r["dx"], dctx, r["dw"], r["db"], dw_q, dw_kv, dw_proj, db_proj, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------ MLP sub-block (inside a5)
@@ -204,17 +219,19 @@ class MlpBranch(Function):
     """x + gate_mlp * W2 gelu(W1 ((1+scale_mlp) * LN3(x) + shift_mlp) + b1) + b2   hybrid_vit_backbone.py:136-139."""
 
     @staticmethod
-    def forward(ctx, x, mod, ln_w, ln_b, w1, b1, w2, b2, B, N, off):
+    def forward(ctx, x, mod, ln_w, ln_b, w1, b1, w2, b2, B, N, off, drop=None):
         T, C = x.shape
         shift, scale, gate = _mod_views(mod, off, C)
+        d_act, d_out = _drops(drop)
         y, mean, rstd = K.ln_fwd(x, ln_w, ln_b, shift, scale, mod.stride(0), N)
         h = torch.empty(T, w1.shape[0], device=x.device, dtype=torch.bfloat16)
-        g = K.gemm(y, w16(w1), bias=b1, activation=K.ACT_GELU, out2=h)
+        g = K.gemm(y, w16(w1), bias=b1, activation=K.ACT_GELU, out2=h, drop=d_act)     # g = Dropout(GELU(h)), :77-78
         branch = torch.empty(T, C, device=x.device, dtype=torch.bfloat16)
         out = K.gemm(g, w16(w2), epilogue=K.EPI_RESIDUAL, bias=b2, resid=x, gate=gate, gate_ld=mod.stride(0),
-                     rows_per_batch=N, out2=branch)
+                     rows_per_batch=N, out2=branch, drop=d_out)
         ctx.save_for_backward(x, mod, ln_w, ln_b, w1, w2, mean, rstd, y, h, g, branch)
         ctx.dims = (B, N, off)
+        ctx.drop = drop
         return out
 
     @staticmethod
@@ -224,9 +241,10 @@ class MlpBranch(Function):
         T, C = x.shape
         dout = dout.contiguous()
         shift, scale, gate = _mod_views(mod, off, C)
-        dbranch, dgate, db2 = K.resid_bwd(dout, B, N, branch=branch, gate=gate, gate_ld=mod.stride(0))
+        d_act, d_out = _drops(ctx.drop)
+        dbranch, dgate, db2 = K.resid_bwd(dout, B, N, branch=branch, gate=gate, gate_ld=mod.stride(0), drop=d_out)
         dw2 = _wgrad(dbranch, g)
-        dh = _dgrad(dbranch, w16(w2), activation=K.ACT_GELU_GRAD, aux=h)
+        dh = _dgrad(dbranch, w16(w2), activation=K.ACT_GELU_GRAD, aux=h, drop=d_act)
         db1 = K.colsum_bf16(dh)
         dw1 = _wgrad(dh, y)
         dy = _dgrad(dh, w16(w1))
@@ -235,25 +253,37 @@ class MlpBranch(Function):
         dmod[:, off:off + C] = r["dmod"][:, 0]
         dmod[:, off + C:off + 2 * C] = r["dmod"][:, 1]
         dmod[:, off + 2 * C:off + 3 * C] = dgate
-        return r["dx"], dmod, r["dw"], r["db"], dw1, db1, dw2, db2, None, None, None
+        return r["dx"], dmod, r["dw"], r["db"], dw1, db1, dw2, db2, None, None, None, None
 
 
 # ------------------------------------------------------------------ standalone attention modules (a1, a2)
+
+def _proj_out_grad(dout, B, N, C, d_proj):
+    """Gradient entering the output projection of a standalone attention module: bf16 [B*N, C] (through proj_drop's
+    mask when it was applied) and the bias gradient."""
+    if d_proj is None:
+        dy16 = K.cast_tokens(dout)
+        return dy16, K.colsum_bf16(dy16)
+    dy16, _, db = K.resid_bwd(dout.float().contiguous().view(B * N, C), B, N, drop=d_proj)
+    return dy16, db
+
 
 class SelfAttention(Function):
     """proj(attn(qkv(x)))  -- MultiHeadSelfAttention.forward, vit_components.py:31-57 (dropout off)."""
 
     @staticmethod
-    def forward(ctx, x, w_qkv, w_proj, b_proj, H):
+    def forward(ctx, x, w_qkv, w_proj, b_proj, H, drop=None):
         B, N, C = x.shape
         d = C // H
+        d_attn, d_proj = _drops(drop)
         x16 = K.cast_tokens(x)
         qkv = K.gemm(x16, w16(w_qkv))
-        o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, d, d ** -0.5)
+        o, lse = K.attn_fwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], B, H, N, N, d, d ** -0.5, drop=d_attn)
         f32 = x.dtype == torch.float32
-        out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16)
+        out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16, drop=d_proj)
         ctx.save_for_backward(x16, w_qkv, w_proj, qkv, o, lse)
         ctx.dims = (B, N, C, H, x.dtype)
+        ctx.drop = drop
         return out.view(B, N, C)
 
     @staticmethod
@@ -261,36 +291,38 @@ class SelfAttention(Function):
         x16, w_qkv, w_proj, qkv, o, lse = ctx.saved_tensors
         B, N, C, H, dt = ctx.dims
         d = C // H
-        dy16 = K.cast_tokens(dout)
-        db_proj = K.colsum_bf16(dy16)
+        d_attn, d_proj = _drops(ctx.drop)
+        dy16, db_proj = _proj_out_grad(dout, B, N, C, d_proj)
         dw_proj = _wgrad(dy16, o)
         d_o = _dgrad(dy16, w16(w_proj))
         dqkv = torch.empty(B * N, 3 * C, device=dout.device, dtype=torch.bfloat16)
         K.attn_bwd(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], o, lse, d_o, B, H, N, N, d, d ** -0.5,
-                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:])
+                   dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:], drop=d_attn)
         dw_qkv = _wgrad(dqkv, x16)
         dx = _dgrad(dqkv, w16(w_qkv), f32_out=(dt == torch.float32)).view(B, N, C)
-        return dx, dw_qkv, dw_proj, db_proj, None
+        return dx, dw_qkv, dw_proj, db_proj, None, None
 
 
 class CrossAttention(Function):
     """proj(attn(q(x), kv(context)))  -- MultiHeadCrossAttention.forward, vit_components.py:83-119 (dropout off)."""
 
     @staticmethod
-    def forward(ctx, x, context, w_q, w_kv, w_proj, b_proj, H, store_probs=False):
+    def forward(ctx, x, context, w_q, w_kv, w_proj, b_proj, H, store_probs=False, drop=None):
         B, N, C = x.shape
         M, Cc = context.shape[1], context.shape[2]
         d = C // H
+        d_attn, d_proj = _drops(drop)
         x16 = K.cast_tokens(x)
         c16 = K.cast_tokens(context)
         q = K.gemm(x16, w16(w_q))
         kv = K.gemm(c16, w16(w_kv))
-        res = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5, want_probs=store_probs)
+        res = K.attn_fwd(q, kv[:, :C], kv[:, C:], B, H, N, M, d, d ** -0.5, want_probs=store_probs, drop=d_attn)
         o, lse = res[0], res[1]
         f32 = x.dtype == torch.float32
-        out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16)
+        out = K.gemm(o, w16(w_proj), bias=b_proj, epilogue=K.EPI_F32 if f32 else K.EPI_BF16, drop=d_proj)
         ctx.save_for_backward(x16, c16, w_q, w_kv, w_proj, q, kv, o, lse)
         ctx.dims = (B, N, M, C, Cc, H, x.dtype, context.dtype)
+        ctx.drop = drop
         if store_probs:
             ctx.mark_non_differentiable(res[2])
             return out.view(B, N, C), res[2]
@@ -301,20 +333,20 @@ class CrossAttention(Function):
         x16, c16, w_q, w_kv, w_proj, q, kv, o, lse = ctx.saved_tensors
         B, N, M, C, Cc, H, dt, cdt = ctx.dims
         d = C // H
-        dy16 = K.cast_tokens(dout)
-        db_proj = K.colsum_bf16(dy16)
+        d_attn, d_proj = _drops(ctx.drop)
+        dy16, db_proj = _proj_out_grad(dout, B, N, C, d_proj)
         dw_proj = _wgrad(dy16, o)
         d_o = _dgrad(dy16, w16(w_proj))
         dq = torch.empty(B * N, C, device=dout.device, dtype=torch.bfloat16)
         dkv = torch.empty(B * M, 2 * C, device=dout.device, dtype=torch.bfloat16)
-        K.attn_bwd(q, kv[:, :C], kv[:, C:], o, lse, d_o, B, H, N, M, d, d ** -0.5, dq, dkv[:, :C], dkv[:, C:])
+        K.attn_bwd(q, kv[:, :C], kv[:, C:], o, lse, d_o, B, H, N, M, d, d ** -0.5, dq, dkv[:, :C], dkv[:, C:], drop=d_attn)
         dw_q = _wgrad(dq, x16)
         dw_kv = _wgrad(dkv, c16)
         dx = _dgrad(dq, w16(w_q), f32_out=(dt == torch.float32)).view(B, N, C)
         dctx = None
         if ctx.needs_input_grad[1]:
             dctx = _dgrad(dkv, w16(w_kv), f32_out=(cdt == torch.float32)).view(B, M, Cc)
-        return dx, dctx, dw_q, dw_kv, dw_proj, db_proj, None, None
+        return dx, dctx, dw_q, dw_kv, dw_proj, db_proj, None, None, None
 
 
 # ------------------------------------------------------------------ voxel embedding + positional encoding (a7 head of forward)

@@ -7,32 +7,38 @@ backward passes run on the sm_100a kernels of libhvc_sm100a.so (see ops.py).  Th
 called on the hot path.
 """
 import math
-import warnings
 
 import torch
 import torch.nn as nn
 
+from . import kernels as K
 from . import ops
 
-_DROPOUT_POLICY = {"mode": "warn", "warned": False}
+_DROPOUT_POLICY = {"mode": "apply"}
 
 
 def set_dropout_policy(mode):
-    """'warn' (default): train-mode dropout p>0 is skipped with a one-time warning; 'error': raise; 'ignore'."""
-    assert mode in ("warn", "error", "ignore")
+    """'apply' (default): train-mode nn.Dropout(p) is applied inside the fused kernels (counter-based masks seeded from
+    torch's CUDA generator); 'ignore': dropout is skipped even in train mode (outputs equal the reference with dropout
+    disabled -- what the parity tests and the benchmark's dropout-off arm use)."""
+    assert mode in ("apply", "ignore")
     _DROPOUT_POLICY["mode"] = mode
 
 
-def _check_dropout(module, p):
-    if not module.training or p <= 0.0 or _DROPOUT_POLICY["mode"] == "ignore":
-        return
-    msg = ("hybrid_vit_cascade_b200: train-mode dropout (p=%g) is not applied by the fused kernels in this round; "
-           "outputs equal the reference with dropout disabled" % p)
-    if _DROPOUT_POLICY["mode"] == "error":
-        raise NotImplementedError(msg)
-    if not _DROPOUT_POLICY["warned"]:
-        warnings.warn(msg)
-        _DROPOUT_POLICY["warned"] = True
+def _p(drop_module):
+    """Effective drop probability of an nn.Dropout child (0 in eval mode or when dropout is switched off)."""
+    if _DROPOUT_POLICY["mode"] == "ignore" or not drop_module.training:
+        return 0.0
+    return float(drop_module.p)
+
+
+def _drop_cfg(device, p_first, p_second, seed=None, site=0):
+    """(seed, site_base, p_first, p_second) for one sub-block, or None when both probabilities are 0."""
+    if p_first <= 0.0 and p_second <= 0.0:
+        return None
+    if seed is None:
+        seed = K.new_seed(device)
+    return (seed, site, p_first, p_second)
 
 
 def _check_heads(embed_dim, num_heads):
@@ -61,8 +67,8 @@ class MultiHeadSelfAttention(nn.Module):
     def forward(self, x):
         """x: (B, N, C) -> (B, N, C)"""
         _check_heads(self.embed_dim, self.num_heads)
-        _check_dropout(self, self.attn_drop.p)
-        return ops.SelfAttention.apply(x, self.qkv.weight, self.proj.weight, self.proj.bias, self.num_heads)
+        drop = _drop_cfg(x.device, _p(self.attn_drop), _p(self.proj_drop))
+        return ops.SelfAttention.apply(x, self.qkv.weight, self.proj.weight, self.proj.bias, self.num_heads, drop)
 
 
 class MultiHeadCrossAttention(nn.Module):
@@ -86,15 +92,16 @@ class MultiHeadCrossAttention(nn.Module):
     def forward(self, x, context):
         """x: (B, N, C) queries, context: (B, M, context_dim) -> (B, N, C)"""
         _check_heads(self.embed_dim, self.num_heads)
-        _check_dropout(self, self.attn_drop.p)
+        drop = _drop_cfg(x.device, _p(self.attn_drop), _p(self.proj_drop))
         if self.store_attention:
-            # diagnostic slow path: the (B,h,N,M) softmax is materialised by an extra GEMM + exp pass (reference :106-108)
+            # diagnostic slow path: the (B,h,N,M) softmax (before dropout) is materialised by an extra GEMM + exp pass
+            # (reference :106-108)
             out, probs = ops.CrossAttention.apply(x, context, self.q.weight, self.kv.weight, self.proj.weight,
-                                                  self.proj.bias, self.num_heads, True)
+                                                  self.proj.bias, self.num_heads, True, drop)
             self.attention_weights = probs.detach()
             return out
         return ops.CrossAttention.apply(x, context, self.q.weight, self.kv.weight, self.proj.weight, self.proj.bias,
-                                        self.num_heads)
+                                        self.num_heads, False, drop)
 
 
 class AdaLNModulation(nn.Module):

@@ -47,6 +47,21 @@ uint64_t hvc_launch_count(void);
 int hvc_check_device(void);
 
 /* ------------------------------------------------------------------------------------------------
+ * Train-mode dropout (nn.Dropout(p) at vit_components.py:27-29,76-78 and hybrid_vit_backbone.py:78,80) is fused into
+ * the kernels: element (row, col) of a site is dropped iff hash(seed, site, row, col) < p * 2^32 and kept values are
+ * scaled by 1/(1-p).  `seed` points to two 32-bit words in DEVICE memory (drawn by the caller from its generator,
+ * e.g. torch's CUDA generator, so checkpoint recomputation replays them); `site` separates the dropout sites that
+ * share one seed.  seed == NULL or p <= 0 disables it (eval mode).  Forward and backward calls of one site must
+ * pass the same (seed, site, p).  Rows/cols: attention probabilities -> row = (b*heads + h)*nq + q, col = key;
+ * GEMM epilogues / residual backward -> row = output row (token), col = output column (feature).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hvc_dropout {
+  const uint32_t* seed;
+  uint32_t site;
+  float p;
+} hvc_dropout;
+
+/* ------------------------------------------------------------------------------------------------
  * GEMM on tcgen05 tensor cores (TMA -> 128B-swizzled smem -> tcgen05.mma -> TMEM -> epilogue).
  *   D[M,N] = alpha * sum_k A(m,k) * B(n,k)   (bf16 operands, fp32 accumulation)
  * Replaces every nn.Linear on the path and their backward GEMMs:
@@ -87,6 +102,8 @@ typedef struct hvc_gemm_args {
   const void* aux; int64_t ldaux;         /* bf16 [M,N] elementwise operand (HVC_ACT_GELU_GRAD) */
   float alpha;
   int32_t k_splits;             /* >= 1; > 1 only with HVC_EPI_F32_ATOMIC */
+  hvc_dropout drop;             /* applied to act(alpha*acc + bias) before the residual/gate (EPI_BF16, EPI_RESIDUAL, EPI_F32); with
+                                   HVC_ACT_GELU_GRAD it masks the incoming gradient: out = drop(acc) * gelu'(aux) */
 } hvc_gemm_args;
 
 int hvc_gemm(const hvc_gemm_args* args, void* stream);
@@ -99,10 +116,10 @@ int hvc_gemm(const hvc_gemm_args* args, void* stream);
  * columns are [head*head_dim, (head+1)*head_dim) starting at the given base pointer (so q, k, v may
  * all point into one [T, 3C] qkv projection output; ld* are the row pitches in elements).
  * lse: f32 [batch, heads, nq_pad] base-2 logsumexp of the scaled scores (forward output, backward
- * input), nq_pad = nq rounded up to 128.  delta: f32 [2, batch, heads, nq_pad] scratch written by
- * hvc_attn_bwd (plane 0 = rowsum(dO * O), plane 1 = -lse).  dq_accum: f32 [batch, heads, nq_pad, head_dim] zero-filled
+ * input), nq_pad = nq rounded up to 128.  delta: f32 [3, batch, heads, nq_pad] scratch written by
+ * hvc_attn_bwd (plane 0 = rowsum(dO * O), plane 1 = -lse, plane 2 = dropout row keys).  dq_accum: f32 [batch, heads, nq_pad, head_dim] zero-filled
  * scratch for the cross-CTA dQ reduction.
- * head_dim: 64.
+ * head_dim: 64 or 32.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct hvc_attn_args {
   uint32_t size;
@@ -118,8 +135,9 @@ typedef struct hvc_attn_args {
   void* dv; int64_t lddv;
   float* delta;
   float* dq_accum;
-  void* probs;                    /* optional f32 [batch, heads, nq, nk]: materialised softmax (store_attention) */
+  void* probs;                    /* optional f32 [batch, heads, nq, nk]: materialised softmax (store_attention), before dropout */
   float scale;
+  hvc_dropout drop;               /* attn_drop on the probabilities (vit_components.py:49,110) */
 } hvc_attn_args;
 
 int hvc_attn_fwd(const hvc_attn_args* args, void* stream);
@@ -167,7 +185,7 @@ typedef struct hvc_ln_bwd_args {
 int hvc_ln_bwd(const hvc_ln_bwd_args* args, void* stream);
 
 /* Backward of the gated residual  out = resid + gate[batch] * branch  (hybrid_vit_backbone.py:123,128,139):
- *   dbranch bf16 [T,C] = gate * dout;  dgate f32 [batch,C] = sum_n dout*branch (optional, needs branch);
+ *   dbranch bf16 [T,C] = gate * dout;  dgate f32 [batch,C] = sum_n dout*branch (optional, needs branch = the dropped branch);
  *   dbias f32 [C] = sum_T dbranch (optional; the bias of the projection that produced branch).
  * gate == NULL means 1 (cross-attention residual).  D1: f32 [batch, C] scratch. */
 typedef struct hvc_resid_bwd_args {
@@ -178,6 +196,7 @@ typedef struct hvc_resid_bwd_args {
   const float* gate; int64_t gate_ld;
   void* dbranch; int64_t lddbranch;
   float* dgate; float* dbias; float* D1;
+  hvc_dropout drop;               /* the dropout that was applied to branch in the forward epilogue: dbranch = gate * drop(dout) */
 } hvc_resid_bwd_args;
 int hvc_resid_bwd(const hvc_resid_bwd_args* args, void* stream);
 

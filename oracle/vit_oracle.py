@@ -162,22 +162,26 @@ def sinusoidal_time_embedding(t: Tensor, embed_dim: int) -> Tensor:
 # --------------------------------------------------------------------------
 
 def attention_core(q: Tensor, k: Tensor, v: Tensor, scale: float,
-                   attn_chunk: Optional[int] = None, return_probs: bool = False):
+                   attn_chunk: Optional[int] = None, return_probs: bool = False, pmask: Optional[Tensor] = None):
     """softmax(q k^T * scale) v with q,k,v shaped (B, h, N|M, d).
 
     ``attn_chunk=None`` materialises the full (B,h,N,M) matrix exactly as the
     reference does; otherwise queries are processed ``attn_chunk`` rows at a time
     (each row's softmax is independent, so the result is identical).
     """
+    # pmask: attn_drop (vit_components.py:49, :110) as an explicit (B,h,N,M) keep-mask already scaled by 1/(1-p);
+    # None = dropout off.  The stored attention map is taken BEFORE dropout (:106-108).
     if attn_chunk is None:
         attn = (q @ k.transpose(-2, -1)) * scale
         attn = attn.softmax(dim=-1)
-        out = attn @ v
+        out = (attn if pmask is None else attn * pmask) @ v
         return (out, attn) if return_probs else (out, None)
     outs = []
     for s in range(0, q.shape[2], attn_chunk):
         a = (q[:, :, s:s + attn_chunk] @ k.transpose(-2, -1)) * scale
         a = a.softmax(dim=-1)
+        if pmask is not None:
+            a = a * pmask[:, :, s:s + attn_chunk]
         outs.append(a @ v)
     return torch.cat(outs, dim=2), None
 
@@ -187,15 +191,21 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, scale: float,
 # --------------------------------------------------------------------------
 
 def self_attention(x: Tensor, sd: StateDict, pfx: str, num_heads: int,
-                   attn_chunk: Optional[int] = None) -> Tensor:
+                   attn_chunk: Optional[int] = None, drop=None, site: int = 0) -> Tensor:
+    """drop: None (eval / dropout off) or an oracle.dropout_mask.DropoutOracle giving the masks of attn_drop
+    (site) and proj_drop (site + 1), :49 and :55."""
     B, N, C = x.shape
     d = C // num_heads
     qkv = F.linear(x, sd[pfx + "qkv.weight"])                       # :41 (bias=False, :26)
     qkv = qkv.reshape(B, N, 3, num_heads, d).permute(2, 0, 3, 1, 4)  # :41-42
     q, k, v = qkv[0], qkv[1], qkv[2]
-    o, _ = attention_core(q, k, v, d ** -0.5, attn_chunk)            # :46-51
+    pmask = drop.attn(site, B, num_heads, N, N) if drop is not None else None
+    o, _ = attention_core(q, k, v, d ** -0.5, attn_chunk, pmask=pmask)   # :46-51
     o = o.transpose(1, 2).reshape(B, N, C)                           # :51
-    return F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])  # :54
+    o = F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])  # :54
+    if drop is not None:
+        o = o * drop.tokens(site + 1, B * N, C).view(B, N, C)        # :55
+    return o
 
 
 # --------------------------------------------------------------------------
@@ -203,7 +213,7 @@ def self_attention(x: Tensor, sd: StateDict, pfx: str, num_heads: int,
 # --------------------------------------------------------------------------
 
 def cross_attention(x: Tensor, context: Tensor, sd: StateDict, pfx: str, num_heads: int,
-                    attn_chunk: Optional[int] = None, return_probs: bool = False):
+                    attn_chunk: Optional[int] = None, return_probs: bool = False, drop=None, site: int = 0):
     B, N, C = x.shape
     M = context.shape[1]
     d = C // num_heads
@@ -211,9 +221,12 @@ def cross_attention(x: Tensor, context: Tensor, sd: StateDict, pfx: str, num_hea
     kv = F.linear(context, sd[pfx + "kv.weight"]).reshape(B, M, 2, num_heads, d)            # :98
     kv = kv.permute(2, 0, 3, 1, 4)                                                          # :99
     k, v = kv[0], kv[1]
-    o, probs = attention_core(q, k, v, d ** -0.5, attn_chunk, return_probs)                 # :103-113
+    pmask = drop.attn(site, B, num_heads, N, M) if drop is not None else None
+    o, probs = attention_core(q, k, v, d ** -0.5, attn_chunk, return_probs, pmask=pmask)    # :103-113
     o = o.transpose(1, 2).reshape(B, N, C)
     o = F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])                         # :116
+    if drop is not None:
+        o = o * drop.tokens(site + 1, B * N, C).view(B, N, C)                               # :117
     return (o, probs.detach()) if return_probs else o                                       # :107-108
 
 
@@ -232,8 +245,11 @@ def adaln(cond: Tensor, sd: StateDict, pfx: str):
 
 def block(x: Tensor, context: Tensor, cond: Tensor, sd: StateDict, pfx: str, num_heads: int,
           use_prev_stage: bool = False, prev_stage_embed: Optional[Tensor] = None,
-          attn_chunk: Optional[int] = None, return_attention: bool = False):
+          attn_chunk: Optional[int] = None, return_attention: bool = False, drop=None, site_base: int = 0):
+    """drop/site_base: train-mode dropout as explicit masks (oracle.dropout_mask.DropoutOracle); sites site_base + 0..5 =
+    self-attn probabilities, self-attn proj, cross-attn probabilities, cross-attn proj, MLP activation, MLP output."""
     C = x.shape[-1]
+    Bx, Nx = x.shape[0], x.shape[1]
     if use_prev_stage:                                                # :106-114
         if prev_stage_embed is None:
             prev_stage_embed = torch.zeros(x.shape[0], 256, device=x.device, dtype=x.dtype)
@@ -244,18 +260,23 @@ def block(x: Tensor, context: Tensor, cond: Tensor, sd: StateDict, pfx: str, num
         return F.layer_norm(t, (C,), sd[pfx + name + ".weight"], sd[pfx + name + ".bias"], 1e-5)
 
     h = (1 + scale_sa) * ln(x, "norm1") + shift_sa                    # :120-121
-    x = x + gate_sa * self_attention(h, sd, pfx + "self_attn.", num_heads, attn_chunk)      # :122-123
+    x = x + gate_sa * self_attention(h, sd, pfx + "self_attn.", num_heads, attn_chunk, drop, site_base)   # :122-123
     attn_map = None
     if return_attention:
         ca, attn_map = cross_attention(ln(x, "norm2"), context, sd, pfx + "cross_attn.", num_heads,
-                                       attn_chunk, True)
+                                       attn_chunk, True, drop, site_base + 2)
     else:
-        ca = cross_attention(ln(x, "norm2"), context, sd, pfx + "cross_attn.", num_heads, attn_chunk)
+        ca = cross_attention(ln(x, "norm2"), context, sd, pfx + "cross_attn.", num_heads, attn_chunk, False, drop,
+                             site_base + 2)
     x = x + ca                                                        # :126-128
     h = (1 + scale_mlp) * ln(x, "norm3") + shift_mlp                  # :136-137
     h = F.linear(h, sd[pfx + "mlp.0.weight"], sd[pfx + "mlp.0.bias"]) # :75-81
     h = F.gelu(h)                                                     # nn.GELU() = exact erf
+    if drop is not None:
+        h = h * drop.tokens(site_base + 4, Bx * Nx, h.shape[-1]).view(h.shape)      # mlp.2
     h = F.linear(h, sd[pfx + "mlp.3.weight"], sd[pfx + "mlp.3.bias"])
+    if drop is not None:
+        h = h * drop.tokens(site_base + 5, Bx * Nx, C).view(h.shape)                # mlp.4
     x = x + gate_mlp * h                                              # :139
     return (x, attn_map) if return_attention else x
 
@@ -276,7 +297,7 @@ def voxel_embed(x: Tensor, sd: StateDict, pfx: str, cfg: BackboneConfig) -> Tens
 
 def backbone(x: Tensor, context: Tensor, cond: Tensor, sd: StateDict, cfg: BackboneConfig,
              pfx: str = "", prev_stage_embed: Optional[Tensor] = None,
-             attn_chunk: Optional[int] = None) -> Tensor:
+             attn_chunk: Optional[int] = None, drop=None) -> Tensor:
     B = x.shape[0]
     D, H, W = cfg.volume_size
     Dd, Hd, Wd = cfg.downsampled_size
@@ -285,7 +306,7 @@ def backbone(x: Tensor, context: Tensor, cond: Tensor, sd: StateDict, cfg: Backb
     x = x + sd[pfx + "pos_embed"]                                     # :258 (raises on the 128^3 defect)
     for i in range(cfg.depth):                                        # :261-262
         x = block(x, context, cond, sd, f"{pfx}blocks.{i}.", cfg.num_heads,
-                  cfg.use_prev_stage, prev_stage_embed, attn_chunk)
+                  cfg.use_prev_stage, prev_stage_embed, attn_chunk, drop=drop, site_base=8 * i)
     C = x.shape[-1]
     x = F.layer_norm(x, (C,), sd[pfx + "norm.weight"], sd[pfx + "norm.bias"], 1e-5)   # :265
     x = F.linear(x, sd[pfx + "output_proj.weight"], sd[pfx + "output_proj.bias"])    # :266
