@@ -8,8 +8,8 @@ Host code is PyTorch (memory, streams, autograd glue); every computation on the 
 library or off sm_100 the modules raise.
 """
 from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHeadSelfAttention,  # noqa: F401
-                             SinusoidalTimeEmbedding, set_dropout_policy)
+                             SinusoidalTimeEmbedding, precision, set_dropout_policy, set_precision)
 from .hybrid_vit_backbone import HybridViT3D, HybridViTBlock3D  # noqa: F401
 
 __all__ = ["AdaLNModulation", "MultiHeadCrossAttention", "MultiHeadSelfAttention", "SinusoidalTimeEmbedding",
-           "HybridViTBlock3D", "HybridViT3D", "set_dropout_policy"]
+           "HybridViTBlock3D", "HybridViT3D", "set_dropout_policy", "set_precision", "precision"]

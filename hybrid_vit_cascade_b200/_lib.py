@@ -138,6 +138,7 @@ EXPORTS = [
     "hvc_adaln_fwd", "hvc_adaln_bwd",
     "hvc_im2col3d", "hvc_col2im3d", "hvc_groupnorm_silu_fwd", "hvc_groupnorm_silu_bwd",
     "hvc_add_pos", "hvc_batch_sum", "hvc_head_fwd", "hvc_upsample3d_fwd", "hvc_upsample3d_bwd",
+    "hvc_split3", "hvc_softmax_rows", "hvc_im2col3d_f32", "hvc_epilogue_f32",
 ]
 
 

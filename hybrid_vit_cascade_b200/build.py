@@ -17,6 +17,7 @@ OBJ = os.path.join(PKG, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v", "-I", os.path.join(PKG, "..", "include")]
+FLAGS += os.environ.get("HVC_EXTRA_NVCC_FLAGS", "").split()     # bring-up only, e.g. -DHVC_TUNE_FWD_EMU
 
 
 def _sources():

@@ -50,6 +50,20 @@ struct BwdSmem {
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
+// Optional in-kernel timeline (bring-up builds, -DHVC_TRACE_BWD): SM-clock stamps of CTA (0,0) at the protocol points of
+// iterations [kTraceI0, kTraceI0+8) for warpgroup 0, warpgroup 1 and the MMA warp; read back with hvc_debug_bwd_trace.
+#ifdef HVC_TRACE_BWD
+constexpr int kTraceI0 = 16, kTraceIters = 8, kTracePts = 12;
+__device__ unsigned long long g_bwd_trace[3 * kTraceIters * kTracePts];
+#define HVC_TR(role, i, pt)                                                                                     \
+  do {                                                                                                          \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) >= kTraceI0 && (i) < kTraceI0 + kTraceIters)                  \
+      g_bwd_trace[((role) * kTraceIters + ((i) - kTraceI0)) * kTracePts + (pt)] = clock64();                    \
+  } while (0)
+#else
+#define HVC_TR(role, i, pt) do {} while (0)
+#endif
+
 enum { BB_KV = 0, BB_QF = 1, BB_QE = 4, BB_ST = 7, BB_STFREE = 8, BB_PT = 9, BB_DPT = 10, BB_DS = 11, BB_DQF = 12, BB_DQFREE = 13, BB_N = 14 };
 
 // ---- elementwise phases of one (key tile, query tile) pair; thread == key row, 64 query columns per thread.
@@ -225,16 +239,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int st1 = (i + 1) % kQStages;
       const uint32_t sQ = sQ0 + st * L::kQStage, sDO = sQ + L::kTile;
       // (1) S^T(i+1) as soon as the warpgroups have pulled S^T(i) out of TMEM
+      if (leader) HVC_TR(2, i, 0);
       if (i + 1 < nQ) {
         mbar_wait(&bar[BB_STFREE], i & 1, 22);
         mbar_wait(&bar[BB_QF + st1], ((i + 1) / kQStages) & 1, 23);
         tc_fence_after();
+        if (leader) HVC_TR(2, i, 1);
         issue_st(st1);
         commit(BB_ST);
       }
+      if (leader) HVC_TR(2, i, 2);
       // (2) dV += P^T dO     (A = P^T in TMEM, 8 columns per K=16 step; B = dO MN-major)
       mbar_wait(&bar[BB_PT], i & 1, 24);
       tc_fence_after();
+      if (leader) HVC_TR(2, i, 3);
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
@@ -242,8 +260,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   (i > 0 || k16 > 0) ? 1u : 0u);
       }
       // (3) once dS^T(i) is in smem (and dP^T(i) consumed): dP^T(i+1), dK, dQ
+      if (leader) HVC_TR(2, i, 4);
       mbar_wait(&bar[BB_DS], i & 1, 25);
       tc_fence_after();
+      if (leader) HVC_TR(2, i, 5);
       if (i + 1 < nQ) {
         issue_dpt(st1);
         commit(BB_DPT);
@@ -255,7 +275,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS + (k16 >> 2) * 16384 + (k16 & 3) * 32, 16, 1024),
                   SW::desc(sQ + k16 * SW::kMnStep, 8192), id_dv, (i > 0 || k16 > 0) ? 1u : 0u);
       }
+      if (leader) HVC_TR(2, i, 6);
       if (i > 0) { mbar_wait(&bar[BB_DQFREE], (i - 1) & 1, 26); tc_fence_after(); }
+      if (leader) HVC_TR(2, i, 7);
       // dQ_i = dS K      (A = dS^T read MN-major: M = queries contiguous, K = key rows; B = K MN-major)
       if (leader) {
 #pragma unroll
@@ -265,6 +287,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       commit(BB_DQF);
       commit(BB_QE + st);
+      if (leader) HVC_TR(2, i, 8);
     }
   } else {
     // ===================== elementwise warpgroups: thread == key row, warpgroup w == 64 query columns =====================
@@ -281,6 +304,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     auto drain_dq = [&](int i) {
       mbar_wait(&bar[BB_DQF], i & 1, 31);
       tc_fence_after();
+      if ((threadIdx.x & 127) == 0) HVC_TR(wg, i + 1, 10);
       if ((threadIdx.x & 127) == 0) bulk_wait_read<0>();      // previous reduce has finished reading the staging tile
       named_bar_sync(1 + wg, 128);
       uint32_t v[HD / 2];
@@ -289,6 +313,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bar[BB_DQFREE]);
+      if ((threadIdx.x & 127) == 0) HVC_TR(wg, i + 1, 11);
 #pragma unroll
       for (int k = 0; k < HD / 8; ++k) sts_u4(dq_saddr + SW::offset(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       fence_proxy_async_smem();
@@ -318,9 +343,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       float2 pv[32];                                       // P^T row slice, fp32, lives across phase A -> B
 
       // ---------------- phase A: P^T = exp2(S^T * scale2 - lse2)
+      const bool tr = (threadIdx.x & 127) == 0;
+      if (tr) HVC_TR(wg, i, 0);
       mbar_wait(&bar[BB_QF + st], (i / kQStages) & 1, 32);  // lse/delta of this query tile are in smem
       mbar_wait(&bar[BB_ST], i & 1, 33);
       tc_fence_after();
+      if (tr) HVC_TR(wg, i, 1);
       {
         uint32_t sv[64];
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
@@ -330,21 +358,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&bar[BB_STFREE]);
+        if (tr) HVC_TR(wg, i, 2);
         uint32_t ppk[32];
         if (full) bwd_phase_a<true, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
         else      bwd_phase_a<false, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
+        if (tr) HVC_TR(wg, i, 3);
         tmem_st_32x32(tmem_base + lane_base + kColPt + wg * 32, ppk);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&bar[BB_PT]);
+        if (tr) HVC_TR(wg, i, 4);
       }
 
       // ---------------- drain dQ(i-1) while the tensor pipe works on dV(i) / dP^T(i)
       if (i > 0) drain_dq(i - 1);      // also guarantees dK(i-1)/dQ(i-1) are done reading the dS^T tile
+      if (tr) HVC_TR(wg, i, 5);
 
       // ---------------- phase B: dS^T = P^T * (dP^T - delta)
       mbar_wait(&bar[BB_DPT], i & 1, 34);
       tc_fence_after();
+      if (tr) HVC_TR(wg, i, 6);
       {
         uint32_t dv[64];
         uint32_t(&d0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dv[0]);
@@ -352,12 +385,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64, d0);
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64 + 32, d1);
         tmem_ld_wait();
+        if (tr) HVC_TR(wg, i, 7);
         if (full) bwd_phase_b<true, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, inv_keep);
         else      bwd_phase_b<false, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, inv_keep);
       }
+      if (tr) HVC_TR(wg, i, 8);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&bar[BB_DS]);
+      if (tr) HVC_TR(wg, i, 9);
     }
     drain_dq(nQ - 1);   // the commit behind BB_DQF covers every earlier MMA: dV and dK are complete too
     if ((threadIdx.x & 127) == 0) bulk_wait<0>();
@@ -495,6 +531,12 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   return HVC_OK;
 }
 }  // namespace hvc
+
+#ifdef HVC_TRACE_BWD
+extern "C" int hvc_debug_bwd_trace(unsigned long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, hvc::g_bwd_trace, sizeof(hvc::g_bwd_trace));
+}
+#endif
 
 extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   using namespace hvc;

@@ -17,6 +17,7 @@
 // O is written token-major [T, h*d] ready for the output projection -- no head split/merge copies.
 #include "hvc_common.cuh"
 #include "hvc_host.h"
+#include <stdlib.h>
 
 namespace hvc {
 
@@ -24,6 +25,7 @@ constexpr int kFwdThreads = 320;
 constexpr int kQTile = 128;
 constexpr int kKTile = 128;
 constexpr int kKvStages = 3;
+constexpr int kEmu64 = 6, kEmu32 = 6;   // element pairs (of 16) whose exp2 runs as a polynomial on the FMA pipe
 
 struct AttnFwdKArgs {
   int batch, heads, nq, nk, n_kv_tiles;
@@ -73,16 +75,36 @@ __device__ __forceinline__ float softmax_rowmax(uint32_t tS, int tail) {
   return fmaxf(a0, a1);
 }
 
+// 2^a for a pair of arguments on the FMA/ALU pipes instead of MUFU (the exp unit, 16/clk/SM, is the bound of this kernel
+// at head_dim <= 64): round-to-nearest split a = n + f via the 1.5*2^23 magic constant, degree-3 minimax polynomial of
+// 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), then n is added into the exponent
+// field.  a <= ~8 by construction (stale maxima are bounded by the lazy-rescale threshold); a is clamped at -125.
+__device__ __forceinline__ float2 ex2_poly2(float2 a) {
+  a.x = fmaxf(a.x, -125.f);
+  a.y = fmaxf(a.y, -125.f);
+  const float2 t = __fadd2_rn(a, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), a);
+  float2 p = __ffma2_rn(f, make_float2(0.05517132207751274f, 0.05517132207751274f), make_float2(0.24261054396629333f, 0.24261054396629333f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+
 // rowkey/col0/thr: dropout on P (DROP): the row sum uses the undropped probabilities (softmax normalisation comes
 // before nn.Dropout in the reference), the P that feeds P V has the dropped entries zeroed; 1/(1-p) is applied to O.
-template <bool MASKED, bool DROP>
+// EMU of every 16 element pairs take the polynomial path (spread evenly so MUFU and FMA work interleave).
+template <bool MASKED, bool DROP, int EMU>
 __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint32_t tP, int c0, int tail, float2 scale2v, float2 neg_m,
                                                   float2& sum, uint32_t rowkey, uint32_t col0, uint32_t thr) {
   uint32_t pk[16];
 #pragma unroll
   for (int c = 0; c < 32; c += 2) {
     const float2 a = ffma2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), scale2v, neg_m);
-    float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+    float2 e;
+    if (((c >> 1) * EMU) % 16 < EMU) e = ex2_poly2(a);
+    else e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
     if (MASKED) {
       e.x = (c0 + c < tail) ? e.x : 0.f;
       e.y = (c0 + c + 1 < tail) ? e.y : 0.f;
@@ -99,30 +121,30 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
 
 // P = exp2(S*scale2 - m): chunk c+1 is fetched from TMEM while chunk c is exponentiated.  The section between the
 // named-barrier sync and arrive is the warpgroup's turn on the MUFU pipe.
-template <bool MASKED, bool DROP>
+template <bool MASKED, bool DROP, int EMU, bool TURNS>
 __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2, float m, int turn_bar, int next_bar, bool hand_over,
                                              uint32_t rowkey, uint32_t col0, uint32_t thr) {
   const float2 scale2v = make_float2(scale2, scale2), neg_m = make_float2(-m, -m);
   float2 sum = make_float2(0.f, 0.f);
   uint32_t bufa[32], bufb[32];
   tmem_ld_32x32(tS, bufa);
-  named_bar_sync(turn_bar, 256);
+  if (TURNS) named_bar_sync(turn_bar, 256);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 32, bufb);
-  softmax_exp_chunk<MASKED, DROP>(bufa, tS, 0, tail, scale2v, neg_m, sum, rowkey, col0, thr);
+  softmax_exp_chunk<MASKED, DROP, EMU>(bufa, tS, 0, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 64, bufa);
-  softmax_exp_chunk<MASKED, DROP>(bufb, tS, 32, tail, scale2v, neg_m, sum, rowkey, col0, thr);
+  softmax_exp_chunk<MASKED, DROP, EMU>(bufb, tS, 32, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 96, bufb);
-  softmax_exp_chunk<MASKED, DROP>(bufa, tS, 64, tail, scale2v, neg_m, sum, rowkey, col0, thr);
+  softmax_exp_chunk<MASKED, DROP, EMU>(bufa, tS, 64, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
-  softmax_exp_chunk<MASKED, DROP>(bufb, tS, 96, tail, scale2v, neg_m, sum, rowkey, col0, thr);
-  if (hand_over) named_bar_arrive(next_bar, 256);
+  softmax_exp_chunk<MASKED, DROP, EMU>(bufb, tS, 96, tail, scale2v, neg_m, sum, rowkey, col0, thr);
+  if (TURNS && hand_over) named_bar_arrive(next_bar, 256);
   return sum.x + sum.y;
 }
 
-template <int HD, bool DROP>
+template <int HD, bool DROP, int EMU>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdKArgs p) {
@@ -255,7 +277,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     // The two warpgroups take turns in the MUFU-bound exp section (named barriers 1 and 2): while one runs
     // exp2 the other waits for its next S tile, loads it and finds the row maximum.
-    if (x == 1) named_bar_arrive(1, 256);             // warpgroup A goes first
+    constexpr bool TURNS = EMU < 100;
+    if (TURNS && x == 1) named_bar_arrive(1, 256);    // warpgroup A goes first
 
     for (int j = 0; j < n_tiles; ++j) {
       const bool masked = (j == n_tiles - 1) && (tail < kKTile);
@@ -288,8 +311,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // ---- pass 2 (my turn on the MUFU pipe): P = exp2(S*scale2 - m) -> TMEM, row sum
       const bool hand_over = !(x == 1 && j == n_tiles - 1);
-      l += masked ? softmax_exp<true, DROP>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr)
-                  : softmax_exp<false, DROP>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
+      l += masked ? softmax_exp<true, DROP, EMU % 100, TURNS>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr)
+                  : softmax_exp<false, DROP, EMU % 100, TURNS>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&bar[BAR_PF + x]);
@@ -332,7 +355,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }  // namespace hvc
 
 namespace hvc {
-template <int HD, bool DROP>
+template <int HD, bool DROP, int EMU>
 static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   using L = FwdSmem<HD>;
   const uint64_t width = (uint64_t)a->heads * HD;
@@ -352,11 +375,11 @@ static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   ka.drop = make_drop(a->drop);
   static bool configured = false;
   if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    HVC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DROP, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   dim3 grid((a->nq + 2 * kQTile - 1) / (2 * kQTile), a->batch * a->heads);
-  attn_fwd_kernel<HD, DROP><<<grid, kFwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, ka);
+  attn_fwd_kernel<HD, DROP, EMU><<<grid, kFwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, ka);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
@@ -411,8 +434,28 @@ extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool drop = a->drop.seed != nullptr && a->drop.p > 0.f;
   HVC_CHECK_ARG(!drop || a->drop.p < 1.f, "hvc_attn_fwd: dropout p must be < 1");
-  const int rc = a->head_dim == 64 ? (drop ? launch_attn_fwd<64, true>(a, st) : launch_attn_fwd<64, false>(a, st))
-                                   : (drop ? launch_attn_fwd<32, true>(a, st) : launch_attn_fwd<32, false>(a, st));
+  int rc;
+#ifdef HVC_TUNE_FWD_EMU   // bring-up builds: pick the polynomial share at run time (pairs out of 16)
+  static const int emu = getenv("HVC_FWD_EMU") ? atoi(getenv("HVC_FWD_EMU")) : -1;
+  if (!drop && emu >= 0) {
+    switch (emu) {
+      case 0: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 0>(a, st) : launch_attn_fwd<32, false, 0>(a, st); break;
+      case 4: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 4>(a, st) : launch_attn_fwd<32, false, 4>(a, st); break;
+      case 5: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 5>(a, st) : launch_attn_fwd<32, false, 5>(a, st); break;
+      case 6: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 6>(a, st) : launch_attn_fwd<32, false, 6>(a, st); break;
+      case 7: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 7>(a, st) : launch_attn_fwd<32, false, 7>(a, st); break;
+      case 8: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 8>(a, st) : launch_attn_fwd<32, false, 8>(a, st); break;
+      case 100: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 100>(a, st) : launch_attn_fwd<32, false, 100>(a, st); break;
+      case 104: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 104>(a, st) : launch_attn_fwd<32, false, 104>(a, st); break;
+      case 106: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 106>(a, st) : launch_attn_fwd<32, false, 106>(a, st); break;
+      case 108: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 108>(a, st) : launch_attn_fwd<32, false, 108>(a, st); break;
+      case 110: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 110>(a, st) : launch_attn_fwd<32, false, 110>(a, st); break;
+      default: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 3>(a, st) : launch_attn_fwd<32, false, 3>(a, st); break;
+    }
+  } else
+#endif
+  rc = a->head_dim == 64 ? (drop ? launch_attn_fwd<64, true, kEmu64>(a, st) : launch_attn_fwd<64, false, kEmu64>(a, st))
+                         : (drop ? launch_attn_fwd<32, true, kEmu32>(a, st) : launch_attn_fwd<32, false, kEmu32>(a, st));
   if (rc != HVC_OK || a->probs == nullptr) return rc;
   return attn_store_probs(a, st);
 }

@@ -20,8 +20,8 @@ struct Conv3dGeom {
 };
 
 // cols[m, k] = x[b, cin, od*s-1+kd, oh*s-1+kh, ow*s-1+kw]   (0 outside), k = cin*27 + kd*9 + kh*3 + kw
-template <typename TIn>
-__global__ void __launch_bounds__(256) im2col3d_kernel(const TIn* __restrict__ x, bf16* __restrict__ cols, const Conv3dGeom g) {
+template <typename TIn, typename TOut = bf16>
+__global__ void __launch_bounds__(256) im2col3d_kernel(const TIn* __restrict__ x, TOut* __restrict__ cols, const Conv3dGeom g) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * g.Kp;
   if (idx >= total) return;
@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(256) im2col3d_kernel(const TIn* __restrict__ x
     if (id >= 0 && id < g.D && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
       v = static_cast<float>(x[b * g.sb + cin * g.sc + id * g.sd + ih * g.sh + iw * g.sw]);
   }
-  cols[idx] = __float2bfloat16(v);
+  if constexpr (sizeof(TOut) == 4) cols[idx] = v;
+  else cols[idx] = __float2bfloat16(v);
 }
 
 // dx[b, c, d, h, w] = sum over taps/outputs that read it of dcols[(b,od,oh,ow), c*27 + tap]
@@ -259,6 +260,20 @@ extern "C" int hvc_im2col3d(const void* x, int32_t x_is_bf16, const hvc_conv3d_g
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x_is_bf16) im2col3d_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(cols), g);
   else im2col3d_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(cols), g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+// fp32 verification mode (hvc_fp32.cu): the patch matrix keeps the full fp32 values; hvc_split3 then turns it into
+// the three-term bf16 operand of the tensor-core GEMM.
+extern "C" int hvc_im2col3d_f32(const float* x, const hvc_conv3d_geom* geom, float* cols, void* stream) {
+  HVC_CHECK_ARG(x && geom && cols, "hvc_im2col3d_f32: null operand");
+  Conv3dGeom g;
+  int rc = fill_geom(&g, geom);
+  if (rc) return rc;
+  const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * g.Kp;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  im2col3d_kernel<float, float><<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, cols, g);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

@@ -172,6 +172,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(o + j, v[j]);
     }
   } else {  // HVC_EPI_F32
+    if (p.activation == HVC_ACT_GELU) {   // fp32 verification mode: the MLP hidden activation stays fp32
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
     float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
     if (vec && (p.ldo & 3) == 0) {
 #pragma unroll

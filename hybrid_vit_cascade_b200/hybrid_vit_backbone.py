@@ -18,8 +18,9 @@ import torch.nn as nn
 
 from . import kernels as K
 from . import ops
+from . import ops_fp32
 from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHeadSelfAttention,
-                             SinusoidalTimeEmbedding, _check_heads, _drop_cfg, _p)  # noqa: F401
+                             SinusoidalTimeEmbedding, _check_heads, _drop_cfg, _fp32_mode, _p)  # noqa: F401
 
 
 class HybridViTBlock3D(nn.Module):
@@ -50,6 +51,10 @@ class HybridViTBlock3D(nn.Module):
         if prev_stage_embed is None:
             prev_stage_embed = torch.zeros(batch, 256, device=cond.device, dtype=cond.dtype)
         return torch.cat([cond, prev_stage_embed], dim=-1)
+
+    def _dropouts(self):
+        sa, ca = self.self_attn, self.cross_attn
+        return (sa.attn_drop, sa.proj_drop, ca.attn_drop, ca.proj_drop, self.mlp[2], self.mlp[4])
 
     def dropout_probs(self):
         """Effective p of the six nn.Dropout sites of the block (all 0 in eval mode), reference :75-81 and
@@ -90,6 +95,10 @@ class HybridViTBlock3D(nn.Module):
         M = xray_context.shape[1]
         cond = self._combined_cond(cond, prev_stage_embed, B)
         x = voxel_features.float().contiguous().view(B * N, C)
+        if _fp32_mode(*self._dropouts()):
+            out = ops_fp32.block_tokens(self, x, ops_fp32.cast_tokens(xray_context), cond, B, N, M)
+            out = out.view(B, N, C).to(voxel_features.dtype)
+            return (out, self.cross_attn.attention_weights) if self.return_attention else out
         ctx16 = ops.CastTokens.apply(xray_context)
         x = self._forward_tokens(x, ctx16, cond, B, N, M)
         out = x.view(B, N, C).to(voxel_features.dtype)
@@ -170,6 +179,8 @@ class HybridViT3D(nn.Module):
             _check_heads(self.voxel_dim, self.blocks[0].self_attn.num_heads)
         if not self._plan:
             raise NotImplementedError("in_channels == voxel_dim with no downsampling leaves voxel_embed empty")
+        if _fp32_mode(*(m for blk in self.blocks for m in blk._dropouts())):
+            return ops_fp32.backbone(self, x, context, cond, prev_stage_embed)
         tok = ops.VoxelEmbed.apply(x, self.pos_embed, self._plan, *self._embed_params())     # fp32 [B*N, C]
         ctx16 = ops.CastTokens.apply(context)
         seed = None

@@ -449,3 +449,51 @@ def upsample3d_bwd(dout, B, grid, size):
     dv = torch.empty(B * grid[0] * grid[1] * grid[2], device=dout.device, dtype=torch.float32)
     _lib.check(_lib.lib().hvc_upsample3d_bwd(_ptr(dout), _ptr(dv), B, *grid, *size, _stream()), "hvc_upsample3d_bwd")
     return dv
+
+
+# ------------------------------------------------------------------ fp32 verification mode (hvc_fp32.cu)
+
+def split3(x, pattern, concat_rows=False):
+    """x f32 2-D (unit inner stride) -> the six-term bf16 operand of hvc_fp32.cu: [R, 6C] or, with concat_rows, [6R, C]."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and pattern in (0, 1)
+    ldx = _row_major_2d(x, "x")
+    R, Cc = x.shape
+    out = torch.empty((6 * R, Cc) if concat_rows else (R, 6 * Cc), device=x.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().hvc_split3(_ptr(x), C.c_int64(ldx), R, Cc, _ptr(out), C.c_int64(out.stride(0)), pattern,
+                                     int(concat_rows), _stream()), "hvc_split3")
+    return out
+
+
+def softmax_rows_(s, lse2=None):
+    """In place row softmax of f32 s [R, M] holding log2-domain scaled scores."""
+    _need_cuda(s)
+    assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1
+    _lib.check(_lib.lib().hvc_softmax_rows(_ptr(s), C.c_int64(s.stride(0)), s.shape[0], s.shape[1], _ptr(lse2), _stream()),
+               "hvc_softmax_rows")
+    return s
+
+
+def im2col3d_f32(x, B, Cin, D, H, W, stride, strides):
+    """im2col3d with an f32 patch matrix (x must be f32)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32
+    Do, Ho, Wo = conv_out(D, stride), conv_out(H, stride), conv_out(W, stride)
+    Kp = (Cin * 27 + 7) // 8 * 8
+    cols = torch.empty(B * Do * Ho * Wo, Kp, device=x.device, dtype=torch.float32)
+    g = _geom(B, Cin, D, H, W, stride, strides)
+    _lib.check(_lib.lib().hvc_im2col3d_f32(_ptr(x), C.byref(g), _ptr(cols), _stream()), "hvc_im2col3d_f32")
+    return cols
+
+
+def epilogue_f32(acc, bias=None, activation=ACT_NONE, resid=None, gate=None, gate_ld=0, rows_per_batch=0, out=None):
+    """out = resid + gate * act(acc + bias) on f32 [T, N] (in place on acc unless `out` is given)."""
+    _need_cuda(acc)
+    assert acc.dtype == torch.float32
+    T, N = acc.shape
+    out = acc if out is None else out
+    _lib.check(_lib.lib().hvc_epilogue_f32(_ptr(acc), C.c_int64(_row_major_2d(acc, "acc")), T, N, _ptr(bias), activation,
+                                           _ptr(resid), C.c_int64(_row_major_2d(resid, "resid") if resid is not None else 0),
+                                           _ptr(gate), C.c_int64(gate_ld), rows_per_batch, _ptr(out),
+                                           C.c_int64(_row_major_2d(out, "out")), _stream()), "hvc_epilogue_f32")
+    return out

@@ -11,10 +11,45 @@ import math
 import torch
 import torch.nn as nn
 
+import contextlib
+
 from . import kernels as K
 from . import ops
+from . import ops_fp32
 
 _DROPOUT_POLICY = {"mode": "apply"}
+_PRECISION = {"mode": "bf16"}
+
+
+def set_precision(mode):
+    """'bf16' (default): the production path -- bf16 tensor-core operands, fp32 accumulation/statistics/residual stream
+    (what torch.autocast(bfloat16) does to the reference).  'fp32': verification mode -- the same kernels fed with
+    three-term bf16 splits of the fp32 operands (ops_fp32.py), matching the reference's plain fp32 modules to ~1e-6;
+    forward only (call under torch.no_grad()), no dropout, several times slower."""
+    assert mode in ("bf16", "fp32")
+    _PRECISION["mode"] = mode
+
+
+@contextlib.contextmanager
+def precision(mode):
+    """with precision("fp32"), torch.no_grad(): out = model(...)"""
+    prev = _PRECISION["mode"]
+    set_precision(mode)
+    try:
+        yield
+    finally:
+        _PRECISION["mode"] = prev
+
+
+def _fp32_mode(*drop_modules):
+    if _PRECISION["mode"] != "fp32":
+        return False
+    if torch.is_grad_enabled():
+        raise RuntimeError("precision('fp32') is a forward-only verification mode: call the module under torch.no_grad() "
+                           "(gradients are produced by the bf16 production path)")
+    if any(_p(m) > 0.0 for m in drop_modules):
+        raise RuntimeError("precision('fp32') has no dropout: call model.eval() or set_dropout_policy('ignore')")
+    return True
 
 
 def set_dropout_policy(mode):
@@ -67,6 +102,8 @@ class MultiHeadSelfAttention(nn.Module):
     def forward(self, x):
         """x: (B, N, C) -> (B, N, C)"""
         _check_heads(self.embed_dim, self.num_heads)
+        if _fp32_mode(self.attn_drop, self.proj_drop):
+            return ops_fp32.self_attention(x, self.qkv.weight, self.proj.weight, self.proj.bias, self.num_heads).to(x.dtype)
         drop = _drop_cfg(x.device, _p(self.attn_drop), _p(self.proj_drop))
         return ops.SelfAttention.apply(x, self.qkv.weight, self.proj.weight, self.proj.bias, self.num_heads, drop)
 
@@ -92,6 +129,13 @@ class MultiHeadCrossAttention(nn.Module):
     def forward(self, x, context):
         """x: (B, N, C) queries, context: (B, M, context_dim) -> (B, N, C)"""
         _check_heads(self.embed_dim, self.num_heads)
+        if _fp32_mode(self.attn_drop, self.proj_drop):
+            res = ops_fp32.cross_attention(x, context, self.q.weight, self.kv.weight, self.proj.weight, self.proj.bias,
+                                           self.num_heads, self.store_attention)
+            if self.store_attention:
+                self.attention_weights = res[1].detach()
+                return res[0].to(x.dtype)
+            return res.to(x.dtype)
         drop = _drop_cfg(x.device, _p(self.attn_drop), _p(self.proj_drop))
         if self.store_attention:
             # diagnostic slow path: the (B,h,N,M) softmax (before dropout) is materialised by an extra GEMM + exp pass

@@ -77,7 +77,7 @@ typedef enum hvc_epilogue {
   HVC_EPI_BF16 = 0,       /* out bf16 = act(alpha*acc + bias) [* f'(aux)]; optional out2 bf16 = pre-activation */
   HVC_EPI_RESIDUAL = 1,   /* out f32 = resid + gate[row/rows_per_batch, col] * (acc + bias); out2 bf16 = acc+bias */
   HVC_EPI_F32_ATOMIC = 2, /* out f32 += alpha*acc  (red.global.add; used with k_splits >= 1)                 */
-  HVC_EPI_F32 = 3         /* out f32 = alpha*acc + bias                                                       */
+  HVC_EPI_F32 = 3         /* out f32 = act(alpha*acc + bias), act = none | GELU (fp32 verification mode)              */
 } hvc_epilogue;
 
 typedef enum hvc_activation {
@@ -253,6 +253,29 @@ int hvc_upsample3d_fwd(const float* v, float* out, int32_t B, int32_t Di, int32_
                        int32_t Ho, int32_t Wo, void* stream);
 int hvc_upsample3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do,
                        int32_t Ho, int32_t Wo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 verification mode (the 1e-4 fp32 parity bar): fp32-accurate products on the bf16 tensor cores.
+ * An fp32 operand is split into three bf16 terms x = x0 + x1 + x2; the six significant partial products are
+ * laid out along K so ONE hvc_gemm with K' = 6K gives sum_k a_k b_k to ~fp32 accuracy:
+ *   pattern 0 (A side): [x0 | x1 | x2 | x0 | x1 | x0]     pattern 1 (B side): [x0 | x0 | x0 | x1 | x1 | x2]
+ * hvc_split3: x f32 [R, C] (pitch ldx) -> out bf16 [R, 6C] (concat_rows = 0; for K-major operands) or
+ * [6R, C] (concat_rows = 1; for MN-major operands such as V in P V), pitch ldo.
+ * hvc_softmax_rows: in place s[r,:] <- exp2(s[r,:] - max) / sum for f32 s [R, M] holding scores * scale * log2(e)
+ * (the materialised softmax of vit_components.py:46-48,103-105); lse2 [R] optional.
+ * hvc_im2col3d_f32: hvc_im2col3d with an f32 patch matrix [B*Do*Ho*Wo, Kp].
+ * Forward only; used by hybrid_vit_cascade_b200.precision("fp32").
+ * ---------------------------------------------------------------------------------------------- */
+int hvc_split3(const float* x, int64_t ldx, int32_t R, int32_t C, void* out, int64_t ldo, int32_t pattern,
+               int32_t concat_rows, void* stream);
+int hvc_softmax_rows(float* s, int64_t lds, int32_t R, int32_t M, float* lse2, void* stream);
+int hvc_im2col3d_f32(const float* x, const hvc_conv3d_geom* geom, float* cols, void* stream);
+/* out f32 [T,N] = resid + gate[t / rows_per_batch] * act(acc + bias)  (bias, resid, gate optional; act NONE | GELU):
+ * the epilogue of a verification-mode GEMM whose split-K partial sums were reduced into acc with fp32 atomics
+ * (TMEM accumulation chains are kept <= 256 elements because the tensor-core accumulator truncates). out may alias acc. */
+int hvc_epilogue_f32(const float* acc, int64_t lda, int32_t T, int32_t N, const float* bias, int32_t activation,
+                     const float* resid, int64_t ldr, const float* gate, int64_t gate_ld, int32_t rows_per_batch,
+                     float* out, int64_t ldo, void* stream);
 
 #ifdef __cplusplus
 }
