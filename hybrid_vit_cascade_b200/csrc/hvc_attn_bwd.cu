@@ -7,25 +7,48 @@
 //   attn_delta_kernel   delta[b,h,q] = sum_d dO * O                       (HBM-bound pre-pass)
 //   attn_bwd_kernel     one CTA = one (batch, head, 128-key tile), loops over 128-query tiles i:
 //        S^T  = K Q_i^T   (SS)      phase A: P^T = exp2(S^T*scale2 - lse2)          -> TMEM (bf16, own columns)
-//        dP^T = V dO_i^T  (SS)      phase B: dS^T = P^T * (dP^T - delta)            -> smem (bf16, swizzled)
+//        dP^T = V dO_i^T  (SS)      phase B: dS^T = P^T * (dP^T - delta)            -> smem (bf16, swizzled, 2 buffers)
 //        dV  += P^T  dO_i (TS, dO MN-major)
 //        dK  += dS^T Q_i  (SS, dS^T K-major, Q MN-major)          (softmax scale applied in the epilogue)
-//        dQ_i = dS   K    (SS, dS^T read MN-major as A, K MN-major) -> TMA reduce-add (fp32) into dq_accum
-//      320 threads: two elementwise warpgroups (thread == key row == TMEM lane; warpgroup w owns query
-//      columns [64w, 64w+64)), a TMA warp and an MMA warp.  TMEM is used to the last column
-//      (S^T 128 | P^T 64 | dP^T 128 | dV 64 | dK 64 | dQ 64 = 512) so that S^T(i+1) is computed while the
-//      warpgroups are still in phase B of tile i and dP^T(i+1) during phase A of tile i+1: the tensor
-//      pipe, the MUFU pipe (exp2) and the FMA pipe (packed f32x2 math) overlap instead of taking turns.
-//      The single swizzled smem copy of dS^T serves both the dK (K-major) and the dQ (MN-major) products.
+//        dQ_i = dS   K    (SS, dS^T read MN-major as A, K^T K-major) -> TMA reduce-add (fp32) into dq_accum
+//      320 threads: two elementwise warpgroups (thread == key row == TMEM lane; warpgroup x owns query columns
+//      [64x, 64x+64) of every tile), a TMA warp and an MMA warp.  Design points, each from a measurement on B200:
+//      * tcgen05.mma with a K-major A operand in shared memory costs ~108 clk per 128x128x16 step, an MN-major A
+//        ~65 clk (profiles/r01_umma_bench_by_operand_layout.log).  K and V stay fixed for the whole CTA, so they are
+//        transposed ONCE into MN-major K^T / V^T tiles; S^T and dP^T then run at the fast rate, and the same K^T tile
+//        is the (K-major) B operand of dQ.
+//      * the v3 kernel ran both warpgroups in lockstep on shared barriers: the exp unit was saturated during phase A
+//        and idle for the rest of the tile, and the loop-carried chain  dS(i-1) -> dP^T(i), dK(i-1), dQ(i-1) -> drain
+//        dQ -> phase B(i) -> dS(i)  left the tensor pipe idle ~1450 of 3800 clk per tile
+//        (profiles/r01_attn_bwd_timeline_d64_v3.log).  Now every product except dQ is issued per column half with its
+//        own barriers, the warpgroups take turns on the exp unit (named barriers, as in the forward kernel) so that one
+//        is in phase A while the other is in phase B / draining, dS^T is double-buffered and dQ(i-1) is drained after
+//        phase B(i).
+//      * four warpgroups of 32 columns (more warps per scheduler) were tried and lost: the per-thread fixed cost of a
+//        tile (waits, fences, address arithmetic, ~150 instructions) then weighs as much as the arithmetic
+//        (profiles/r01_attn_bwd_timeline_d64_v4a.log).
+//      * dQ tiles are staged for the TMA reduce in the dS^T sub-tile that the same warpgroup wrote two tiles earlier
+//        and dK/dQ have released, which is what lets three Q/dO stages and two dS^T buffers fit in shared memory.
+//      TMEM is used to the last column (S^T 128 | P^T 64 | dP^T 128 | dV d | dK d | dQ d).
 //   attn_dq_convert_kernel   dq_accum (f32, per head) * scale -> dq (bf16, packed token-major)
 #include "hvc_common.cuh"
 #include "hvc_host.h"
 
 namespace hvc {
 
-constexpr int kBwdThreads = 320;
-constexpr int kBT = 128;  // tile edge (queries and keys)
+constexpr int kBwdWGs = 2;                        // elementwise warpgroups
+constexpr int kBwdThreads = kBwdWGs * 128 + 64;   // + TMA warp (8) + MMA warp (9)
+constexpr int kBT = 128;                          // tile edge (queries and keys)
 constexpr int kQStages = 3;
+constexpr int kWgCols = kBT / kBwdWGs;            // query columns per warpgroup (64)
+#ifndef HVC_BWD_LSE_PRE
+#define HVC_BWD_LSE_PRE 2
+#endif
+constexpr int kLsePre = HVC_BWD_LSE_PRE;          // lse float4 loads issued ahead of their arithmetic in phase A (phase B preloads 8)
+#ifndef HVC_BWD_EMU
+#define HVC_BWD_EMU 0
+#endif
+constexpr int kBwdEmu = HVC_BWD_EMU;              // element pairs of every 16 whose exp2 is the FMA-pipe polynomial (0: MUFU has headroom here)
 
 struct AttnBwdKArgs {
   int batch, heads, nq, nk, nq_pad, n_q_tiles;
@@ -39,22 +62,29 @@ struct AttnBwdKArgs {
 
 template <int HD>
 struct BwdSmem {
-  static constexpr int kTile = kBT * HD * 2;                 // 16 KB
-  static constexpr int kK = 0;
-  static constexpr int kV = kTile;
+  static constexpr int kTile = kBT * HD * 2;                 // one 128 x HD bf16 tile (16 KB at HD 64)
+  static constexpr int kKT = 0;                              // K^T: HD rows x 128 keys, two 64-key sub-tiles of 128-byte rows
+  static constexpr int kVT = kTile;
   static constexpr int kQStage = 2 * kTile + 2048;           // Q, dO, lse2[128], delta[128], dropout row keys[128] (+pad to 1 KB)
   static constexpr int kQ = 2 * kTile;
-  static constexpr int kDS = kQ + kQStages * kQStage;        // [128 keys x 128 queries] bf16, two 64-query sub-tiles
-  static constexpr int kDQ = kDS + kBT * kBT * 2;            // dQ staging: two [128 x HD/2] fp32 halves (swizzled)
-  static constexpr int kBar = kDQ + kBT * HD * 4;
+  static constexpr int kDS = kQ + kQStages * kQStage;        // 2 x [128 keys x 128 queries] bf16 (two 64-query sub-tiles each);
+  static constexpr int kDSBuf = kBT * kBT * 2;               //   also: K/V landing zone at start, dQ staging when released
+  static constexpr int kBar = kDS + 2 * kDSBuf;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
+// mbarriers; the ones marked [2] exist once per column half (warpgroup)
+enum { BB_KV = 0, BB_KT = 1, BB_QF = 2, BB_QE = 5, BB_ST = 8 /*[2]*/, BB_STFREE = 10 /*[2]*/, BB_PT = 12 /*[2]*/, BB_DPT = 14 /*[2]*/,
+       BB_DS = 16 /*[2]*/, BB_DQF = 18, BB_DQFREE = 19, BB_N = 20 };
+// named barriers: 1 + x = warpgroup x (drain / staging), 3 + x = warpgroup x's turn on the exp unit
+enum { NB_WG = 1, NB_TURN = 3 };
+
 // Optional in-kernel timeline (bring-up builds, -DHVC_TRACE_BWD): SM-clock stamps of CTA (0,0) at the protocol points of
-// iterations [kTraceI0, kTraceI0+8) for warpgroup 0, warpgroup 1 and the MMA warp; read back with hvc_debug_bwd_trace.
+// iterations [kTraceI0, kTraceI0+8) for the two warpgroups (roles 0-1) and the MMA warp (role 2); read back with
+// hvc_debug_bwd_trace (tests/bringup/bwd_trace.py).
 #ifdef HVC_TRACE_BWD
-constexpr int kTraceI0 = 16, kTraceIters = 8, kTracePts = 12;
-__device__ unsigned long long g_bwd_trace[3 * kTraceIters * kTracePts];
+constexpr int kTraceI0 = 16, kTraceIters = 8, kTracePts = 12, kTraceRoles = 3;
+__device__ unsigned long long g_bwd_trace[kTraceRoles * kTraceIters * kTracePts];
 #define HVC_TR(role, i, pt)                                                                                     \
   do {                                                                                                          \
     if (blockIdx.x == 0 && blockIdx.y == 0 && (i) >= kTraceI0 && (i) < kTraceI0 + kTraceIters)                  \
@@ -64,82 +94,100 @@ __device__ unsigned long long g_bwd_trace[3 * kTraceIters * kTracePts];
 #define HVC_TR(role, i, pt) do {} while (0)
 #endif
 
-enum { BB_KV = 0, BB_QF = 1, BB_QE = 4, BB_ST = 7, BB_STFREE = 8, BB_PT = 9, BB_DPT = 10, BB_DS = 11, BB_DQF = 12, BB_DQFREE = 13, BB_N = 14 };
-
-// ---- elementwise phases of one (key tile, query tile) pair; thread == key row, 64 query columns per thread.
+// ---- elementwise phases of one (key tile, query tile) pair; thread == key row, 32 query columns per thread.
 // FULL = no padding rows/columns in this pair (the masked variant is a separate code path: selects cost issue slots).
 // Phase A: P^T = exp2(S^T*scale2 - lse2); the pre-pass stores -lse2 so the argument is a single FFMA2.
 // DROP: attn_drop on P.  The keep decision of element (query, key) is regenerated from the query's row key (smem,
 // written by the pre-pass) and this thread's key column; it is carried to phase B in the SIGN of the fp32 P value
 // (P >= 0): dropped entries are stored negated, and the bf16 P^T that feeds dV is packed with relu (dropped -> 0).
 template <bool FULL, bool DROP>
-__device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[64], uint32_t lse_saddr, float2 nss, bool key_ok, int q_valid,
-                                            float2 (&pv)[32], uint32_t (&ppk)[32], uint32_t rk_saddr, uint32_t colkey, uint32_t thr) {
+__device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[kWgCols], uint32_t lse_saddr, float2 nss, bool key_ok, int q_valid,
+                                            float2 (&pv)[kWgCols / 2], uint32_t (&ppk)[kWgCols / 2], uint32_t rk_saddr, uint32_t colkey,
+                                            uint32_t thr) {
+  // lse loads are issued in small batches ahead of their arithmetic: the asm statements keep program order, and a load
+  // placed next to its first use exposes the shared-memory latency once per 4 columns
 #pragma unroll
-  for (int t = 0; t < 64; t += 4) {
-    const float4 l4 = lds_f4(lse_saddr + t * 4);
-    const float2 a = ffma2(make_float2(__uint_as_float(sv[t]), __uint_as_float(sv[t + 1])), nss, make_float2(l4.x, l4.y));
-    const float2 c = ffma2(make_float2(__uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3])), nss, make_float2(l4.z, l4.w));
-    float2 e0 = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-    float2 e1 = make_float2(ex2_approx(c.x), ex2_approx(c.y));
-    if (!FULL) {
-      e0.x = (key_ok && t + 0 < q_valid) ? e0.x : 0.f;
-      e0.y = (key_ok && t + 1 < q_valid) ? e0.y : 0.f;
-      e1.x = (key_ok && t + 2 < q_valid) ? e1.x : 0.f;
-      e1.y = (key_ok && t + 3 < q_valid) ? e1.y : 0.f;
+  for (int g = 0; g < kWgCols; g += 4 * kLsePre) {
+    float4 lq[kLsePre];
+#pragma unroll
+    for (int u = 0; u < kLsePre; ++u) lq[u] = lds_f4(lse_saddr + (g + 4 * u) * 4);
+#pragma unroll
+    for (int u = 0; u < kLsePre; ++u) {
+      const int t = g + 4 * u;
+      const float4 l4 = lq[u];
+      const float2 a = ffma2(make_float2(__uint_as_float(sv[t]), __uint_as_float(sv[t + 1])), nss, make_float2(l4.x, l4.y));
+      const float2 c = ffma2(make_float2(__uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3])), nss, make_float2(l4.z, l4.w));
+      float2 e0, e1;
+      if (((t >> 1) * kBwdEmu) % 16 < kBwdEmu) e0 = ex2_poly2(a);
+      else e0 = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+      if ((((t >> 1) + 1) * kBwdEmu) % 16 < kBwdEmu) e1 = ex2_poly2(c);
+      else e1 = make_float2(ex2_approx(c.x), ex2_approx(c.y));
+      if (!FULL) {
+        e0.x = (key_ok && t + 0 < q_valid) ? e0.x : 0.f;
+        e0.y = (key_ok && t + 1 < q_valid) ? e0.y : 0.f;
+        e1.x = (key_ok && t + 2 < q_valid) ? e1.x : 0.f;
+        e1.y = (key_ok && t + 3 < q_valid) ? e1.y : 0.f;
+      }
+      if (DROP) {
+        const uint4 rk = lds_u4(rk_saddr + t * 4);
+        e0.x = mum32(rk.x ^ colkey, 0x2545F491u) >= thr ? e0.x : -e0.x;
+        e0.y = mum32(rk.y ^ colkey, 0x2545F491u) >= thr ? e0.y : -e0.y;
+        e1.x = mum32(rk.z ^ colkey, 0x2545F491u) >= thr ? e1.x : -e1.x;
+        e1.y = mum32(rk.w ^ colkey, 0x2545F491u) >= thr ? e1.y : -e1.y;
+      }
+      pv[t >> 1] = e0;
+      pv[(t >> 1) + 1] = e1;
+      ppk[t >> 1] = DROP ? pack_bf16_relu(e0.x, e0.y) : pack_bf16(e0.x, e0.y);
+      ppk[(t >> 1) + 1] = DROP ? pack_bf16_relu(e1.x, e1.y) : pack_bf16(e1.x, e1.y);
     }
-    if (DROP) {
-      const uint4 rk = lds_u4(rk_saddr + t * 4);
-      e0.x = mum32(rk.x ^ colkey, 0x2545F491u) >= thr ? e0.x : -e0.x;
-      e0.y = mum32(rk.y ^ colkey, 0x2545F491u) >= thr ? e0.y : -e0.y;
-      e1.x = mum32(rk.z ^ colkey, 0x2545F491u) >= thr ? e1.x : -e1.x;
-      e1.y = mum32(rk.w ^ colkey, 0x2545F491u) >= thr ? e1.y : -e1.y;
-    }
-    pv[t >> 1] = e0;
-    pv[(t >> 1) + 1] = e1;
-    ppk[t >> 1] = DROP ? pack_bf16_relu(e0.x, e0.y) : pack_bf16(e0.x, e0.y);
-    ppk[(t >> 1) + 1] = DROP ? pack_bf16_relu(e1.x, e1.y) : pack_bf16(e1.x, e1.y);
   }
 }
-// Phase B: dS^T = P^T * (dP^T - delta) -> swizzled smem sub-tile (8 x 16-byte chunks of this thread's row)
+// Phase B: dS^T = P^T * (dP^T - delta) -> four 16-byte chunks (chunk0 ..) of this thread's row in a swizzled sub-tile
 // DROP: dS = P * (keep ? dP / (1-p) : 0  -  delta), keep = sign of the stored P value.
 template <bool FULL, bool DROP>
-__device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[64], uint32_t delta_saddr, const float2 (&pv)[32], bool key_ok,
-                                            int q_valid, uint32_t sub_saddr, int r, float inv_keep) {
+__device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[kWgCols], uint32_t delta_saddr, const float2 (&pv)[kWgCols / 2],
+                                            bool key_ok, int q_valid, uint32_t sub_saddr, int r, int chunk0, float inv_keep) {
   const float2 neg1 = make_float2(-1.f, -1.f);
   const float2 rp2 = make_float2(inv_keep, inv_keep);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint32_t w4[4];
+  for (int g = 0; g < kWgCols; g += 32) {
+    float4 dq4[8];                          // delta of a 32-column group, loaded ahead of the arithmetic (see phase A)
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = 8 * k + 4 * u;
-      const float4 d4 = lds_f4(delta_saddr + t * 4);
-      float2 x0, x1;
-      if (DROP) {
-        const float2 p0 = pv[t >> 1], p1 = pv[(t >> 1) + 1];
-        const float2 a0 = ffma2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), rp2, make_float2(-d4.x, -d4.y));
-        const float2 a1 = ffma2(make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])), rp2, make_float2(-d4.z, -d4.w));
-        x0.x = (p0.x > 0.f ? a0.x : -d4.x) * fabsf(p0.x);
-        x0.y = (p0.y > 0.f ? a0.y : -d4.y) * fabsf(p0.y);
-        x1.x = (p1.x > 0.f ? a1.x : -d4.z) * fabsf(p1.x);
-        x1.y = (p1.y > 0.f ? a1.y : -d4.w) * fabsf(p1.y);
-      } else {
-        x0 = ffma2(make_float2(d4.x, d4.y), neg1, make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])));
-        x1 = ffma2(make_float2(d4.z, d4.w), neg1, make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])));
-        x0 = fmul2(x0, pv[t >> 1]);
-        x1 = fmul2(x1, pv[(t >> 1) + 1]);
+    for (int u = 0; u < 8; ++u) dq4[u] = lds_f4(delta_saddr + (g + 4 * u) * 4);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = (g >> 3) + kk;
+      uint32_t w4[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = 8 * k + 4 * u;
+        const float4 d4 = dq4[2 * kk + u];
+        float2 x0, x1;
+        if (DROP) {
+          const float2 p0 = pv[t >> 1], p1 = pv[(t >> 1) + 1];
+          const float2 a0 = ffma2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), rp2, make_float2(-d4.x, -d4.y));
+          const float2 a1 = ffma2(make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])), rp2, make_float2(-d4.z, -d4.w));
+          x0.x = (p0.x > 0.f ? a0.x : -d4.x) * fabsf(p0.x);
+          x0.y = (p0.y > 0.f ? a0.y : -d4.y) * fabsf(p0.y);
+          x1.x = (p1.x > 0.f ? a1.x : -d4.z) * fabsf(p1.x);
+          x1.y = (p1.y > 0.f ? a1.y : -d4.w) * fabsf(p1.y);
+        } else {
+          x0 = ffma2(make_float2(d4.x, d4.y), neg1, make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])));
+          x1 = ffma2(make_float2(d4.z, d4.w), neg1, make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])));
+          x0 = fmul2(x0, pv[t >> 1]);
+          x1 = fmul2(x1, pv[(t >> 1) + 1]);
+        }
+        if (!FULL) {   // padded delta may be garbage: 0 * NaN must not leak
+          x0.x = (key_ok && t + 0 < q_valid) ? x0.x : 0.f;
+          x0.y = (key_ok && t + 1 < q_valid) ? x0.y : 0.f;
+          x1.x = (key_ok && t + 2 < q_valid) ? x1.x : 0.f;
+          x1.y = (key_ok && t + 3 < q_valid) ? x1.y : 0.f;
+        }
+        w4[2 * u] = pack_bf16(x0.x, x0.y);
+        w4[2 * u + 1] = pack_bf16(x1.x, x1.y);
       }
-      if (!FULL) {   // padded delta may be garbage: 0 * NaN must not leak
-        x0.x = (key_ok && t + 0 < q_valid) ? x0.x : 0.f;
-        x0.y = (key_ok && t + 1 < q_valid) ? x0.y : 0.f;
-        x1.x = (key_ok && t + 2 < q_valid) ? x1.x : 0.f;
-        x1.y = (key_ok && t + 3 < q_valid) ? x1.y : 0.f;
-      }
-      w4[2 * u] = pack_bf16(x0.x, x0.y);
-      w4[2 * u + 1] = pack_bf16(x1.x, x1.y);
+      sts_u4(sub_saddr + sw128_offset(r, chunk0 + k), w4[0], w4[1], w4[2], w4[3]);
     }
-    sts_u4(sub_saddr + sw128_offset(r, k), w4[0], w4[1], w4[2], w4[3]);
   }
 }
 
@@ -150,7 +198,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmDQ, const AttnBwdKArgs p) {
   static_assert(HD == 64 || HD == 32, "head_dim 64 (SWIZZLE_128B tiles) or 32 (SWIZZLE_64B tiles)");
   using L = BwdSmem<HD>;
-  using SW = Swz<HD * 2>;        // Q / K / V / dO tiles and the fp32 dQ staging halves: rows of HD*2 bytes
+  using SW = Swz<HD * 2>;        // Q / K / V / dO tiles as TMA delivers them: rows of HD*2 bytes
+  constexpr int kDCols = HD / kBwdWGs;     // d columns of dQ / dK / dV owned by one warpgroup (16 or 8)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
@@ -162,33 +211,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int j = blockIdx.x;           // key tile
   const int nQ = p.n_q_tiles;
+  constexpr int kTmaWarp = kBwdWGs * 4, kMmaWarp = kBwdWGs * 4 + 1;
+  constexpr uint32_t kEw = kBwdWGs * 4;     // elementwise warps: one mbarrier arrival per warp on the joint barriers
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO); tma_prefetch_desc(&tmDQ);
     mbar_init(&bar[BB_KV], 1);
+    mbar_init(&bar[BB_KT], kEw);
     for (int s = 0; s < kQStages; ++s) { mbar_init(&bar[BB_QF + s], 1); mbar_init(&bar[BB_QE + s], 1); }
-    mbar_init(&bar[BB_ST], 1);
-    mbar_init(&bar[BB_STFREE], 256);
-    mbar_init(&bar[BB_PT], 256);
-    mbar_init(&bar[BB_DPT], 1);
-    mbar_init(&bar[BB_DS], 256);
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&bar[BB_ST + x], 1);
+      mbar_init(&bar[BB_STFREE + x], 4);
+      mbar_init(&bar[BB_PT + x], 4);
+      mbar_init(&bar[BB_DPT + x], 1);
+      mbar_init(&bar[BB_DS + x], 4);
+    }
     mbar_init(&bar[BB_DQF], 1);
-    mbar_init(&bar[BB_DQFREE], 256);
+    mbar_init(&bar[BB_DQFREE], kEw);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t kColSt = 0, kColPt = 128, kColDPt = 192, kColDV = 320, kColDK = 320 + HD, kColDQ = 320 + 2 * HD;
+  constexpr uint32_t kSubKT = HD * 128;     // one 64-key sub-tile of K^T / V^T: HD rows of 128 bytes
+  constexpr uint32_t kHalfRows = 64 * HD * 2;   // byte offset of row 64 inside a Q / dO tile (a whole number of swizzle atoms)
 
-  if (warp == 8) {
+  if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(&bar[BB_KV], 2 * L::kTile);
-      tma_load_2d(smem + L::kK, &tmK, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
-      tma_load_2d(smem + L::kV, &tmV, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
+      mbar_arrive_expect_tx(&bar[BB_KV], 2 * L::kTile);     // K, V land in the (still unused) dS^T buffers
+      tma_load_2d(smem + L::kDS, &tmK, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
+      tma_load_2d(smem + L::kDS + L::kTile, &tmV, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
       for (int i = 0; i < nQ; ++i) {
         const int st = i % kQStages;
         const uint32_t ph = (i / kQStages) & 1;
@@ -202,95 +258,116 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (DROP) bulk_load_1d(base + 2 * L::kTile + 2 * kBT * 4, p.rowkeys + (long long)bh * p.nq_pad + i * kBT, kBT * 4, &bar[BB_QF + st]);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (whole warp runs the loop; only the elected lane issues) =====================
+    // Warpgroup 1 runs about half a tile behind warpgroup 0 (they alternate on the exp unit), and the issue order below
+    // follows the order in which their results become available:
+    //   dS_1(i-1) | P_0(i) | STFREE_0+1(i) | dS_0(i) | P_1(i)
     const bool leader = elect_one();
-    constexpr uint32_t id_s = make_idesc_bf16(kBT, kBT, kMajorK, kMajorK);      // S^T, dP^T
-    constexpr uint32_t id_dv = make_idesc_bf16(kBT, HD, kMajorK, kMajorMN);     // dV (A in TMEM), dK (A K-major smem)
-    constexpr uint32_t id_dq = make_idesc_bf16(kBT, HD, kMajorMN, kMajorMN);    // dQ
-    const uint32_t sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
-    const uint32_t sQ0 = smem_u32(smem + L::kQ), sDS = smem_u32(smem + L::kDS);
-    auto issue_st = [&](int st) {
+    constexpr uint32_t id_s = make_idesc_bf16(kBT, kWgCols, kMajorMN, kMajorK);  // dP^T_x: A = V^T (MN-major), B = 64 rows of dO
+    constexpr uint32_t id_s2 = make_idesc_bf16(kBT, kBT, kMajorMN, kMajorK);     // S^T (both halves): A = K^T (MN-major), B = Q
+    constexpr uint32_t id_dv = make_idesc_bf16(kBT, HD, kMajorK, kMajorMN);      // dV_x (A in TMEM), dK_x (A K-major smem), B MN-major
+    constexpr uint32_t id_dq = make_idesc_bf16(kBT, HD, kMajorMN, kMajorK);      // dQ: A = dS^T read MN-major, B = K^T (K-major)
+    const uint32_t sKT = smem_u32(smem + L::kKT), sVT = smem_u32(smem + L::kVT);
+    const uint32_t sQ0 = smem_u32(smem + L::kQ), sDS0 = smem_u32(smem + L::kDS);
+    auto commit = [&](int barrier) { if (leader) tc_commit(&bar[barrier]); };
+    auto issue_st = [&](int st) {       // S^T = K Q^T for both column halves in one N=128 product (cheaper per column than two N=64)
       const uint32_t sQ = sQ0 + st * L::kQStage;
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
-          umma_ss(tmem_base + kColSt, SW::desc(sK + k16 * 32), SW::desc(sQ + k16 * 32), id_s, k16 > 0 ? 1u : 0u);
+          umma_ss(tmem_base + kColSt, make_sdesc_sw128(sKT + k16 * 2048, kSubKT, 1024), SW::desc(sQ + k16 * 32), id_s2, k16 > 0 ? 1u : 0u);
       }
+      commit(BB_ST + 0);
+      commit(BB_ST + 1);
     };
-    auto issue_dpt = [&](int st) {
-      const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
+    auto issue_dpt = [&](int x, int st) {      // dP^T_x = V dO_x^T
+      const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile + x * kHalfRows;
       if (leader) {
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
-          umma_ss(tmem_base + kColDPt, SW::desc(sV + k16 * 32), SW::desc(sDO + k16 * 32), id_s, k16 > 0 ? 1u : 0u);
+          umma_ss(tmem_base + kColDPt + x * kWgCols, make_sdesc_sw128(sVT + k16 * 2048, kSubKT, 1024), SW::desc(sDO + k16 * 32), id_s,
+                  k16 > 0 ? 1u : 0u);
+      }
+      commit(BB_DPT + x);
+    };
+    auto issue_dv = [&](int x, int st, bool first) {   // dV += P^T_x dO_x   (A = P^T_x in TMEM, 8 columns per K=16 step; B = dO MN-major)
+      const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < kWgCols / 16; ++k16)
+          umma_ts(tmem_base + kColDV, tmem_base + kColPt + x * (kWgCols / 2) + k16 * 8,
+                  SW::desc(sDO + (x * (kWgCols / 16) + k16) * SW::kMnStep, 8192), id_dv, (!first || k16 > 0) ? 1u : 0u);
       }
     };
-    auto commit = [&](int barrier) { if (leader) tc_commit(&bar[barrier]); };
-    mbar_wait(&bar[BB_KV], 0, 20);
+    auto issue_dk = [&](int x, int st, int buf, bool first) {   // dK += dS^T_x Q_x   (A = sub-tile x of the dS^T buffer, K-major; B = Q MN-major)
+      const uint32_t sQ = sQ0 + st * L::kQStage;
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < kWgCols / 16; ++k16)
+          umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS0 + buf * L::kDSBuf + x * 16384 + k16 * 32, 16, 1024),
+                  SW::desc(sQ + (x * (kWgCols / 16) + k16) * SW::kMnStep, 8192), id_dv, (!first || k16 > 0) ? 1u : 0u);
+      }
+    };
+    auto issue_dq = [&](int buf) {   // dQ = dS K   (A = both dS^T sub-tiles read MN-major: M = queries; B = K^T K-major: rows = d, two 64-key sub-tiles)
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < kBT / 16; ++k16)
+          umma_ss(tmem_base + kColDQ, make_sdesc_sw128(sDS0 + buf * L::kDSBuf + k16 * 2048, 16384, 1024),
+                  make_sdesc_sw128(sKT + (k16 >> 2) * kSubKT + (k16 & 3) * 32, 16, 1024), id_dq, k16 > 0 ? 1u : 0u);
+      }
+      commit(BB_DQF);
+    };
+    // tail of tile t (needs dS_1(t)): dP^T_1(t+1), dK_1(t), dQ(t); releases the Q/dO stage of tile t
+    auto finish_tile = [&](int t) {
+      mbar_wait(&bar[BB_DS + 1], t & 1, 25);
+      tc_fence_after();
+      if (leader) HVC_TR(2, t + 1, 2);
+      if (t + 1 < nQ) issue_dpt(1, (t + 1) % kQStages);
+      issue_dk(1, t % kQStages, t & 1, false);
+      if (t > 0) { mbar_wait(&bar[BB_DQFREE], (t - 1) & 1, 26); tc_fence_after(); }
+      issue_dq(t & 1);
+      commit(BB_QE + t % kQStages);
+      if (leader) HVC_TR(2, t + 1, 3);
+    };
+    mbar_wait(&bar[BB_KT], 0, 20);
     mbar_wait(&bar[BB_QF + 0], 0, 21);
     tc_fence_after();
     issue_st(0);
-    commit(BB_ST);
-    issue_dpt(0);
-    commit(BB_DPT);
+    issue_dpt(0, 0);
+    issue_dpt(1, 0);
     for (int i = 0; i < nQ; ++i) {
       const int st = i % kQStages;
       const int st1 = (i + 1) % kQStages;
-      const uint32_t sQ = sQ0 + st * L::kQStage, sDO = sQ + L::kTile;
-      // (1) S^T(i+1) as soon as the warpgroups have pulled S^T(i) out of TMEM
+      const bool more = i + 1 < nQ;
       if (leader) HVC_TR(2, i, 0);
-      if (i + 1 < nQ) {
-        mbar_wait(&bar[BB_STFREE], i & 1, 22);
+      if (leader) HVC_TR(2, i, 1);
+      if (i > 0) finish_tile(i - 1);
+      mbar_wait(&bar[BB_PT + 0], i & 1, 24);
+      tc_fence_after();
+      if (leader) HVC_TR(2, i, 4);
+      issue_dv(0, st, i == 0);
+      if (more) {                                   // S^T(i+1) once both warpgroups have pulled S^T(i) out of TMEM
+        mbar_wait(&bar[BB_STFREE + 0], i & 1, 22);
+        mbar_wait(&bar[BB_STFREE + 1], i & 1, 27);
         mbar_wait(&bar[BB_QF + st1], ((i + 1) / kQStages) & 1, 23);
         tc_fence_after();
-        if (leader) HVC_TR(2, i, 1);
         issue_st(st1);
-        commit(BB_ST);
       }
-      if (leader) HVC_TR(2, i, 2);
-      // (2) dV += P^T dO     (A = P^T in TMEM, 8 columns per K=16 step; B = dO MN-major)
-      mbar_wait(&bar[BB_PT], i & 1, 24);
-      tc_fence_after();
-      if (leader) HVC_TR(2, i, 3);
-      if (leader) {
-#pragma unroll
-        for (int k16 = 0; k16 < kBT / 16; ++k16)
-          umma_ts(tmem_base + kColDV, tmem_base + kColPt + k16 * 8, SW::desc(sDO + k16 * SW::kMnStep, 8192), id_dv,
-                  (i > 0 || k16 > 0) ? 1u : 0u);
-      }
-      // (3) once dS^T(i) is in smem (and dP^T(i) consumed): dP^T(i+1), dK, dQ
-      if (leader) HVC_TR(2, i, 4);
-      mbar_wait(&bar[BB_DS], i & 1, 25);
-      tc_fence_after();
       if (leader) HVC_TR(2, i, 5);
-      if (i + 1 < nQ) {
-        issue_dpt(st1);
-        commit(BB_DPT);
-      }
-      // dK += dS^T Q     (A = dS^T K-major: two 64-query sub-tiles; B = Q MN-major)
-      if (leader) {
-#pragma unroll
-        for (int k16 = 0; k16 < kBT / 16; ++k16)
-          umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS + (k16 >> 2) * 16384 + (k16 & 3) * 32, 16, 1024),
-                  SW::desc(sQ + k16 * SW::kMnStep, 8192), id_dv, (i > 0 || k16 > 0) ? 1u : 0u);
-      }
+      mbar_wait(&bar[BB_DS + 0], i & 1, 28);        // dS_0(i) in smem, dP^T_0(i) consumed
+      tc_fence_after();
       if (leader) HVC_TR(2, i, 6);
-      if (i > 0) { mbar_wait(&bar[BB_DQFREE], (i - 1) & 1, 26); tc_fence_after(); }
+      if (more) issue_dpt(0, st1);
+      issue_dk(0, st, i & 1, i == 0);
+      mbar_wait(&bar[BB_PT + 1], i & 1, 29);
+      tc_fence_after();
       if (leader) HVC_TR(2, i, 7);
-      // dQ_i = dS K      (A = dS^T read MN-major: M = queries contiguous, K = key rows; B = K MN-major)
-      if (leader) {
-#pragma unroll
-        for (int k16 = 0; k16 < kBT / 16; ++k16)
-          umma_ss(tmem_base + kColDQ, make_sdesc_sw128(sDS + k16 * 2048, 16384, 1024),
-                  SW::desc(sK + k16 * SW::kMnStep, 8192), id_dq, k16 > 0 ? 1u : 0u);
-      }
-      commit(BB_DQF);
-      commit(BB_QE + st);
-      if (leader) HVC_TR(2, i, 8);
+      issue_dv(1, st, false);
     }
+    finish_tile(nQ - 1);
   } else {
-    // ===================== elementwise warpgroups: thread == key row, warpgroup w == 64 query columns =====================
+    // ===================== elementwise warpgroups: thread == key row, warpgroup x == query columns [64x, 64x+64) =====================
     const int wg = warp >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -298,34 +375,60 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool key_ok = (j * kBT + r) < p.nk;
     const bool keys_full = (j + 1) * kBT <= p.nk;
     const float scale2 = p.scale2;
-    uint8_t* dq_stage = smem + L::kDQ + wg * (kBT * (HD / 2) * 4);
-    const uint32_t dq_saddr = smem_u32(dq_stage);
+    const bool wg_lead = (threadIdx.x & 127) == 0;
+    const uint32_t sDS0 = smem_u32(smem + L::kDS);
 
+    // ---- one-time: transpose K and V (landed K-major, rows = keys) into MN-major K^T / V^T (rows = d, 64 keys per 128-byte
+    // row, SWIZZLE_128B).  Warpgroup x moves d columns [x*HD/2, (x+1)*HD/2) of this thread's key row.
+    mbar_wait(&bar[BB_KV], 0, 30);
+    {
+      const uint32_t dst_row_base = (r >> 6) * kSubKT + (r & 7) * 2;
+      const uint32_t key_chunk = (r & 63) >> 3;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t land = sDS0 + which * L::kTile;
+        const uint32_t dst = smem_u32(smem + (which == 0 ? L::kKT : L::kVT)) + dst_row_base;
+#pragma unroll
+        for (int c = 0; c < kDCols / 8; ++c) {
+          const int chunk = wg * (kDCols / 8) + c;
+          const uint4 u = lds_u4(land + SW::offset(r, chunk));
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t d = chunk * 8 + e;
+            sts_u16(dst + d * 128 + ((key_chunk ^ (d & 7)) << 4), static_cast<uint16_t>(w[e >> 1] >> (16 * (e & 1))));
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&bar[BB_KT]);
+    }
+
+    // dQ(i) drain: TMEM -> registers -> swizzled staging tile -> TMA reduce-add.  The staging tile is sub-tile `wg` of the
+    // dS^T buffer (i & 1), which dK/dQ(i) have released and which this same warpgroup rewrites in phase B(i+2).
     auto drain_dq = [&](int i) {
       mbar_wait(&bar[BB_DQF], i & 1, 31);
       tc_fence_after();
-      if ((threadIdx.x & 127) == 0) HVC_TR(wg, i + 1, 10);
-      if ((threadIdx.x & 127) == 0) bulk_wait_read<0>();      // previous reduce has finished reading the staging tile
-      named_bar_sync(1 + wg, 128);
-      uint32_t v[HD / 2];
-      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + kColDQ + wg * 32, v);   // lane = query row of tile i,
-      else                    tmem_ld_32x16(tmem_base + lane_base + kColDQ + wg * 16, v);   // this warpgroup's half of the d columns
+      if (wg_lead) HVC_TR(wg, i + 1, 8);
+      uint32_t v[kDCols];
+      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + kColDQ + wg * kDCols, v);   // lane = query row of tile i,
+      else                    tmem_ld_32x16(tmem_base + lane_base + kColDQ + wg * kDCols, v);   // this warpgroup's half of the d columns
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&bar[BB_DQFREE]);
-      if ((threadIdx.x & 127) == 0) HVC_TR(wg, i + 1, 11);
+      mbar_arrive_warp(&bar[BB_DQFREE]);
+      const uint32_t stage_off = L::kDS + (i & 1) * L::kDSBuf + wg * 16384;
+      const uint32_t stage = smem_u32(smem + stage_off);
 #pragma unroll
-      for (int k = 0; k < HD / 8; ++k) sts_u4(dq_saddr + SW::offset(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      for (int k = 0; k < kDCols / 4; ++k) sts_u4(stage + swz_offset<kDCols * 4>(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
       fence_proxy_async_smem();
-      named_bar_sync(1 + wg, 128);
-      if ((threadIdx.x & 127) == 0) {
-        tma_reduce_add_2d(&tmDQ, dq_stage, wg * (HD / 2), bh * p.nq_pad + i * kBT);
+      named_bar_sync(NB_WG + wg, 128);
+      if (wg_lead) {
+        tma_reduce_add_2d(&tmDQ, smem + stage_off, wg * kDCols, bh * p.nq_pad + i * kBT);
         bulk_commit();
       }
     };
 
     const float2 nss = make_float2(scale2, scale2);
-    const uint32_t sub_saddr = smem_u32(smem + L::kDS + wg * 16384);
     uint32_t colkey = 0, thr = 0;
     float inv_keep = 1.f;
     if (DROP) {
@@ -333,84 +436,91 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       thr = p.drop.thr;
       inv_keep = p.drop.inv_keep;
     }
+    if (wg == 1) named_bar_arrive(NB_TURN + 0, 256);          // warpgroup 0 takes the first turn on the exp unit
     for (int i = 0; i < nQ; ++i) {
       const int st = i % kQStages;
-      const uint32_t lse_saddr = smem_u32(smem + L::kQ + st * L::kQStage + 2 * L::kTile) + wg * 64 * 4;
+      const uint32_t lse_saddr = smem_u32(smem + L::kQ + st * L::kQStage + 2 * L::kTile) + wg * kWgCols * 4;
       const uint32_t delta_saddr = lse_saddr + kBT * 4;
       const uint32_t rk_saddr = lse_saddr + 2 * kBT * 4;
-      const int q_valid = p.nq - i * kBT - wg * 64;        // this warpgroup's columns >= q_valid are padding
-      const bool full = keys_full && q_valid >= 64;
-      float2 pv[32];                                       // P^T row slice, fp32, lives across phase A -> B
+      const int q_valid = p.nq - i * kBT - wg * kWgCols;      // this warpgroup's columns >= q_valid are padding
+      const bool full = keys_full && q_valid >= kWgCols;
+      float2 pv[kWgCols / 2];                                 // P^T row slice, fp32, lives across phase A -> B
 
       // ---------------- phase A: P^T = exp2(S^T * scale2 - lse2)
-      const bool tr = (threadIdx.x & 127) == 0;
-      if (tr) HVC_TR(wg, i, 0);
+      if (wg_lead) HVC_TR(wg, i, 0);
       mbar_wait(&bar[BB_QF + st], (i / kQStages) & 1, 32);  // lse/delta of this query tile are in smem
-      mbar_wait(&bar[BB_ST], i & 1, 33);
+      mbar_wait(&bar[BB_ST + wg], i & 1, 33);
       tc_fence_after();
-      if (tr) HVC_TR(wg, i, 1);
       {
-        uint32_t sv[64];
+        uint32_t sv[kWgCols];
         uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
         uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
-        tmem_ld_32x32(tmem_base + lane_base + kColSt + wg * 64, s0);
-        tmem_ld_32x32(tmem_base + lane_base + kColSt + wg * 64 + 32, s1);
+        tmem_ld_32x32(tmem_base + lane_base + kColSt + wg * kWgCols, s0);
+        tmem_ld_32x32(tmem_base + lane_base + kColSt + wg * kWgCols + 32, s1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&bar[BB_STFREE]);
-        if (tr) HVC_TR(wg, i, 2);
-        uint32_t ppk[32];
+        mbar_arrive_warp(&bar[BB_STFREE + wg]);
+        if (wg_lead) HVC_TR(wg, i, 1);
+        named_bar_sync(NB_TURN + wg, 256);                    // my turn on the exp unit
+        if (wg_lead) HVC_TR(wg, i, 2);
+        uint32_t ppk[kWgCols / 2];
         if (full) bwd_phase_a<true, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
         else      bwd_phase_a<false, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
-        if (tr) HVC_TR(wg, i, 3);
-        tmem_st_32x32(tmem_base + lane_base + kColPt + wg * 32, ppk);
+        if (!(wg == 1 && i == nQ - 1)) named_bar_arrive(NB_TURN + (wg ^ 1), 256);
+        if (wg_lead) HVC_TR(wg, i, 3);
+        // dP^T_x(i) was issued after dV_x(i-1): once it has completed, dV_x(i-1) has finished reading P^T_x(i-1) and the
+        // P^T columns may be overwritten (the wait is long satisfied by now; it is also phase B's input)
+        mbar_wait(&bar[BB_DPT + wg], i & 1, 34);
+        tc_fence_after();
+        tmem_st_32x32(tmem_base + lane_base + kColPt + wg * (kWgCols / 2), ppk);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(&bar[BB_PT]);
-        if (tr) HVC_TR(wg, i, 4);
+        mbar_arrive_warp(&bar[BB_PT + wg]);
       }
 
-      // ---------------- drain dQ(i-1) while the tensor pipe works on dV(i) / dP^T(i)
-      if (i > 0) drain_dq(i - 1);      // also guarantees dK(i-1)/dQ(i-1) are done reading the dS^T tile
-      if (tr) HVC_TR(wg, i, 5);
-
-      // ---------------- phase B: dS^T = P^T * (dP^T - delta)
-      mbar_wait(&bar[BB_DPT], i & 1, 34);
-      tc_fence_after();
-      if (tr) HVC_TR(wg, i, 6);
+      // ---------------- phase B: dS^T_x = P^T * (dP^T - delta) -> sub-tile x of dS^T buffer (i & 1)
+      if (wg_lead) HVC_TR(wg, i, 4);
       {
-        uint32_t dv[64];
+        uint32_t dv[kWgCols];
         uint32_t(&d0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dv[0]);
         uint32_t(&d1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dv[32]);
-        tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64, d0);
-        tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * 64 + 32, d1);
+        tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * kWgCols, d0);
+        tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * kWgCols + 32, d1);
+        // the sub-tile held this warpgroup's dQ(i-2) staging tile: its reduce must have finished reading it
+        if (wg_lead) bulk_wait_read<0>();
+        named_bar_sync(NB_WG + wg, 128);
         tmem_ld_wait();
-        if (tr) HVC_TR(wg, i, 7);
-        if (full) bwd_phase_b<true, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, inv_keep);
-        else      bwd_phase_b<false, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, inv_keep);
+        if (wg_lead) HVC_TR(wg, i, 5);
+        const uint32_t sub_saddr = sDS0 + (i & 1) * L::kDSBuf + wg * 16384;
+        if (full) bwd_phase_b<true, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, 0, inv_keep);
+        else      bwd_phase_b<false, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, 0, inv_keep);
       }
-      if (tr) HVC_TR(wg, i, 8);
+      if (wg_lead) HVC_TR(wg, i, 6);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&bar[BB_DS]);
-      if (tr) HVC_TR(wg, i, 9);
+      mbar_arrive_warp(&bar[BB_DS + wg]);
+      if (wg_lead) HVC_TR(wg, i, 7);
+
+      // ---------------- drain dQ(i-1) while the tensor pipe works on the next products
+      if (i > 0) drain_dq(i - 1);
+      if (wg_lead) HVC_TR(wg, i, 9);
     }
     drain_dq(nQ - 1);   // the commit behind BB_DQF covers every earlier MMA: dV and dK are complete too
-    if ((threadIdx.x & 127) == 0) bulk_wait<0>();
+    if (wg_lead) bulk_wait<0>();
 
-    // ---- epilogue: dV, dK (x softmax scale) -> bf16 -> global; warpgroup w writes d columns [HD/2 w, HD/2 (w+1))
+    // ---- epilogue: dV, dK (x softmax scale) -> bf16 -> global; warpgroup x writes d columns [x*HD/2, (x+1)*HD/2)
     const int key = j * kBT + r;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD + wg * (HD / 2);
+      bf16* dst = (which == 0 ? p.dv + (long long)(b * p.nk + key) * p.lddv : p.dk + (long long)(b * p.nk + key) * p.lddk) + h * HD + wg * kDCols;
       const float mul = which == 0 ? inv_keep : p.scale;     // dV = (drop(P))^T dO carries the 1/(1-p) of the kept entries
-      uint32_t v[HD / 2];
-      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 32, v);
-      else                    tmem_ld_32x16(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * 16, v);
+      uint32_t v[kDCols];
+      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * kDCols, v);
+      else                    tmem_ld_32x16(tmem_base + lane_base + (which == 0 ? kColDV : kColDK) + wg * kDCols, v);
       tmem_ld_wait();
       if (key_ok) {
 #pragma unroll
-        for (int t = 0; t < HD / 2; t += 8) {
+        for (int t = 0; t < kDCols; t += 8) {
           uint4 u;
           u.x = pack_bf16(__uint_as_float(v[t]) * mul, __uint_as_float(v[t + 1]) * mul);
           u.y = pack_bf16(__uint_as_float(v[t + 2]) * mul, __uint_as_float(v[t + 3]) * mul);
@@ -424,7 +534,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -501,7 +611,7 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   }
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int rc;
-  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, HD / 2, kBT, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, HD / kBwdWGs, kBT, swz))) return rc;
   if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kBT, swz))) return rc;
   if ((rc = make_tmap_2d(&tmDO, a->d_o, 2, (uint64_t)a->batch * a->nq, width, a->lddo, HD, kBT, swz))) return rc;
   if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kBT, swz))) return rc;

@@ -75,23 +75,6 @@ __device__ __forceinline__ float softmax_rowmax(uint32_t tS, int tail) {
   return fmaxf(a0, a1);
 }
 
-// 2^a for a pair of arguments on the FMA/ALU pipes instead of MUFU (the exp unit, 16/clk/SM, is the bound of this kernel
-// at head_dim <= 64): round-to-nearest split a = n + f via the 1.5*2^23 magic constant, degree-3 minimax polynomial of
-// 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), then n is added into the exponent
-// field.  a <= ~8 by construction (stale maxima are bounded by the lazy-rescale threshold); a is clamped at -125.
-__device__ __forceinline__ float2 ex2_poly2(float2 a) {
-  a.x = fmaxf(a.x, -125.f);
-  a.y = fmaxf(a.y, -125.f);
-  const float2 t = __fadd2_rn(a, make_float2(12582912.f, 12582912.f));
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), a);
-  float2 p = __ffma2_rn(f, make_float2(0.05517132207751274f, 0.05517132207751274f), make_float2(0.24261054396629333f, 0.24261054396629333f));
-  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
-  p = __ffma2_rn(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
-}
-
 // rowkey/col0/thr: dropout on P (DROP): the row sum uses the undropped probabilities (softmax normalisation comes
 // before nn.Dropout in the reference), the P that feeds P V has the dropped entries zeroed; 1/(1-p) is applied to O.
 // EMU of every 16 element pairs take the polynomial path (spread evenly so MUFU and FMA work interleave).
@@ -176,7 +159,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(&bar[BAR_SF + x], 1);
-      mbar_init(&bar[BAR_PF + x], 128);
+      mbar_init(&bar[BAR_PF + x], 4);      // one arrival per softmax warp
       mbar_init(&bar[BAR_OD + x], 1);
     }
     fence_barrier_init();
@@ -315,7 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   : softmax_exp<false, DROP, EMU % 100, TURNS>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&bar[BAR_PF + x]);
+      mbar_arrive_warp(&bar[BAR_PF + x]);
     }
 
     // ---- epilogue: O / l -> bf16 -> global, logsumexp

@@ -55,6 +55,13 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival for the whole (converged) warp: every lane's earlier writes / tcgen05 operations are ordered before the
+// arrival by the warp barrier.  Per-thread arrivals on one mbarrier serialise in the shared-memory atomic unit -- 512 of
+// them cost several hundred clocks per synchronisation point (profiles/r01_attn_bwd_timeline_d64_v4a.log).
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31u) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
@@ -246,6 +253,12 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : HVC_R4(v, 0), HVC_R4(v, 4)
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 #define HVC_S4(v, i) "r"(v[i]), "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3])
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -266,6 +279,23 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// byte offset of 16-byte chunk `chunk` of row `row` in a tile whose rows are ROWB bytes, swizzled the way TMA does for
+// that row size (128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B, 32 -> SWIZZLE_32B): chunk index ^= address bits [7, 7+log2(ROWB/16))
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz_offset(uint32_t row, uint32_t chunk) {
+  static_assert(ROWB == 128 || ROWB == 64 || ROWB == 32, "row bytes");
+  if (ROWB == 128) return row * 128u + ((chunk ^ (row & 7u)) << 4);
+  if (ROWB == 64) return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4);
+  return row * 32u + ((chunk ^ ((row >> 2) & 1u)) << 4);
+}
+
+// Register re-partitioning between warpgroups (all four warps of a warpgroup execute the same instruction): the block is
+// launched with a uniform budget; producer / MMA warps give registers back, the elementwise warpgroups take them.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ------------------------------------------------------------------ named barriers
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -278,6 +308,9 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
 __device__ __forceinline__ void sts_u4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -329,6 +362,23 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
+// 2^a for a pair of arguments on the FMA/ALU pipes instead of MUFU (the exp unit runs 16/clk/SM, the bound of the
+// attention kernels' softmax stages at head_dim <= 64): round-to-nearest split a = n + f via the 1.5*2^23 magic constant, degree-3 minimax polynomial of
+// 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far below the bf16 rounding of P), then n is added into the exponent
+// field.  a <= ~8 by construction (stale maxima are bounded by the lazy-rescale threshold); a is clamped at -125.
+__device__ __forceinline__ float2 ex2_poly2(float2 a) {
+  a.x = fmaxf(a.x, -125.f);
+  a.y = fmaxf(a.y, -125.f);
+  const float2 t = __fadd2_rn(a, make_float2(12582912.f, 12582912.f));
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), a);
+  float2 p = __ffma2_rn(f, make_float2(0.05517132207751274f, 0.05517132207751274f), make_float2(0.24261054396629333f, 0.24261054396629333f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -43,7 +43,7 @@ void count_launch(int n = 1);
   } while (0)
 
 // ---- TMA descriptors.  2-D row-major tensor [rows, cols] of `elem_bytes` elements with leading
-// dimension `ld` (elements); box = box_cols x box_rows; swizzle: 0 none, 1 (true) 128-byte, 2 64-byte.
+// dimension `ld` (elements); box = box_cols x box_rows; swizzle: 0 none, 1 (true) 128-byte, 2 64-byte, 3 32-byte.
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_cols, uint32_t box_rows, int swizzle);
 

@@ -19,19 +19,18 @@ o, lse = K.attn_fwd(q, k, v, B, H, N, N, d, d ** -0.5)
 for _ in range(2):
     K.attn_bwd(q, k, v, o, lse, d_o, B, H, N, N, d, d ** -0.5, dq, dk, dv)
 torch.cuda.synchronize()
-IT, PTS = 8, 12
-buf = (C.c_ulonglong * (3 * IT * PTS))()
+IT, PTS, ROLES = 8, 12, 3
+buf = (C.c_ulonglong * (ROLES * IT * PTS))()
 rc = _lib.lib().hvc_debug_bwd_trace(buf)
 assert rc == 0, rc
-t = [[[buf[(r * IT + i) * PTS + p] for p in range(PTS)] for i in range(IT)] for r in range(3)]
+t = [[[buf[(r * IT + i) * PTS + p] for p in range(PTS)] for i in range(IT)] for r in range(ROLES)]
 t0 = min(x for r in t for it in r for x in it if x)
 names = {0: "wg0", 1: "wg1", 2: "mma"}
-el = ["wait_ST", "S_ready", "S_loaded", "A_done", "PT_arrived", "drained", "DPT_ready", "dP_loaded", "B_done", "DS_arrived",
-      "(drain)DQF_ready", "(drain)dQ_loaded"]
-mm = ["iter_start", "STFREE+QF_ok", "ST_issued", "PT_ready", "dV_issued", "DS_ready", "dPT_dK_issued", "DQFREE_ok", "dQ_issued"]
-for r in range(3):
+el = ["iter_top", "S_loaded", "turn_start", "A_done", "PT_arrived", "dP_loaded", "B_done", "DS_arrived", "(drain)DQF_ready", "drained"]
+mm = ["iter_start", "ST0_issued", "(tail i-1)DS1_ready", "(tail i-1)dQ_issued", "PT0_ready", "ST1_issued", "DS0_ready", "PT1_ready"]
+for r in range(ROLES):
     print(f"--- {names[r]}  ({', '.join(mm if r == 2 else el)})")
     for i in range(IT):
-        n = 9 if r == 2 else 12
-        print(f" it{i}: " + " ".join(f"{t[r][i][p] - t0:7d}" for p in range(n)))
-print("per-iteration period (wg0 S_ready):", [t[0][i + 1][1] - t[0][i][1] for i in range(IT - 1)])
+        n = 8 if r == 2 else 10
+        print(f" it{i}: " + " ".join(f"{max(t[r][i][p] - t0, 0):7d}" for p in range(n)))
+print("per-iteration period (wg0 iter_top):", [t[0][i + 1][0] - t[0][i][0] for i in range(IT - 1)])
