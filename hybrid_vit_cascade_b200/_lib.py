@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libhvc_sm100a.so")
+LIB_PATH = os.environ.get("HVC_LIB") or os.path.join(_PKG, "libhvc_sm100a.so")     # HVC_LIB: A/B-test another build of the same ABI
 
 c_f32p = C.c_void_p
 _lib = None

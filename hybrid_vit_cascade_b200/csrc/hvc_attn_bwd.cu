@@ -44,7 +44,11 @@ constexpr int kWgCols = kBT / kBwdWGs;            // query columns per warpgroup
 #ifndef HVC_BWD_LSE_PRE
 #define HVC_BWD_LSE_PRE 2
 #endif
-constexpr int kLsePre = HVC_BWD_LSE_PRE;          // lse float4 loads issued ahead of their arithmetic in phase A (phase B preloads 8)
+constexpr int kLsePre = HVC_BWD_LSE_PRE;          // lse float4 loads issued ahead of their arithmetic in phase A
+#ifndef HVC_BWD_DELTA_PRE
+#define HVC_BWD_DELTA_PRE 4
+#endif
+constexpr int kDeltaPre = HVC_BWD_DELTA_PRE;      // delta float4 loads issued ahead of their arithmetic in phase B (even)
 #ifndef HVC_BWD_EMU
 #define HVC_BWD_EMU 0
 #endif
@@ -79,20 +83,19 @@ enum { BB_KV = 0, BB_KT = 1, BB_QF = 2, BB_QE = 5, BB_ST = 8 /*[2]*/, BB_STFREE 
 // named barriers: 1 + x = warpgroup x (drain / staging), 3 + x = warpgroup x's turn on the exp unit
 enum { NB_WG = 1, NB_TURN = 3 };
 
-// Optional in-kernel timeline (bring-up builds, -DHVC_TRACE_BWD): SM-clock stamps of CTA (0,0) at the protocol points of
-// iterations [kTraceI0, kTraceI0+8) for the two warpgroups (roles 0-1) and the MMA warp (role 2); read back with
-// hvc_debug_bwd_trace (tests/bringup/bwd_trace.py).
-#ifdef HVC_TRACE_BWD
+// In-kernel timeline: SM-clock stamps of CTA (0,0) at the protocol points of iterations [kTraceI0, kTraceI0+8) for the two
+// warpgroups (roles 0-1) and the MMA warp (role 2), written when tracing is switched on (hvc_debug_bwd_trace_enable;
+// tests/bringup/bwd_trace.py prints them).  The stamps stay compiled in: they cost a not-taken branch per protocol point,
+// and with them ptxas keeps the loop state in registers -- the same source without them spills ~120 bytes per thread in
+// the elementwise loop and runs 13 % slower (same box, B200: 713 vs 818 TFLOP/s at d=64).
 constexpr int kTraceI0 = 16, kTraceIters = 8, kTracePts = 12, kTraceRoles = 3;
 __device__ unsigned long long g_bwd_trace[kTraceRoles * kTraceIters * kTracePts];
+__device__ int g_bwd_trace_on = 0;
 #define HVC_TR(role, i, pt)                                                                                     \
   do {                                                                                                          \
-    if (blockIdx.x == 0 && blockIdx.y == 0 && (i) >= kTraceI0 && (i) < kTraceI0 + kTraceIters)                  \
+    if (trace_on && (i) >= kTraceI0 && (i) < kTraceI0 + kTraceIters)                                            \
       g_bwd_trace[((role) * kTraceIters + ((i) - kTraceI0)) * kTracePts + (pt)] = clock64();                    \
   } while (0)
-#else
-#define HVC_TR(role, i, pt) do {} while (0)
-#endif
 
 // ---- elementwise phases of one (key tile, query tile) pair; thread == key row, 32 query columns per thread.
 // FULL = no padding rows/columns in this pair (the masked variant is a separate code path: selects cost issue slots).
@@ -150,12 +153,12 @@ __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[kWgCols], uint3
   const float2 neg1 = make_float2(-1.f, -1.f);
   const float2 rp2 = make_float2(inv_keep, inv_keep);
 #pragma unroll
-  for (int g = 0; g < kWgCols; g += 32) {
-    float4 dq4[8];                          // delta of a 32-column group, loaded ahead of the arithmetic (see phase A)
+  for (int g = 0; g < kWgCols; g += 4 * kDeltaPre) {
+    float4 dq4[kDeltaPre];                  // delta of a column group, loaded ahead of the arithmetic (see phase A)
 #pragma unroll
-    for (int u = 0; u < 8; ++u) dq4[u] = lds_f4(delta_saddr + (g + 4 * u) * 4);
+    for (int u = 0; u < kDeltaPre; ++u) dq4[u] = lds_f4(delta_saddr + (g + 4 * u) * 4);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < kDeltaPre / 2; ++kk) {
       const int k = (g >> 3) + kk;
       uint32_t w4[4];
 #pragma unroll
@@ -211,6 +214,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int j = blockIdx.x;           // key tile
   const int nQ = p.n_q_tiles;
+  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && *reinterpret_cast<volatile int*>(&g_bwd_trace_on) != 0;
   constexpr int kTmaWarp = kBwdWGs * 4, kMmaWarp = kBwdWGs * 4 + 1;
   constexpr uint32_t kEw = kBwdWGs * 4;     // elementwise warps: one mbarrier arrival per warp on the joint barriers
 
@@ -642,11 +646,13 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
 }
 }  // namespace hvc
 
-#ifdef HVC_TRACE_BWD
+// bring-up hooks (not part of include/hvc.h): switch the in-kernel timeline of attn_bwd_kernel on/off, read it back
+extern "C" int hvc_debug_bwd_trace_enable(int on) {
+  return (int)cudaMemcpyToSymbol(hvc::g_bwd_trace_on, &on, sizeof(int));
+}
 extern "C" int hvc_debug_bwd_trace(unsigned long long* dst) {
   return (int)cudaMemcpyFromSymbol(dst, hvc::g_bwd_trace, sizeof(hvc::g_bwd_trace));
 }
-#endif
 
 extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   using namespace hvc;

@@ -10,6 +10,10 @@
 //   warp  9     MMA issuer          : S = Q K^T (SS, 128x128xd), O += P V (TS: P from TMEM, V MN-major)
 // While one warpgroup runs exp2 on tile j the tensor core computes S for the other one, so the MUFU
 // pipe (the real bound at d<=64: 16 ex2/clk/SM vs 4*d flop per score) stays busy.
+// Part of the exp2 work (kEmu pairs of every 16) runs as a degree-3 polynomial on the FMA pipe (ex2_poly2): +6 % at d=64,
+// +8 % at d=32 (profiles/r01_attn_fwd_exp2_poly_sweep.log).  Tried and rejected on B200, both slower: no turn-taking
+// (633 vs 765 TFLOP/s) and two warpgroups per query tile splitting the key columns (760 vs 812): per tile the chain
+// exp -> P V -> S(next) -> row max leaves ~1300 clk outside the exp section, so shorter turns do not shorten the period.
 // O is rescaled lazily: only when a row maximum grows by more than 2^8 (then the owning warp fixes O
 // in TMEM); otherwise stale maxima are carried and cancel in the final 1/l normalisation.
 //
@@ -17,7 +21,6 @@
 // O is written token-major [T, h*d] ready for the output projection -- no head split/merge copies.
 #include "hvc_common.cuh"
 #include "hvc_host.h"
-#include <stdlib.h>
 
 namespace hvc {
 
@@ -104,14 +107,14 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
 
 // P = exp2(S*scale2 - m): chunk c+1 is fetched from TMEM while chunk c is exponentiated.  The section between the
 // named-barrier sync and arrive is the warpgroup's turn on the MUFU pipe.
-template <bool MASKED, bool DROP, int EMU, bool TURNS>
+template <bool MASKED, bool DROP, int EMU>
 __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2, float m, int turn_bar, int next_bar, bool hand_over,
                                              uint32_t rowkey, uint32_t col0, uint32_t thr) {
   const float2 scale2v = make_float2(scale2, scale2), neg_m = make_float2(-m, -m);
   float2 sum = make_float2(0.f, 0.f);
   uint32_t bufa[32], bufb[32];
   tmem_ld_32x32(tS, bufa);
-  if (TURNS) named_bar_sync(turn_bar, 256);
+  named_bar_sync(turn_bar, 256);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 32, bufb);
   softmax_exp_chunk<MASKED, DROP, EMU>(bufa, tS, 0, tail, scale2v, neg_m, sum, rowkey, col0, thr);
@@ -123,7 +126,7 @@ __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2
   softmax_exp_chunk<MASKED, DROP, EMU>(bufa, tS, 64, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   tmem_ld_wait();
   softmax_exp_chunk<MASKED, DROP, EMU>(bufb, tS, 96, tail, scale2v, neg_m, sum, rowkey, col0, thr);
-  if (TURNS && hand_over) named_bar_arrive(next_bar, 256);
+  if (hand_over) named_bar_arrive(next_bar, 256);
   return sum.x + sum.y;
 }
 
@@ -260,8 +263,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     // The two warpgroups take turns in the MUFU-bound exp section (named barriers 1 and 2): while one runs
     // exp2 the other waits for its next S tile, loads it and finds the row maximum.
-    constexpr bool TURNS = EMU < 100;
-    if (TURNS && x == 1) named_bar_arrive(1, 256);    // warpgroup A goes first
+    if (x == 1) named_bar_arrive(1, 256);             // warpgroup A goes first
 
     for (int j = 0; j < n_tiles; ++j) {
       const bool masked = (j == n_tiles - 1) && (tail < kKTile);
@@ -294,8 +296,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       // ---- pass 2 (my turn on the MUFU pipe): P = exp2(S*scale2 - m) -> TMEM, row sum
       const bool hand_over = !(x == 1 && j == n_tiles - 1);
-      l += masked ? softmax_exp<true, DROP, EMU % 100, TURNS>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr)
-                  : softmax_exp<false, DROP, EMU % 100, TURNS>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
+      l += masked ? softmax_exp<true, DROP, EMU>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr)
+                  : softmax_exp<false, DROP, EMU>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_warp(&bar[BAR_PF + x]);
@@ -417,27 +419,7 @@ extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool drop = a->drop.seed != nullptr && a->drop.p > 0.f;
   HVC_CHECK_ARG(!drop || a->drop.p < 1.f, "hvc_attn_fwd: dropout p must be < 1");
-  int rc;
-#ifdef HVC_TUNE_FWD_EMU   // bring-up builds: pick the polynomial share at run time (pairs out of 16)
-  static const int emu = getenv("HVC_FWD_EMU") ? atoi(getenv("HVC_FWD_EMU")) : -1;
-  if (!drop && emu >= 0) {
-    switch (emu) {
-      case 0: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 0>(a, st) : launch_attn_fwd<32, false, 0>(a, st); break;
-      case 4: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 4>(a, st) : launch_attn_fwd<32, false, 4>(a, st); break;
-      case 5: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 5>(a, st) : launch_attn_fwd<32, false, 5>(a, st); break;
-      case 6: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 6>(a, st) : launch_attn_fwd<32, false, 6>(a, st); break;
-      case 7: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 7>(a, st) : launch_attn_fwd<32, false, 7>(a, st); break;
-      case 8: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 8>(a, st) : launch_attn_fwd<32, false, 8>(a, st); break;
-      case 100: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 100>(a, st) : launch_attn_fwd<32, false, 100>(a, st); break;
-      case 104: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 104>(a, st) : launch_attn_fwd<32, false, 104>(a, st); break;
-      case 106: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 106>(a, st) : launch_attn_fwd<32, false, 106>(a, st); break;
-      case 108: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 108>(a, st) : launch_attn_fwd<32, false, 108>(a, st); break;
-      case 110: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 110>(a, st) : launch_attn_fwd<32, false, 110>(a, st); break;
-      default: rc = a->head_dim == 64 ? launch_attn_fwd<64, false, 3>(a, st) : launch_attn_fwd<32, false, 3>(a, st); break;
-    }
-  } else
-#endif
-  rc = a->head_dim == 64 ? (drop ? launch_attn_fwd<64, true, kEmu64>(a, st) : launch_attn_fwd<64, false, kEmu64>(a, st))
+  const int rc = a->head_dim == 64 ? (drop ? launch_attn_fwd<64, true, kEmu64>(a, st) : launch_attn_fwd<64, false, kEmu64>(a, st))
                          : (drop ? launch_attn_fwd<32, true, kEmu32>(a, st) : launch_attn_fwd<32, false, kEmu32>(a, st));
   if (rc != HVC_OK || a->probs == nullptr) return rc;
   return attn_store_probs(a, st);

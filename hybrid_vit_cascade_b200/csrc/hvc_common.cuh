@@ -347,6 +347,43 @@ __device__ __forceinline__ float ex2_neg_approx(float x) {
   asm("{\n\t.reg .f32 t;\n\tneg.ftz.f32 t, %1;\n\tex2.approx.ftz.f32 %0, t;\n\t}" : "=f"(y) : "f"(x));
   return y;
 }
+// 256-bit global accesses (one full 32-byte sector per lane): the GEMM epilogue's threads each own a row, so a warp-wide
+// store touches 32 different lines; 32-byte pieces halve the number of sector transactions of the 16-byte form.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// erf(u) and exp(-u^2) together (Abramowitz & Stegun 7.1.26, |error| <= 1.5e-7): two MUFU ops and ~10 FMA-pipe instructions,
+// about half of erff(); the bf16 GEMM epilogues evaluate GELU / GELU' for every element of the MLP hidden activation
+// with it.  (The fp32 verification path keeps erff.)
+__device__ __forceinline__ void erf_exp_fast(float u, float& erf_u, float& exp_mu2) {
+  const float a = fabsf(u);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  pl *= t;
+  exp_mu2 = ex2_approx(-1.4426950408889634f * a * a);
+  erf_u = copysignf(fmaf(-pl, exp_mu2, 1.0f), u);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e, ex;
+  erf_exp_fast(x * 0.70710678118654752f, e, ex);
+  return 0.5f * x * (1.0f + e);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x); exp(-x^2/2) is shared with the erf evaluation
+  float e, ex;
+  erf_exp_fast(x * 0.70710678118654752f, e, ex);
+  return fmaf(0.3989422804014327f * x, ex, fmaf(0.5f, e, 0.5f));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));

@@ -2,12 +2,17 @@
 //
 //   D[M,N] = alpha * sum_k A(m,k) B(n,k)         fp32 accumulation in TMEM
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0      TMA producer   : cp.async.bulk.tensor -> 128B-swizzled smem ring (5 stages x 32 KB)
 //   warp 1      MMA issuer     : one elected lane issues tcgen05.mma (128x128x16), commits to mbarriers;
 //                                owns the TMEM allocation (2 accumulator stages x 128 columns)
-//   warps 2..5  epilogue       : tcgen05.ld accumulator -> registers -> fused epilogue -> global
-// The epilogue of tile i overlaps the main loop of tile i+1 through the two TMEM stages.
+//   warps 2..9  epilogue       : tcgen05.ld accumulator -> registers -> fused epilogue -> global; two warps per TMEM
+//                                lane quarter, each taking 64 of the tile's 128 columns
+// The epilogue of tile i overlaps the main loop of tile i+1 through the two TMEM stages.  At the backbone's K = 256 a
+// tile's main loop is only ~1700 clk, so the epilogue is the bound: it is specialised per epilogue kind (template), uses
+// 32-byte global accesses (each thread owns a row), fetches residual / aux operands while the TMEM load is in flight, and
+// evaluates GELU with a 2-MUFU erf (hvc_common.cuh) -- with four epilogue warps and erff() the MLP GEMMs ran at
+// 145-216 TFLOP/s (profiles/r01_gemm_time_by_shape.log).
 //
 // Operands may be K-major (stored [rows, K]) or MN-major (stored [K, rows]); the latter is what the
 // backward GEMMs need (dgrad reads W as stored, wgrad reads dy and x as stored) so no transposed copies
@@ -24,7 +29,8 @@ constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int kStages = 5;
 constexpr int kTileBytes = BM * BK * 2;  // 16 KB, same for A and B
 constexpr int kStageBytes = 2 * kTileBytes;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;
+constexpr int kEpiWarps = 8;
 constexpr int kAccStages = 2;
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 
@@ -41,6 +47,7 @@ struct GemmKArgs {
   const bf16* aux; long long ldaux;
   float alpha;
   DropArg drop;   // fused nn.Dropout on the epilogue value (seed == nullptr: off)
+  int v256;       // every epilogue operand (out, out2, resid, aux) is 32-byte aligned with a 32-byte-multiple row pitch
 };
 
 struct WorkItem {
@@ -66,7 +73,55 @@ __device__ __forceinline__ void epilogue_dropout(const GemmKArgs& p, float (&v)[
 }
 
 // ---------------------------------------------------------------- epilogue for one 32-column chunk
-__device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_t (&acc)[32], int row, int col0) {
+// Operands that come from global memory (residual row, aux row) are fetched into `Side` before the TMEM load is waited
+// for, on the fast path (full chunk, 32-byte aligned).
+struct Side {
+  uint32_t r[32];   // residual, f32 bits              (HVC_EPI_RESIDUAL)
+  uint32_t a[16];   // aux, bf16 pairs                 (HVC_ACT_GELU_GRAD)
+};
+template <int EPI>
+__device__ __forceinline__ void side_load(const GemmKArgs& p, int row, int col0, bool fast, Side& s) {
+  if (!fast) return;
+  if (EPI == HVC_EPI_RESIDUAL) {
+    const float* r = p.resid + (long long)row * p.ldr + col0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ldg256(r + 8 * j, *reinterpret_cast<uint32_t(*)[8]>(&s.r[8 * j]));
+  }
+  if (EPI == HVC_EPI_BF16 && p.activation == HVC_ACT_GELU_GRAD) {
+    const bf16* ax = p.aux + (long long)row * p.ldaux + col0;
+    ldg256(ax, *reinterpret_cast<uint32_t(*)[8]>(&s.a[0]));
+    ldg256(ax + 16, *reinterpret_cast<uint32_t(*)[8]>(&s.a[8]));
+  }
+}
+__device__ __forceinline__ void store_bf16_row(bf16* o, const float (&v)[32], int ncols, bool fast) {
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 16) {
+      uint32_t u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = pack_bf16(v[j + 2 * k], v[j + 2 * k + 1]);
+      stg256(o + j, u);
+    }
+  } else {
+    _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = __float2bfloat16(v[j]);
+  }
+}
+__device__ __forceinline__ void store_f32_row(float* o, const float (&v)[32], int ncols, bool fast) {
+  if (fast) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint32_t u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = __float_as_uint(v[j + k]);
+      stg256(o + j, u);
+    }
+  } else {
+    _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = v[j];
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_t (&acc)[32], int row, int col0, bool fast, const Side& s) {
   if (row >= p.M || col0 >= p.N) return;
   const int ncols = min(32, p.N - col0);
   float v[32];
@@ -83,111 +138,67 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
     }
   }
-  const bool vec = (ncols == 32);
   const bool drop = p.drop.seed != nullptr;
-  if (drop && p.epilogue != HVC_EPI_BF16) epilogue_dropout(p, v, row, col0);   // residual / f32: the value before gate + residual
+  if (drop && EPI != HVC_EPI_BF16) epilogue_dropout(p, v, row, col0);   // residual / f32: the value before gate + residual
 
-  if (p.epilogue == HVC_EPI_BF16) {
-    if (p.out2 != nullptr) {
-      bf16* o2 = reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col0;
-      if (vec && (p.ldo2 & 7) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 u = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                               pack_bf16(v[j + 6], v[j + 7]));
-          *reinterpret_cast<uint4*>(o2 + j) = u;
-        }
-      } else {
-        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o2[j] = __float2bfloat16(v[j]);
-      }
-    }
+  if (EPI == HVC_EPI_BF16) {
+    if (p.out2 != nullptr) store_bf16_row(reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col0, v, ncols, fast);
     if (p.activation == HVC_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
     } else if (p.activation == HVC_ACT_GELU_GRAD) {
-      const bf16* ax = p.aux + (long long)row * p.ldaux + col0;
-      if (vec && (p.ldaux & 7) == 0) {
+      if (fast) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const uint4 u = __ldg(reinterpret_cast<const uint4*>(ax + j));
-          const float2 a0 = unpack_bf16(u.x), a1 = unpack_bf16(u.y), a2 = unpack_bf16(u.z), a3 = unpack_bf16(u.w);
-          v[j] *= gelu_erf_grad(a0.x); v[j + 1] *= gelu_erf_grad(a0.y);
-          v[j + 2] *= gelu_erf_grad(a1.x); v[j + 3] *= gelu_erf_grad(a1.y);
-          v[j + 4] *= gelu_erf_grad(a2.x); v[j + 5] *= gelu_erf_grad(a2.y);
-          v[j + 6] *= gelu_erf_grad(a3.x); v[j + 7] *= gelu_erf_grad(a3.y);
+        for (int j = 0; j < 16; ++j) {
+          const float2 a = unpack_bf16(s.a[j]);
+          v[2 * j] *= gelu_grad_fast(a.x);
+          v[2 * j + 1] *= gelu_grad_fast(a.y);
         }
       } else {
-        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) v[j] *= gelu_erf_grad(__bfloat162float(ax[j]));
+        const bf16* ax = p.aux + (long long)row * p.ldaux + col0;
+        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) v[j] *= gelu_grad_fast(__bfloat162float(ax[j]));
       }
     }
     if (drop) epilogue_dropout(p, v, row, col0);   // after the activation (mlp: Linear -> GELU -> Dropout); out2 stays pre-activation
-    bf16* o = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0;
-    if (vec && (p.ldo & 7) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 u = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                             pack_bf16(v[j + 6], v[j + 7]));
-        *reinterpret_cast<uint4*>(o + j) = u;
-      }
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = __float2bfloat16(v[j]);
-    }
-  } else if (p.epilogue == HVC_EPI_RESIDUAL) {
-    if (p.out2 != nullptr) {
-      bf16* o2 = reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col0;
-      if (vec && (p.ldo2 & 7) == 0) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 u = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                               pack_bf16(v[j + 6], v[j + 7]));
-          *reinterpret_cast<uint4*>(o2 + j) = u;
-        }
-      } else {
-        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o2[j] = __float2bfloat16(v[j]);
-      }
-    }
-    const float* r = p.resid + (long long)row * p.ldr + col0;
+    store_bf16_row(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0, v, ncols, fast);
+  } else if (EPI == HVC_EPI_RESIDUAL) {
+    if (p.out2 != nullptr) store_bf16_row(reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col0, v, ncols, fast);
     float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
     const float* g = p.gate ? p.gate + (long long)(row / p.rows_per_batch) * p.gate_ld + col0 : nullptr;
-    if (vec && (p.ldr & 3) == 0 && (p.ldo & 3) == 0 && (g == nullptr || (p.gate_ld & 3) == 0)) {
+    if (fast && (g == nullptr || (p.gate_ld & 3) == 0)) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        const float4 rr = __ldg(reinterpret_cast<const float4*>(r + j));
         float4 gg = make_float4(1.f, 1.f, 1.f, 1.f);
         if (g) gg = __ldg(reinterpret_cast<const float4*>(g + j));
-        float4 oo;
-        oo.x = fmaf(gg.x, v[j], rr.x); oo.y = fmaf(gg.y, v[j + 1], rr.y);
-        oo.z = fmaf(gg.z, v[j + 2], rr.z); oo.w = fmaf(gg.w, v[j + 3], rr.w);
-        *reinterpret_cast<float4*>(o + j) = oo;
+        v[j] = fmaf(gg.x, v[j], __uint_as_float(s.r[j]));
+        v[j + 1] = fmaf(gg.y, v[j + 1], __uint_as_float(s.r[j + 1]));
+        v[j + 2] = fmaf(gg.z, v[j + 2], __uint_as_float(s.r[j + 2]));
+        v[j + 3] = fmaf(gg.w, v[j + 3], __uint_as_float(s.r[j + 3]));
       }
+      store_f32_row(o, v, ncols, true);
     } else {
+      const float* r = p.resid + (long long)row * p.ldr + col0;
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = fmaf(g ? g[j] : 1.f, v[j], r[j]);
     }
-  } else if (p.epilogue == HVC_EPI_F32_ATOMIC) {
+  } else if (EPI == HVC_EPI_F32_ATOMIC) {
     float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
-    if (vec && (p.ldo & 3) == 0) {
+    if (ncols == 32 && (p.ldo & 3) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) atomicAdd(reinterpret_cast<float4*>(o + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
     } else {
       _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) atomicAdd(o + j, v[j]);
     }
   } else {  // HVC_EPI_F32
-    if (p.activation == HVC_ACT_GELU) {   // fp32 verification mode: the MLP hidden activation stays fp32
+    if (p.activation == HVC_ACT_GELU) {   // (kept exact: this epilogue also serves verification-style callers)
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
     }
-    float* o = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0;
-    if (vec && (p.ldo & 3) == 0) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (j < ncols) o[j] = v[j];
-    }
+    store_f32_row(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0, v, ncols, fast);
   }
 }
 
 // ---------------------------------------------------------------- kernel
-template <int A_MAJOR, int B_MAJOR>
+template <int A_MAJOR, int B_MAJOR, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmKArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -211,7 +222,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < kAccStages; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -281,8 +292,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // which 64 of the tile's 128 columns
     uint32_t acc = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
@@ -290,13 +302,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const int row = it.m0 + quarter * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * 64;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = it.n0 + half * 64 + c * 32;
+        const bool fast = p.v256 && row < p.M && col0 + 32 <= p.N;
         uint32_t v[32];
+        Side side;
         tmem_ld_32x32(taddr + c * 32, v);
+        side_load<EPI>(p, row, col0, fast, side);
         tmem_ld_wait();
-        epilogue_chunk(p, v, row, it.n0 + c * 32);
+        epilogue_chunk<EPI>(p, v, row, col0, fast, side);
       }
       tc_fence_before();
       __syncwarp();
@@ -313,16 +329,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int A_MAJOR, int B_MAJOR>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKArgs& ka, int grid, cudaStream_t st) {
+template <int A_MAJOR, int B_MAJOR, int EPI>
+static int launch_gemm_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKArgs& ka, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MAJOR, B_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    HVC_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MAJOR, B_MAJOR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     configured = true;
   }
-  gemm_bf16_kernel<A_MAJOR, B_MAJOR><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, ka);
+  gemm_bf16_kernel<A_MAJOR, B_MAJOR, EPI><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, ka);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
+}
+template <int A_MAJOR, int B_MAJOR>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKArgs& ka, int grid, cudaStream_t st) {
+  switch (ka.epilogue) {
+    case HVC_EPI_BF16: return launch_gemm_epi<A_MAJOR, B_MAJOR, HVC_EPI_BF16>(tmA, tmB, ka, grid, st);
+    case HVC_EPI_RESIDUAL: return launch_gemm_epi<A_MAJOR, B_MAJOR, HVC_EPI_RESIDUAL>(tmA, tmB, ka, grid, st);
+    case HVC_EPI_F32_ATOMIC: return launch_gemm_epi<A_MAJOR, B_MAJOR, HVC_EPI_F32_ATOMIC>(tmA, tmB, ka, grid, st);
+    default: return launch_gemm_epi<A_MAJOR, B_MAJOR, HVC_EPI_F32>(tmA, tmB, ka, grid, st);
+  }
 }
 
 }  // namespace hvc
@@ -364,6 +389,13 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   ka.aux = reinterpret_cast<const bf16*>(a->aux); ka.ldaux = a->ldaux;
   ka.alpha = a->alpha;
   ka.drop = make_drop(a->drop);
+  {
+    auto ok32 = [](const void* ptr, long long ld, int esz) {
+      return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31u) == 0 && ((ld * esz) & 31) == 0);
+    };
+    const int out_esz = a->epilogue == HVC_EPI_BF16 ? 2 : 4;
+    ka.v256 = ok32(a->out, a->ldo, out_esz) && ok32(a->out2, a->ldo2, 2) && ok32(a->resid, a->ldr, 4) && ok32(a->aux, a->ldaux, 2);
+  }
   HVC_CHECK_ARG(ka.drop.seed == nullptr || (a->epilogue != HVC_EPI_F32_ATOMIC && a->drop.p < 1.f), "hvc_gemm: dropout needs p < 1 and a non-atomic epilogue");
 
   const long long num_work = (long long)ka.m_blocks * ka.n_blocks * ka.k_splits;

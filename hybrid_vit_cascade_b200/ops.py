@@ -7,6 +7,8 @@ accumulation; LayerNorm / GroupNorm statistics, softmax statistics, gates and re
 Gradient layouts are what ``nn.Linear`` expects ((out, in) weights) so optimizers, clipping and
 checkpoints are untouched.  Nothing here falls back to torch math: torch only allocates.
 """
+import weakref
+
 import torch
 from torch.autograd import Function
 
@@ -26,14 +28,28 @@ def _sms(dev):
 _W16 = {}
 
 
+def _cache_get(cache, p, pad_to):
+    """Entry of a per-parameter cache if it still describes `p`: same object (ids are reused after garbage collection,
+    so the entry holds a weak reference), same in-place version, same storage and shape."""
+    ent = cache.get((id(p), pad_to))
+    if ent is not None and ent[0]() is p and ent[1] == p._version and ent[2] == p.data_ptr() and ent[4] == tuple(p.shape):
+        return ent[3]
+    return None
+
+
+def _cache_put(cache, p, pad_to, t):
+    if len(cache) > 256:      # drop entries of parameters that no longer exist
+        for k in [k for k, e in cache.items() if e[0]() is None]:
+            del cache[k]
+    cache[(id(p), pad_to)] = (weakref.ref(p), p._version, p.data_ptr(), t, tuple(p.shape))
+
+
 def w16(p, pad_to=None):
     """bf16 copy of an fp32 parameter viewed [out, in] (zero-padded along `in` to pad_to), cached until
     the parameter is modified in place (optimizer step) or replaced (load_state_dict)."""
-    key = (id(p), pad_to)
-    ver = p._version
-    ent = _W16.get(key)
-    if ent is not None and ent[0] == ver and ent[1] == p.data_ptr() and ent[3] == tuple(p.shape):
-        return ent[2]
+    t = _cache_get(_W16, p, pad_to)
+    if t is not None:
+        return t
     src = p.detach()
     if src.dtype != torch.float32:
         src = src.float()
@@ -43,7 +59,7 @@ def w16(p, pad_to=None):
         padded[:, :src.shape[1]] = src
         src = padded
     t = K.cast_bf16(src)
-    _W16[key] = (ver, p.data_ptr(), t, tuple(p.shape))
+    _cache_put(_W16, p, pad_to, t)
     return t
 
 

@@ -10,6 +10,7 @@ Attention materialises the scores per (batch, head).  Forward only (no autograd 
 import torch
 
 from . import kernels as K
+from .ops import _cache_get, _cache_put
 
 A_SIDE, B_SIDE = 0, 1
 _W6 = {}
@@ -17,17 +18,16 @@ _W6 = {}
 
 def w6(p, pad_to=None):
     """Six-term B-side operand [out, 6*in] of an fp32 parameter viewed [out, in]; cached like ops.w16."""
-    key = (id(p), pad_to)
-    ent = _W6.get(key)
-    if ent is not None and ent[0] == p._version and ent[1] == p.data_ptr() and ent[3] == tuple(p.shape):
-        return ent[2]
+    t = _cache_get(_W6, p, pad_to)
+    if t is not None:
+        return t
     src = p.detach().float().reshape(p.shape[0], -1).contiguous()
     if pad_to is not None and pad_to != src.shape[1]:
         padded = torch.zeros(src.shape[0], pad_to, device=src.device, dtype=torch.float32)
         padded[:, :src.shape[1]] = src
         src = padded
     t = K.split3(src, B_SIDE)
-    _W6[key] = (p._version, p.data_ptr(), t, tuple(p.shape))
+    _cache_put(_W6, p, pad_to, t)
     return t
 
 

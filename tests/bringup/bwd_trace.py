@@ -1,4 +1,4 @@
-"""In-kernel timeline of attn_bwd_kernel (library built with -DHVC_TRACE_BWD): prints, for 8 steady-state iterations of
+"""In-kernel timeline of attn_bwd_kernel (switched on through hvc_debug_bwd_trace_enable): prints, for 8 steady-state iterations of
 CTA (0,0), the SM-clock offsets of the protocol points of warpgroup 0, warpgroup 1 and the MMA warp."""
 import ctypes as C
 import os
@@ -16,6 +16,7 @@ g = torch.Generator(device="cuda").manual_seed(3)
 q, k, v, d_o = (torch.randn(B * N, Cc, device="cuda", generator=g).bfloat16() for _ in range(4))
 dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
 o, lse = K.attn_fwd(q, k, v, B, H, N, N, d, d ** -0.5)
+assert _lib.lib().hvc_debug_bwd_trace_enable(1) == 0
 for _ in range(2):
     K.attn_bwd(q, k, v, o, lse, d_o, B, H, N, N, d, d ** -0.5, dq, dk, dv)
 torch.cuda.synchronize()

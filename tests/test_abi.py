@@ -85,3 +85,28 @@ def test_same_seed_same_init_as_reference_fixture():
         else:
             assert torch.equal(v, c["sd"][k]), k
     m.load_state_dict(c["sd"], strict=True)
+
+
+def test_weight_cache_is_not_fooled_by_id_reuse():
+    """The bf16 / six-term weight caches are keyed by id(parameter); CPython reuses ids (and the allocator reuses
+    addresses) once a model is garbage collected, so an entry must also prove it belongs to the live object."""
+    import weakref
+
+    import torch
+
+    from hybrid_vit_cascade_b200 import ops
+    cache = {}
+    p = torch.nn.Parameter(torch.zeros(4, 4))
+    ops._cache_put(cache, p, None, "A")
+    assert ops._cache_get(cache, p, None) == "A"
+    q = torch.nn.Parameter(torch.zeros(4, 4))
+
+    class Dead:
+        pass
+
+    # what a collected parameter leaves behind when its id, version, address and shape all coincide with q's
+    cache[(id(q), None)] = (weakref.ref(Dead()), q._version, q.data_ptr(), "stale", tuple(q.shape))
+    assert ops._cache_get(cache, q, None) is None
+    with torch.no_grad():
+        p.add_(1)
+    assert ops._cache_get(cache, p, None) is None       # an in-place update (optimizer step) invalidates the entry
