@@ -544,31 +544,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
-// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]; one warp per (token, head): 2 elements per lane (HD 64) or 1 (HD 32)
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]: HD/8 lanes per (token, head), 16 bytes of O and dO each (a token's heads
+// are contiguous, so a warp reads whole 128-byte lines), shuffle-reduced; also writes -lse2 and the dropout row keys.
 template <int HD>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ d_o,
                                                          long long lddo, const float* __restrict__ lse2, float* __restrict__ delta,
                                                          float* __restrict__ nlse2, int batch, int heads, int nq, int nq_pad,
                                                          uint32_t* __restrict__ rowkeys, const DropArg drop) {
-  const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  constexpr int kLanes = HD / 8;                          // lanes per (token, head): 8 or 4
+  const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long item = gid / kLanes;                    // (token, head) index, head fastest
+  const int part = (int)(gid - item * kLanes);
   const long long total = (long long)batch * nq * heads;
-  if (gw >= total) return;
-  const int h = (int)(gw % heads);
-  const long long tok = gw / heads;
-  const int b = (int)(tok / nq), q = (int)(tok - (long long)b * nq);
-  float part;
-  if constexpr (HD == 64) {
-    const float2 a = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(o + tok * ldo + h * 64 + 2 * lane)));
-    const float2 g = unpack_bf16(__ldg(reinterpret_cast<const uint32_t*>(d_o + tok * lddo + h * 64 + 2 * lane)));
-    part = a.x * g.x + a.y * g.y;
-  } else {
-    part = __bfloat162float(o[tok * ldo + h * 32 + lane]) * __bfloat162float(d_o[tok * lddo + h * 32 + lane]);
-  }
-  const float s = warp_sum(part);
-  if (lane == 0) {
+  const bool live = item < total;
+  const long long it = live ? item : total - 1;           // keep the whole warp in the shuffles
+  const int h = (int)(it % heads);
+  const long long tok = it / heads;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + tok * ldo + h * HD + part * 8));
+  const uint4 g = __ldg(reinterpret_cast<const uint4*>(d_o + tok * lddo + h * HD + part * 8));
+  const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+  const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+  float sum = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y + a2.x * g2.x + a2.y * g2.y + a3.x * g3.x + a3.y * g3.y;
+#pragma unroll
+  for (int off = kLanes / 2; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if (live && part == 0) {
+    const int b = (int)(tok / nq), q = (int)(tok - (long long)b * nq);
     const long long idx = ((long long)b * heads + h) * nq_pad + q;
-    delta[idx] = s;
+    delta[idx] = sum;
     nlse2[idx] = -lse2[idx];
     if (drop.seed != nullptr) rowkeys[idx] = drop_rowkey(drop_load(drop), static_cast<uint32_t>((b * heads + h) * nq + q));
   }
@@ -606,8 +608,8 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   const long long plane = (long long)a->batch * a->heads * nq_pad;
   const DropArg drop = make_drop(a->drop);
   {
-    const long long warps = (long long)a->batch * a->nq * a->heads;
-    attn_delta_kernel<HD><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->ldo,
+    const long long threads = (long long)a->batch * a->nq * a->heads * (HD / 8);
+    attn_delta_kernel<HD><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(a->o), a->ldo,
                                                                       reinterpret_cast<const bf16*>(a->d_o), a->lddo, a->lse, a->delta,
                                                                       a->delta + plane, a->batch, a->heads, a->nq, nq_pad,
                                                                       reinterpret_cast<uint32_t*>(a->delta + 2 * plane), drop);
@@ -662,6 +664,8 @@ extern "C" int hvc_attn_bwd(const hvc_attn_args* a, void* stream) {
   HVC_CHECK_ARG(a->q && a->k && a->v && a->o && a->d_o && a->lse && a->delta && a->dq_accum && a->dq && a->dk && a->dv,
                 "hvc_attn_bwd: null operand");
   HVC_CHECK_ARG(((a->lddq | a->lddk | a->lddv) & 7) == 0, "hvc_attn_bwd: gradient row pitches must be multiples of 8");
+  HVC_CHECK_ARG(((a->ldo | a->lddo) & 7) == 0 && ((reinterpret_cast<uintptr_t>(a->o) | reinterpret_cast<uintptr_t>(a->d_o)) & 15) == 0,
+                "hvc_attn_bwd: o and d_o must have 16-byte aligned rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool drop = a->drop.seed != nullptr && a->drop.p > 0.f;
   HVC_CHECK_ARG(!drop || a->drop.p < 1.f, "hvc_attn_bwd: dropout p must be < 1");
