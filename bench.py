@@ -46,6 +46,13 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE self-attention backward launch per sample at 32768
+# tokens, from the `ncu --set full` capture profiles/r01_ncu_full_hot_kernels_b1.csv (one sample, C = 256): head_dim -> bytes.
+# A launch over B samples moves B times that (each (batch, head) slice is touched by its own CTAs only).  The algorithmic
+# bytes are Q, K, V, dO, O reads + dK, dV writes + the fp32 dQ reduction = 8 * N * C * 2 + N * C * 4 = 151 MB per sample.
+NCU_ATTN_BWD_DRAM_BYTES_PER_SAMPLE_32K = {64: 129.0e6, 32: 141.4e6}
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -290,7 +297,10 @@ def run_b200(args, w):
         ach = sum(f for _, f in big) / (sum(t for t, _ in big) * 1e9)
         roof = {"kernel": f"attn_bwd_kernel<{w['voxel_dim'] // w['heads']}> (self-attention; call also includes the delta and dq-convert passes)",
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "peak_source": peak_src, "launches": len(big), "ms_per_launch": sum(t for t, _ in big) / len(big),
+                "traffic": (NCU_ATTN_BWD_DRAM_BYTES_PER_SAMPLE_32K.get(w["voxel_dim"] // w["heads"], 0.0) * B
+                            if oracle_cfg(w).num_tokens == 32768 and w["voxel_dim"] == 256 else None),
+                "traffic_note": "bytes per launch = ncu DRAM read+write of a one-sample launch x batch (profiles/r01_ncu_full_hot_kernels_b1.csv)",
+                "peak_source": peak_src, "launches": len(big), "ms_per_launch": sum(t for t, _ in big) / len(big),
                 "frac_of_nominal_2250": ach / 2250.0}
     line = {
         "metric": "train volumes/sec (3D ViT backbone fwd+bwd)", "value": value, "unit": "volumes/s", "n_gpus": world,
