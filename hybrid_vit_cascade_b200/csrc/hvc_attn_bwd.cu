@@ -27,6 +27,8 @@
 //      * four warpgroups of 32 columns (more warps per scheduler) were tried and lost: the per-thread fixed cost of a
 //        tile (waits, fences, address arithmetic, ~150 instructions) then weighs as much as the arithmetic
 //        (profiles/r01_attn_bwd_timeline_d64_v4a.log).
+//      * dQ goes to HBM through the TMA engine (cp.reduce.async.bulk.tensor, whole 128-byte lines): red.global.add.v4.f32
+//        straight from registers needs no staging but hits the L2 atomic rate (600 vs 794 TFLOP/s at d=64, B=8).
 //      * dQ tiles are staged for the TMA reduce in the dS^T sub-tile that the same warpgroup wrote two tiles earlier
 //        and dK/dQ have released, which is what lets three Q/dO stages and two dS^T buffers fit in shared memory.
 //      TMEM is used to the last column (S^T 128 | P^T 64 | dP^T 128 | dV d | dK d | dQ d).
