@@ -14,6 +14,11 @@
 // +8 % at d=32 (profiles/r01_attn_fwd_exp2_poly_sweep.log).  Tried and rejected on B200, both slower: no turn-taking
 // (633 vs 765 TFLOP/s) and two warpgroups per query tile splitting the key columns (760 vs 812): per tile the chain
 // exp -> P V -> S(next) -> row max leaves ~1300 clk outside the exp section, so shorter turns do not shorten the period.
+// Timeline of this version (profiles/r01_attn_fwd_timeline_d64_v2.log): period ~2830 clk per key tile pair = exp turn (~1260)
+// + the chain P -> P V -> S(next) -> row max (~1590).  Tried on top of it, all within +-2 % of this version in the training step:
+// Q^T as an MN-major A operand + P in its own TMEM columns + S(j+1) issued before P(j) V (the chain shrinks to ~1000 clk but the
+// row-max pass, now overlapping the other tile's MMAs, grows from ~420 to ~690 clk: TMEM reads slow down while TS-form MMAs run);
+// the whole S row held in registers (one TMEM read per tile; 752 vs 800 TFLOP/s).  The bound is each warpgroup's own serial work.
 // O is rescaled lazily: only when a row maximum grows by more than 2^8 (then the owning warp fixes O
 // in TMEM); otherwise stale maxima are carried and cancel in the final 1/l normalisation.
 //
@@ -48,6 +53,25 @@ struct FwdSmem {
   static constexpr int kBar = kV + kKvStages * kTile;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
+
+// In-kernel timeline (bring-up): SM-clock stamps of CTA (0,0) for iterations [kFwdTraceI0, +8) of softmax warpgroup A (role 0),
+// B (role 1) and the MMA warp (role 2); switched on with hvc_debug_fwd_trace_enable, read with hvc_debug_fwd_trace
+// (tests/bringup/fwd_trace.py).  Compiled only with -DHVC_TRACE_FWD (HVC_EXTRA_NVCC_FLAGS): unlike in the backward kernel the
+// stamps are not free here -- left in, the forward runs ~5 % slower in the training step (729 vs 770 TFLOP/s).
+#ifdef HVC_TRACE_FWD
+constexpr int kFwdTraceI0 = 16, kFwdTraceIters = 8, kFwdTracePts = 8;
+__device__ unsigned long long g_fwd_trace[3 * kFwdTraceIters * kFwdTracePts];
+__device__ int g_fwd_trace_on = 0;
+#define HVC_FTR(role, j, pt)                                                                                    \
+  do {                                                                                                          \
+    if (trace_on && (j) >= kFwdTraceI0 && (j) < kFwdTraceI0 + kFwdTraceIters)                                   \
+      g_fwd_trace[((role) * kFwdTraceIters + ((j) - kFwdTraceI0)) * kFwdTracePts + (pt)] = clock64();           \
+  } while (0)
+#define HVC_FTR_ON(expr) (expr)
+#else
+#define HVC_FTR(role, j, pt) do {} while (0)
+#define HVC_FTR_ON(expr) false
+#endif
 
 enum { BAR_Q = 0, BAR_KF = 1, BAR_KE = 4, BAR_VF = 7, BAR_VE = 10, BAR_SF = 13, BAR_PF = 15, BAR_OD = 17, BAR_N = 19 };
 
@@ -109,12 +133,13 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
 // named-barrier sync and arrive is the warpgroup's turn on the MUFU pipe.
 template <bool MASKED, bool DROP, int EMU>
 __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2, float m, int turn_bar, int next_bar, bool hand_over,
-                                             uint32_t rowkey, uint32_t col0, uint32_t thr) {
+                                             uint32_t rowkey, uint32_t col0, uint32_t thr, bool trace_on, int role, int j) {
   const float2 scale2v = make_float2(scale2, scale2), neg_m = make_float2(-m, -m);
   float2 sum = make_float2(0.f, 0.f);
   uint32_t bufa[32], bufb[32];
   tmem_ld_32x32(tS, bufa);
   named_bar_sync(turn_bar, 256);
+  HVC_FTR(role, j, 3);
   tmem_ld_wait();
   tmem_ld_32x32(tS + 32, bufb);
   softmax_exp_chunk<MASKED, DROP, EMU>(bufa, tS, 0, tail, scale2v, neg_m, sum, rowkey, col0, thr);
@@ -127,6 +152,7 @@ __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2
   tmem_ld_wait();
   softmax_exp_chunk<MASKED, DROP, EMU>(bufb, tS, 96, tail, scale2v, neg_m, sum, rowkey, col0, thr);
   if (hand_over) named_bar_arrive(next_bar, 256);
+  HVC_FTR(role, j, 4);
   return sum.x + sum.y;
 }
 
@@ -148,6 +174,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int q0 = blockIdx.x * (2 * kQTile);
   const int n_tiles = p.n_kv_tiles;
+  const bool trace_cta = HVC_FTR_ON(blockIdx.x == 0 && blockIdx.y == 0 && *reinterpret_cast<volatile int*>(&g_fwd_trace_on) != 0);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -227,11 +254,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int st1 = (j + 1) % kKvStages;
       const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
       const bool more = (j + 1 < n_tiles);
+      const bool trace_on = trace_cta && leader;
+      HVC_FTR(2, j, 0);
       mbar_wait(&bar[BAR_VF + st], ph, 22);
+      HVC_FTR(2, j, 1);
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         mbar_wait(&bar[BAR_PF + x], j & 1, 23);
         tc_fence_after();
+        HVC_FTR(2, j, 2 + 2 * x);
         issue_pv(x, st, j > 0);
         commit(BAR_OD + x);
         if (x == 1) commit(BAR_VE + st);
@@ -241,6 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           commit(BAR_SF + x);
           if (x == 1) commit(BAR_KE + st1);
         }
+        HVC_FTR(2, j, 3 + 2 * x);
       }
     }
   } else {
@@ -265,10 +297,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // exp2 the other waits for its next S tile, loads it and finds the row maximum.
     if (x == 1) named_bar_arrive(1, 256);             // warpgroup A goes first
 
+    const bool trace_on = trace_cta && (threadIdx.x & 127) == 0;
     for (int j = 0; j < n_tiles; ++j) {
       const bool masked = (j == n_tiles - 1) && (tail < kKTile);
+      HVC_FTR(x, j, 0);
       mbar_wait(&bar[BAR_SF + x], j & 1, 30);
       tc_fence_after();
+      HVC_FTR(x, j, 1);
       // ---- pass 1: row maximum (S stays in TMEM; TMEM reads are cheap)
       const float mx = masked ? softmax_rowmax<true>(tS, tail) : softmax_rowmax<false>(tS, tail);
       const float m_new = fmaxf(m, mx * scale2);
@@ -294,13 +329,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (need) { l *= f; m = m_new; }
         }
       }
+      HVC_FTR(x, j, 2);
       // ---- pass 2 (my turn on the MUFU pipe): P = exp2(S*scale2 - m) -> TMEM, row sum
       const bool hand_over = !(x == 1 && j == n_tiles - 1);
-      l += masked ? softmax_exp<true, DROP, EMU>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr)
-                  : softmax_exp<false, DROP, EMU>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr);
+      l += masked ? softmax_exp<true, DROP, EMU>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr, trace_on, x, j)
+                  : softmax_exp<false, DROP, EMU>(tS, tail, scale2, m, 1 + x, 1 + (x ^ 1), hand_over, rowkey, j * kKTile, thr, trace_on, x, j);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive_warp(&bar[BAR_PF + x]);
+      HVC_FTR(x, j, 5);
     }
 
     // ---- epilogue: O / l -> bf16 -> global, logsumexp
@@ -407,6 +444,13 @@ static int attn_store_probs(const hvc_attn_args* a, cudaStream_t st) {
   return HVC_OK;
 }
 }  // namespace hvc
+
+#ifdef HVC_TRACE_FWD   // bring-up hooks (not part of include/hvc.h)
+extern "C" int hvc_debug_fwd_trace_enable(int on) { return (int)cudaMemcpyToSymbol(hvc::g_fwd_trace_on, &on, sizeof(int)); }
+extern "C" int hvc_debug_fwd_trace(unsigned long long* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, hvc::g_fwd_trace, sizeof(hvc::g_fwd_trace));
+}
+#endif
 
 extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
   using namespace hvc;

@@ -353,3 +353,30 @@ def test_gradient_linearity_property():
     g2, = torch.autograd.grad((m(x, ctx, cond) * (2 * r)).sum(), x)
     assert O.cosine(g2, 2 * g1) > 0.9999
     assert O.max_rel(g2, 2 * g1) < 2e-2
+
+
+@pytest.mark.parametrize("d", [64, 32])
+def test_attention_lazy_rescale_path(d):
+    """The forward kernel carries stale row maxima and only rescales O when a maximum grows by more than 2^8 between key
+    tiles.  Keys whose magnitude grows tile by tile force that path on every tile; the result must still match fp32, and
+    the backward (which recomputes P from the saved log-sum-exp) must match autograd."""
+    from hybrid_vit_cascade_b200 import kernels as K
+    g = torch.Generator(device="cuda").manual_seed(9)
+    N, M = 300, 1024
+    q = torch.randn(N, d, device="cuda", generator=g)
+    k = torch.randn(M, d, device="cuda", generator=g)
+    k = k * (2.0 * (torch.arange(M, device="cuda") // 128 + 1)).unsqueeze(1)       # 8 key tiles, scores grow ~8.7 log2 units per tile
+    v = torch.randn(M, d, device="cuda", generator=g)
+    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    o, lse2 = K.attn_fwd(qb, kb, vb, 1, 1, N, M, d, d ** -0.5)
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (qb, kb, vb))
+    ref = ((qf @ kf.t()) * d ** -0.5).softmax(-1) @ vf
+    assert O.max_rel(o, ref) <= FWD_TOL
+    lse_ref = torch.logsumexp((qf @ kf.t()) * d ** -0.5, -1) * 1.4426950408889634
+    assert float((lse2[0, 0, :N] - lse_ref).abs().max()) < 1e-2
+    r = torch.randn(N, d, device="cuda", generator=g).bfloat16()
+    ref.backward(r.float())
+    dq, dk, dv = (torch.empty_like(t) for t in (qb, kb, vb))
+    K.attn_bwd(qb, kb, vb, o, lse2, r, 1, 1, N, M, d, d ** -0.5, dq, dk, dv)
+    for a, b in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
+        assert O.cosine(a, b) >= COS_TOL
