@@ -110,6 +110,14 @@ class Conv3dGeom(C.Structure):
     ]
 
 
+class Conv2dGeom(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("Cin", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("k", C.c_int32), ("stride", C.c_int32),
+        ("pad", C.c_int32),
+        ("sn", C.c_int64), ("sc", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64),
+    ]
+
+
 def lib():
     """Load the shared library once; raise loudly if it is not there."""
     global _lib
@@ -139,6 +147,8 @@ EXPORTS = [
     "hvc_im2col3d", "hvc_col2im3d", "hvc_groupnorm_silu_fwd", "hvc_groupnorm_silu_bwd",
     "hvc_add_pos", "hvc_batch_sum", "hvc_head_fwd", "hvc_upsample3d_fwd", "hvc_upsample3d_bwd",
     "hvc_split3", "hvc_softmax_rows", "hvc_im2col3d_f32", "hvc_epilogue_f32",
+    "hvc_im2col2d", "hvc_col2im2d", "hvc_norm_act_fwd", "hvc_norm_act_bwd", "hvc_maxpool2d_fwd", "hvc_maxpool2d_bwd",
+    "hvc_view_mean_fwd", "hvc_view_mean_bwd", "hvc_silu",
 ]
 
 

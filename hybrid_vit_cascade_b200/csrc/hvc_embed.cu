@@ -97,11 +97,14 @@ struct GnStatArgs {
   const float* w; const float* b;       // [C]
   float* S1; float* S2;                 // [B, C]
   int V, C, cpg, rows_per_block;
+  int act;                              // 0 = SiLU (GroupNorm+SiLU of the voxel embed), 1 = ReLU (BatchNorm2d+ReLU of the X-ray encoder)
 };
+__device__ __forceinline__ float act_fwd(float z, int act) { return act == 0 ? z / (1.f + __expf(-z)) : fmaxf(z, 0.f); }
 __device__ __forceinline__ float silu_grad(float z) {
   const float s = 1.f / (1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
 }
+__device__ __forceinline__ float act_grad(float z, int act) { return act == 0 ? silu_grad(z) : (z > 0.f ? 1.f : 0.f); }
 template <int MODE>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const GnStatArgs a) {
   __shared__ float4 red1[256], red2[256];
@@ -134,8 +137,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const GnStatArgs a) {
       } else {
         const float4 dy = __ldg(reinterpret_cast<const float4*>(a.dy + off));
         const float xh[4] = {(x.x - mean[0]) * rstd[0], (x.y - mean[1]) * rstd[1], (x.z - mean[2]) * rstd[2], (x.w - mean[3]) * rstd[3]};
-        const float d0 = dy.x * silu_grad(xh[0] * wv.x + bv.x), d1 = dy.y * silu_grad(xh[1] * wv.y + bv.y);
-        const float d2 = dy.z * silu_grad(xh[2] * wv.z + bv.z), d3 = dy.w * silu_grad(xh[3] * wv.w + bv.w);
+        const float d0 = dy.x * act_grad(xh[0] * wv.x + bv.x, a.act), d1 = dy.y * act_grad(xh[1] * wv.y + bv.y, a.act);
+        const float d2 = dy.z * act_grad(xh[2] * wv.z + bv.z, a.act), d3 = dy.w * act_grad(xh[3] * wv.w + bv.w, a.act);
         s1.x += d0; s1.y += d1; s1.z += d2; s1.w += d3;
         s2.x += d0 * xh[0]; s2.y += d1 * xh[1]; s2.z += d2 * xh[2]; s2.w += d3 * xh[3];
       }
@@ -196,7 +199,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                                                        const float* __restrict__ A, const float* __restrict__ Bq, bf16* __restrict__ y,
-                                                       float* __restrict__ dx, int B, int V, int C, int cpg, int y_f32) {
+                                                       float* __restrict__ dx, int B, int V, int C, int cpg, int y_f32, int act) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*V*C/4
   const int tpr = C >> 2;
   const long long total = (long long)B * V * tpr;
@@ -222,9 +225,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__
     const float xh = (xs[e] - mu) * rs;
     const float z = xh * ws[e] + bs[e];
     if (MODE == 0) {
-      out[e] = z / (1.f + __expf(-z));
+      out[e] = act_fwd(z, act);
     } else {
-      const float ds = dys[e] * silu_grad(z);
+      const float ds = dys[e] * act_grad(z, act);
       out[e] = rs * (ds * ws[e] - A[bb * G + g] - xh * Bq[bb * G + g]);
     }
   }
@@ -295,45 +298,61 @@ static int gn_rows_per_block(int B, int V) {
   return rpb;
 }
 
-extern "C" int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
-                                      void* y, int32_t y_is_bf16, float* mean, float* rstd, float* scratch, void* stream) {
-  HVC_CHECK_ARG(x && w && b && y && mean && rstd && scratch, "hvc_groupnorm_silu_fwd: null operand");
-  HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_groupnorm_silu_fwd: bad shape C=%d G=%d", C, groups);
+extern "C" int hvc_norm_act_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
+                                int32_t activation, int32_t stats_given, void* y, int32_t y_is_bf16, float* mean, float* rstd,
+                                float* scratch, void* stream) {
+  HVC_CHECK_ARG(x && w && b && y && mean && rstd && (scratch || stats_given), "hvc_norm_act_fwd: null operand");
+  HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_norm_act_fwd: bad shape C=%d G=%d", C, groups);
+  HVC_CHECK_ARG(activation == 0 || activation == 1, "hvc_norm_act_fwd: activation must be 0 (SiLU) or 1 (ReLU)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  HVC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * C, st));
-  GnStatArgs a;
-  a.x = x; a.dy = nullptr; a.mean = nullptr; a.rstd = nullptr; a.w = w; a.b = b; a.S1 = scratch; a.S2 = scratch + (long long)B * C;
-  a.V = V; a.C = C; a.cpg = C / groups; a.rows_per_block = gn_rows_per_block(B, V);
-  gn_stats_kernel<0><<<dim3((V + a.rows_per_block - 1) / a.rows_per_block, B), 256, 0, st>>>(a);
-  HVC_LAUNCH_CHECK();
-  gn_fwd_finalize_kernel<<<(B * groups + 127) / 128, 128, 0, st>>>(a.S1, a.S2, mean, rstd, B, C, a.cpg, V);
-  HVC_LAUNCH_CHECK();
+  const int cpg = C / groups;
+  if (!stats_given) {
+    HVC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * C, st));
+    GnStatArgs a;
+    a.x = x; a.dy = nullptr; a.mean = nullptr; a.rstd = nullptr; a.w = w; a.b = b; a.S1 = scratch; a.S2 = scratch + (long long)B * C;
+    a.V = V; a.C = C; a.cpg = cpg; a.rows_per_block = gn_rows_per_block(B, V); a.act = activation;
+    gn_stats_kernel<0><<<dim3((V + a.rows_per_block - 1) / a.rows_per_block, B), 256, 0, st>>>(a);
+    HVC_LAUNCH_CHECK();
+    gn_fwd_finalize_kernel<<<(B * groups + 127) / 128, 128, 0, st>>>(a.S1, a.S2, mean, rstd, B, C, cpg, V);
+    HVC_LAUNCH_CHECK();
+  }
   const long long total = (long long)B * V * (C / 4);
   gn_apply_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, nullptr, mean, rstd, w, b, nullptr, nullptr, reinterpret_cast<bf16*>(y),
-                                                                      nullptr, B, V, C, a.cpg, y_is_bf16 ? 0 : 1);
+                                                                      nullptr, B, V, C, cpg, y_is_bf16 ? 0 : 1, activation);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
+}
+extern "C" int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
+                                      void* y, int32_t y_is_bf16, float* mean, float* rstd, float* scratch, void* stream) {
+  return hvc_norm_act_fwd(x, w, b, B, V, C, groups, 0, 0, y, y_is_bf16, mean, rstd, scratch, stream);
 }
 
 extern "C" int hvc_groupnorm_silu_bwd(const float* dy, const float* x, const float* w, const float* b, const float* mean, const float* rstd,
                                       int32_t B, int32_t V, int32_t C, int32_t groups, float* dx, float* dw, float* db, float* scratch,
                                       void* stream) {
-  HVC_CHECK_ARG(dy && x && w && b && mean && rstd && dx && dw && db && scratch, "hvc_groupnorm_silu_bwd: null operand");
-  HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_groupnorm_silu_bwd: bad shape");
+  return hvc_norm_act_bwd(dy, x, w, b, mean, rstd, B, V, C, groups, 0, 0, dx, dw, db, scratch, stream);
+}
+extern "C" int hvc_norm_act_bwd(const float* dy, const float* x, const float* w, const float* b, const float* mean, const float* rstd,
+                                int32_t B, int32_t V, int32_t C, int32_t groups, int32_t activation, int32_t stats_frozen, float* dx,
+                                float* dw, float* db, float* scratch, void* stream) {
+  HVC_CHECK_ARG(dy && x && w && b && mean && rstd && dx && dw && db && scratch, "hvc_norm_act_bwd: null operand");
+  HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_norm_act_bwd: bad shape");
+  HVC_CHECK_ARG(activation == 0 || activation == 1, "hvc_norm_act_bwd: activation must be 0 (SiLU) or 1 (ReLU)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // scratch: T1 [B,C], T2 [B,C], A [B,G], Bq [B,G]
   HVC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * C, st));
   float* T1 = scratch; float* T2 = scratch + (long long)B * C; float* A = T2 + (long long)B * C; float* Bq = A + (long long)B * groups;
   GnStatArgs a;
   a.x = x; a.dy = dy; a.mean = mean; a.rstd = rstd; a.w = w; a.b = b; a.S1 = T1; a.S2 = T2;
-  a.V = V; a.C = C; a.cpg = C / groups; a.rows_per_block = gn_rows_per_block(B, V);
+  a.V = V; a.C = C; a.cpg = C / groups; a.rows_per_block = gn_rows_per_block(B, V); a.act = activation;
   gn_stats_kernel<1><<<dim3((V + a.rows_per_block - 1) / a.rows_per_block, B), 256, 0, st>>>(a);
   HVC_LAUNCH_CHECK();
   const int n = C > B * groups ? C : B * groups;
   gn_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(T1, T2, w, dw, db, A, Bq, B, C, a.cpg, V);
   HVC_LAUNCH_CHECK();
+  if (stats_frozen) HVC_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * 2 * B * groups, st));   // eval-mode BatchNorm: statistics are constants
   const long long total = (long long)B * V * (C / 4);
-  gn_apply_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, B, V, C, a.cpg, 0);
+  gn_apply_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, B, V, C, a.cpg, 0, activation);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

@@ -497,3 +497,113 @@ def epilogue_f32(acc, bias=None, activation=ACT_NONE, resid=None, gate=None, gat
                                            _ptr(gate), C.c_int64(gate_ld), rows_per_batch, _ptr(out),
                                            C.c_int64(_row_major_2d(out, "out")), _stream()), "hvc_epilogue_f32")
     return out
+
+
+# ------------------------------------------------------------------ X-ray encoder (hvc_encoder.cu)
+
+def _geom2d(N, Cin, H, W, k, stride, pad, strides):
+    g = _lib.Conv2dGeom()
+    g.N, g.Cin, g.H, g.W, g.k, g.stride, g.pad = N, Cin, H, W, k, stride, pad
+    g.sn, g.sc, g.sh, g.sw = strides
+    return g
+
+
+def conv2d_out(n, k, stride, pad):
+    return (n + 2 * pad - k) // stride + 1
+
+
+def im2col2d(x, N, Cin, H, W, k, stride, pad, strides, out_dtype=torch.bfloat16):
+    """x: f32|bf16 tensor holding the conv input with element strides (sn, sc, sh, sw) -> bf16|f32 [N*Ho*Wo, Kp]."""
+    _need_cuda(x)
+    assert x.dtype in (torch.float32, torch.bfloat16)
+    Ho, Wo = conv2d_out(H, k, stride, pad), conv2d_out(W, k, stride, pad)
+    Kp = (Cin * k * k + 7) // 8 * 8
+    cols = torch.empty(N * Ho * Wo, Kp, device=x.device, dtype=out_dtype)
+    g = _geom2d(N, Cin, H, W, k, stride, pad, strides)
+    _lib.check(_lib.lib().hvc_im2col2d(_ptr(x), int(x.dtype == torch.bfloat16), C.byref(g), _ptr(cols), int(out_dtype == torch.float32),
+                                       _stream()), "hvc_im2col2d")
+    return cols
+
+
+def col2im2d(dcols, N, Cin, H, W, k, stride, pad, out, strides):
+    _need_cuda(dcols, out)
+    assert dcols.dtype == torch.bfloat16 and dcols.is_contiguous() and out.dtype == torch.float32
+    g = _geom2d(N, Cin, H, W, k, stride, pad, strides)
+    _lib.check(_lib.lib().hvc_col2im2d(_ptr(dcols), C.byref(g), _ptr(out), _stream()), "hvc_col2im2d")
+    return out
+
+
+ACT_SILU, ACT_RELU = 0, 1
+
+
+def norm_act_fwd(x, w, b, B, V, Cc, groups, activation, out_dtype=torch.bfloat16, mean=None, rstd=None):
+    """x f32 [B*V, C] channels-last -> (y, mean [B,G], rstd [B,G]); mean/rstd given = eval-mode BatchNorm statistics."""
+    _need_cuda(x, w, b)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    given = mean is not None
+    y = torch.empty(B * V, Cc, device=x.device, dtype=out_dtype)
+    if not given:
+        mean = torch.empty(B, groups, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(B, groups, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_norm_act_fwd(_ptr(x), _ptr(w), _ptr(b), B, V, Cc, groups, activation, int(given), _ptr(y),
+                                           int(out_dtype == torch.bfloat16), _ptr(mean), _ptr(rstd), _ptr(scratch), _stream()),
+               "hvc_norm_act_fwd")
+    return y, mean, rstd
+
+
+def norm_act_bwd(dy, x, w, b, mean, rstd, B, V, Cc, groups, activation, stats_frozen=False):
+    _need_cuda(dy, x)
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    dx = torch.empty(B * V, Cc, device=x.device, dtype=torch.float32)
+    dw = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    db = torch.empty(Cc, device=x.device, dtype=torch.float32)
+    scratch = torch.empty(2 * B * Cc + 2 * B * groups, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_norm_act_bwd(_ptr(dy), _ptr(x), _ptr(w), _ptr(b), _ptr(mean), _ptr(rstd), B, V, Cc, groups, activation,
+                                           int(stats_frozen), _ptr(dx), _ptr(dw), _ptr(db), _ptr(scratch), _stream()), "hvc_norm_act_bwd")
+    return dx, dw, db
+
+
+def maxpool2d_fwd(x, N, H, W, Cc, k, stride, pad):
+    """x f32 [N*H*W, C] channels-last -> (y f32 [N*Ho*Wo, C], arg u8)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    Ho, Wo = conv2d_out(H, k, stride, pad), conv2d_out(W, k, stride, pad)
+    y = torch.empty(N * Ho * Wo, Cc, device=x.device, dtype=torch.float32)
+    arg = torch.empty(N * Ho * Wo, Cc, device=x.device, dtype=torch.uint8)
+    _lib.check(_lib.lib().hvc_maxpool2d_fwd(_ptr(x), _ptr(y), _ptr(arg), N, H, W, Cc, k, stride, pad, _stream()), "hvc_maxpool2d_fwd")
+    return y, arg
+
+
+def maxpool2d_bwd(dy, arg, N, H, W, Cc, k, stride, pad):
+    _need_cuda(dy, arg)
+    assert dy.dtype == torch.float32 and dy.is_contiguous()
+    dx = torch.empty(N * H * W, Cc, device=dy.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_maxpool2d_bwd(_ptr(dy), _ptr(arg), _ptr(dx), N, H, W, Cc, k, stride, pad, _stream()), "hvc_maxpool2d_bwd")
+    return dx
+
+
+def view_mean_fwd(x, B, V, P, Cc, want_pooled=True):
+    """x f32 [B*V*P, C] -> (feat f32 [B*P, C], pooled f32 [B, C] | None)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    feat = torch.empty(B * P, Cc, device=x.device, dtype=torch.float32)
+    pooled = torch.empty(B, Cc, device=x.device, dtype=torch.float32) if want_pooled else None
+    _lib.check(_lib.lib().hvc_view_mean_fwd(_ptr(x), _ptr(feat), _ptr(pooled), B, V, P, Cc, _stream()), "hvc_view_mean_fwd")
+    return feat, pooled
+
+
+def view_mean_bwd(dfeat, dpooled, B, V, P, Cc):
+    t = dfeat if dfeat is not None else dpooled
+    _need_cuda(t)
+    dx = torch.empty(B * V * P, Cc, device=t.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_view_mean_bwd(_ptr(dfeat), _ptr(dpooled), _ptr(dx), B, V, P, Cc, _stream()), "hvc_view_mean_bwd")
+    return dx
+
+
+def silu(x, dy=None):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and (dy is None or (dy.dtype == torch.float32 and dy.is_contiguous()))
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().hvc_silu(_ptr(x), _ptr(dy), _ptr(out), C.c_int64(x.numel()), _stream()), "hvc_silu")
+    return out

@@ -1,0 +1,205 @@
+"""Drop-in replacement for the reference's ``XrayConditioningModule`` (models/diagnostic_losses.py:68-138) and
+``DirectCTRegression`` (direct_regression/model_direct.py:15-85): the producer of ``context`` / ``cond`` in front of the
+3D ViT backbone and the model that wires both together.
+
+Same class names, constructor arguments, forward signatures and ``state_dict`` keys (``encoder.{0,1,4,5,8,9}.*`` incl. the
+BatchNorm running buffers, ``time_mlp.{0,2}.*``, ``to_cond.*``; ``xray_encoder.*``, ``vit_backbone.*``, ``initial_volume``).
+The ``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.Linear`` children are parameter containers; forward and backward run on
+libhvc_sm100a kernels: Conv2d = im2col + tcgen05 GEMM on channels-last activations (forward with the fp32-accurate three-term
+operand split, see ConvBnRelu), BatchNorm2d+ReLU = hvc_norm_act,
+max-pool / view mean / pooling = hvc_encoder.cu, the small linears = the fp32 skinny-GEMM kernels.  The last stage emits the
+(B, H'W', C) token layout the backbone's cross-attention reads, so ``features.flatten(2).transpose(1, 2)`` is a free view.
+"""
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import kernels as K
+from . import ops
+from . import ops_fp32
+from .hybrid_vit_backbone import HybridViT3D
+
+
+class ConvBnRelu(Function):
+    """relu(batch_norm(conv2d(x)))  -- diagnostic_losses.py:81-93 (one of the three stages).
+
+    x: the conv input as a CUDA tensor addressed through `strides` = (sn, sc, sh, sw) element strides; returns channels-last
+    [N*Ho*Wo, Cout] (bf16, or f32 for the last stage).  Train mode normalises with the batch statistics and updates the
+    running buffers in place (momentum, unbiased variance) like nn.BatchNorm2d; eval mode uses the running buffers.
+    """
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, bn_w, bn_b, run_mean, run_var, geom, training, momentum, out_f32):
+        N, Cin, H, W, k, stride, pad, strides = geom
+        Cout = conv_w.shape[0]
+        Ho, Wo = K.conv2d_out(H, k, stride, pad), K.conv2d_out(W, k, stride, pad)
+        M = N * Ho * Wo
+        # fp32-accurate product (three-term bf16 split on the tensor cores, ops_fp32): ReLU and max-pool are discontinuous, and
+        # with plain bf16 products ~0.2 % of their masks differ from the fp32 reference -- enough to pull the gradient cosine
+        # of the early layers under 0.999.  The encoder is <1 % of the step, so the 6x tensor work is invisible.
+        cols32 = K.im2col2d(x, N, Cin, H, W, k, stride, pad, strides, out_dtype=torch.float32)
+        z = ops_fp32.linear(cols32, conv_w, conv_b, pad_to=cols32.shape[1])                            # [M, Cout] f32
+        cols = K.cast_bf16(cols32)                                                                     # operand of the backward GEMMs
+        del cols32
+        out_dtype = torch.float32 if out_f32 else torch.bfloat16
+        if training:
+            y, mean, rstd = K.norm_act_fwd(z, bn_w, bn_b, 1, M, Cout, Cout, K.ACT_RELU, out_dtype)
+            with torch.no_grad():       # running buffers (C-length vectors): momentum update with the unbiased variance
+                var = rstd.view(-1).pow(-2) - 1e-5
+                run_mean.mul_(1.0 - momentum).add_(mean.view(-1), alpha=momentum)
+                run_var.mul_(1.0 - momentum).add_(var * (M / max(M - 1, 1)), alpha=momentum)
+        else:
+            mean = run_mean.detach().float().view(1, Cout).contiguous()
+            rstd = (run_var.detach().float() + 1e-5).rsqrt().view(1, Cout).contiguous()
+            y, _, _ = K.norm_act_fwd(z, bn_w, bn_b, 1, M, Cout, Cout, K.ACT_RELU, out_dtype, mean=mean, rstd=rstd)
+        ctx.save_for_backward(cols, z, mean, rstd, conv_w, bn_w, bn_b)
+        ctx.meta = (geom, training, M, Cout, tuple(x.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, z, mean, rstd, conv_w, bn_w, bn_b = ctx.saved_tensors
+        (N, Cin, H, W, k, stride, pad, strides), training, M, Cout, x_shape = ctx.meta
+        dy = dy.float().contiguous()
+        dz, dbn_w, dbn_b = K.norm_act_bwd(dy, z, bn_w, bn_b, mean, rstd, 1, M, Cout, Cout, K.ACT_RELU, stats_frozen=not training)
+        dz16 = K.cast_bf16(dz)
+        dconv_b = K.colsum_bf16(dz16)
+        dconv_w = ops._wgrad(dz16, cols)[:, :Cin * k * k].reshape(conv_w.shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcols = ops._dgrad(dz16, ops.w16(conv_w, pad_to=cols.shape[1]))
+            dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)     # same (contiguous) layout as the forward input
+            K.col2im2d(dcols, N, Cin, H, W, k, stride, pad, dx, strides)
+        return dx, dconv_w, dconv_b, dbn_w, dbn_b, None, None, None, None, None, None
+
+
+class MaxPool(Function):
+    """nn.MaxPool2d(k, stride, pad) on channels-last f32 [N*H*W, C]  -- diagnostic_losses.py:84,89."""
+
+    @staticmethod
+    def forward(ctx, x, N, H, W, C, k, stride, pad):
+        y, arg = K.maxpool2d_fwd(x, N, H, W, C, k, stride, pad)
+        ctx.save_for_backward(arg)
+        ctx.meta = (N, H, W, C, k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        arg, = ctx.saved_tensors
+        N, H, W, C, k, stride, pad = ctx.meta
+        return K.maxpool2d_bwd(dy.float().contiguous(), arg, N, H, W, C, k, stride, pad), None, None, None, None, None, None, None
+
+
+class ViewMeanPool(Function):
+    """features = mean over views; pooled = mean over pixels  -- diagnostic_losses.py:120-130."""
+
+    @staticmethod
+    def forward(ctx, x, B, V, P, C):
+        feat, pooled = K.view_mean_fwd(x, B, V, P, C)
+        ctx.meta = (B, V, P, C)
+        return feat, pooled
+
+    @staticmethod
+    def backward(ctx, dfeat, dpooled):
+        B, V, P, C = ctx.meta
+        dfeat = None if dfeat is None else dfeat.float().contiguous()
+        dpooled = None if dpooled is None else dpooled.float().contiguous()
+        return K.view_mean_bwd(dfeat, dpooled, B, V, P, C), None, None, None, None
+
+
+class Silu(Function):
+    """nn.SiLU of the time MLP  -- diagnostic_losses.py:100."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float().contiguous()
+        ctx.save_for_backward(x)
+        return K.silu(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, = ctx.saved_tensors
+        return K.silu(x, dy.float().contiguous())
+
+
+class XrayConditioningModule(nn.Module):
+    """reference: models/diagnostic_losses.py:68-138"""
+
+    def __init__(self, img_size: int = 512, in_channels: int = 1, embed_dim: int = 256, num_views: int = 1,
+                 time_embed_dim: int = 256, cond_dim: int = 1024, share_view_weights: bool = True):
+        super().__init__()
+        self.num_views = num_views
+        self.embed_dim = embed_dim
+        self.cond_dim = cond_dim
+        self.encoder = nn.Sequential(
+            nn.Conv2d(in_channels, 64, kernel_size=7, stride=2, padding=3), nn.BatchNorm2d(64), nn.ReLU(inplace=True),
+            nn.MaxPool2d(kernel_size=3, stride=2, padding=1),
+            nn.Conv2d(64, 128, kernel_size=3, padding=1), nn.BatchNorm2d(128), nn.ReLU(inplace=True),
+            nn.MaxPool2d(kernel_size=2, stride=2),
+            nn.Conv2d(128, embed_dim, kernel_size=3, padding=1), nn.BatchNorm2d(embed_dim), nn.ReLU(inplace=True),
+        )
+        self.time_mlp = nn.Sequential(nn.Linear(time_embed_dim, time_embed_dim * 2), nn.SiLU(),
+                                      nn.Linear(time_embed_dim * 2, cond_dim))
+        self.to_cond = nn.Linear(embed_dim, cond_dim)
+
+    def _stage(self, x, conv, bn, geom, out_f32):
+        training = bn.training or not bn.track_running_stats
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        y = ConvBnRelu.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, geom, training,
+                             momentum, out_f32)
+        if training and bn.track_running_stats:
+            bn.num_batches_tracked += 1
+        return y
+
+    def forward(self, xrays: torch.Tensor, t: torch.Tensor):
+        """xrays: (B, num_views, C, H, W); t: (B, time_embed_dim) -> (xray_context (B, cond_dim), time_xray_cond (B, cond_dim),
+        xray_features_2d (B, embed_dim, H/8, W/8))"""
+        B, V = xrays.shape[0], xrays.shape[1]
+        if V == 1 or self.num_views <= 1:
+            x = xrays[:, 0]
+            V = 1
+        else:
+            x = xrays.reshape(B * V, *xrays.shape[2:])
+        x = x.float().contiguous()
+        N, Cin, H, W = x.shape
+        enc = self.encoder
+        y = self._stage(x, enc[0], enc[1], (N, Cin, H, W, 7, 2, 3, tuple(x.stride())), True)     # f32: the max-pool needs unrounded values
+        H1, W1 = K.conv2d_out(H, 7, 2, 3), K.conv2d_out(W, 7, 2, 3)
+        y = MaxPool.apply(y, N, H1, W1, 64, 3, 2, 1)
+        H2, W2 = K.conv2d_out(H1, 3, 2, 1), K.conv2d_out(W1, 3, 2, 1)
+        y = self._stage(y, enc[4], enc[5], (N, 64, H2, W2, 3, 1, 1, (H2 * W2 * 64, 1, W2 * 64, 64)), True)
+        y = MaxPool.apply(y, N, H2, W2, 128, 2, 2, 0)
+        H3, W3 = H2 // 2, W2 // 2
+        y = self._stage(y, enc[8], enc[9], (N, 128, H3, W3, 3, 1, 1, (H3 * W3 * 128, 1, W3 * 128, 128)), True)   # f32 [N*P, E]
+        E, P = self.embed_dim, H3 * W3
+        feat, pooled = ViewMeanPool.apply(y, B, V, P, E)                       # (B*P, E), (B, E)
+        features = feat.view(B, H3, W3, E).permute(0, 3, 1, 2)                # (B, E, H', W') view of the token-major buffer
+        xray_context = ops.AdaLN.apply(pooled, self.to_cond.weight, self.to_cond.bias)
+        h = ops.AdaLN.apply(t, self.time_mlp[0].weight, self.time_mlp[0].bias)
+        time_embed = ops.AdaLN.apply(Silu.apply(h), self.time_mlp[2].weight, self.time_mlp[2].bias)
+        return xray_context, time_embed + xray_context, features
+
+
+class DirectCTRegression(nn.Module):
+    """reference: direct_regression/model_direct.py:15-85 (X-rays -> CT volume, no diffusion)"""
+
+    def __init__(self, volume_size=(64, 64, 64), xray_img_size=512, voxel_dim=256, vit_depth=4, num_heads=4,
+                 xray_feature_dim=512, token_grid="reference"):
+        super().__init__()
+        self.volume_size = volume_size
+        self.xray_encoder = XrayConditioningModule(img_size=xray_img_size, in_channels=1, embed_dim=xray_feature_dim,
+                                                   num_views=2, time_embed_dim=256, cond_dim=1024, share_view_weights=False)
+        self.vit_backbone = HybridViT3D(volume_size=volume_size, in_channels=1, voxel_dim=voxel_dim, depth=vit_depth,
+                                        num_heads=num_heads, context_dim=xray_feature_dim, cond_dim=1024,
+                                        use_prev_stage=False, token_grid=token_grid)
+        D, H, W = volume_size
+        self.initial_volume = nn.Parameter(torch.randn(1, 1, D, H, W) * 0.01)
+
+    def forward(self, xrays):
+        """xrays: (B, num_views, 1, H, W) -> predicted volume (B, 1, D, H, W)"""
+        batch_size = xrays.shape[0]
+        dummy_t = torch.zeros(batch_size, 256, device=xrays.device)
+        xray_context, time_xray_cond, xray_features_2d = self.xray_encoder(xrays, dummy_t)
+        x = self.initial_volume.expand(batch_size, -1, -1, -1, -1)
+        return self.vit_backbone(x=x, context=xray_features_2d.flatten(2).transpose(1, 2), cond=time_xray_cond,
+                                 prev_stage_embed=None)

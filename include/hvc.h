@@ -277,6 +277,45 @@ int hvc_epilogue_f32(const float* acc, int64_t lda, int32_t T, int32_t N, const 
                      const float* resid, int64_t ldr, const float* gate, int64_t gate_ld, int32_t rows_per_batch,
                      float* out, int64_t ldo, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * X-ray encoder in front of the backbone: XrayConditioningModule, models/diagnostic_losses.py:68-138.
+ * Conv2d (k x k, stride 1|2) as im2col + hvc_gemm on channels-last activations [images, pixels, C]; BatchNorm2d + ReLU as
+ * hvc_norm_act with one group per channel over all rows (train mode: batch statistics; eval mode: stats_given = 1 with
+ * mean / rstd derived from the running buffers).  hvc_conv2d_geom describes the conv INPUT: sizes and element strides.
+ * Patch matrix: bf16 or f32 [N*Ho*Wo, Kp], column kk = cin*k*k + kh*k + kw (the order of weight.view(Cout, Cin*k*k)), Kp = K rounded up
+ * to 8.  The forward convolutions of the encoder use the f32 patch matrix with the three-term operand split (hvc_split3): ReLU and
+ * max-pool are discontinuous, and with bf16 products ~0.2 % of the masks flip, which is visible in the gradients of the early layers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct hvc_conv2d_geom {
+  int32_t N, Cin, H, W, k, stride, pad;
+  int64_t sn, sc, sh, sw;
+} hvc_conv2d_geom;
+int hvc_im2col2d(const void* x, int32_t x_is_bf16, const hvc_conv2d_geom* geom, void* cols, int32_t cols_is_f32, void* stream);
+/* dx (f32, layout given by geom strides) = adjoint of im2col2d applied to dcols (bf16 [M, Kp]). */
+int hvc_col2im2d(const void* dcols, const hvc_conv2d_geom* geom, float* dx, void* stream);
+/* y = act(norm(x) * w + b) on f32 x [B, V, C] channels-last with `groups` groups per sample: activation 0 = SiLU (GroupNorm+SiLU
+ * of the voxel embed; hvc_groupnorm_silu_* are the activation-0 forms), 1 = ReLU (BatchNorm2d+ReLU: B = 1, V = all rows,
+ * groups = C, diagnostic_losses.py:81-93).  stats_given: mean/rstd [B, groups] are inputs (eval-mode BatchNorm) instead of outputs.
+ * Backward: stats_frozen = 1 treats mean/rstd as constants.  Scratch sizes as for hvc_groupnorm_silu_*. */
+int hvc_norm_act_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
+                     int32_t activation, int32_t stats_given, void* y, int32_t y_is_bf16, float* mean, float* rstd,
+                     float* scratch, void* stream);
+int hvc_norm_act_bwd(const float* dy, const float* x, const float* w, const float* b, const float* mean, const float* rstd,
+                     int32_t B, int32_t V, int32_t C, int32_t groups, int32_t activation, int32_t stats_frozen, float* dx,
+                     float* dw, float* db, float* scratch, void* stream);
+/* nn.MaxPool2d(k, stride, pad) on channels-last f32 [N, H, W, C] -> f32 (diagnostic_losses.py:84,89); arg = window-relative index of
+ * the maximum (u8 [N, Ho, Wo, C]) for the backward, which gathers dy (f32) into dx (f32 [N, H, W, C], every element written). */
+int hvc_maxpool2d_fwd(const void* x, void* y, uint8_t* arg, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t stride,
+                      int32_t pad, void* stream);
+int hvc_maxpool2d_bwd(const float* dy, const uint8_t* arg, float* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                      int32_t stride, int32_t pad, void* stream);
+/* feat[b, p, c] = mean_v x[b*V + v, p, c] (f32; the view average, diagnostic_losses.py:125) and, when pooled != NULL,
+ * pooled[b, c] = mean_p feat[b, p, c] (:130).  Backward: dx = (dfeat + dpooled / P) / V broadcast over the views. */
+int hvc_view_mean_fwd(const float* x, float* feat, float* pooled, int32_t B, int32_t V, int32_t P, int32_t C, void* stream);
+int hvc_view_mean_bwd(const float* dfeat, const float* dpooled, float* dx, int32_t B, int32_t V, int32_t P, int32_t C, void* stream);
+/* out = silu(x) (dy == NULL) or dy * silu'(x): the nn.SiLU of the time MLP (diagnostic_losses.py:100). */
+int hvc_silu(const float* x, const float* dy, float* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,69 @@
+"""CPU restatement of the X-ray encoder in front of the backbone and of the direct-regression model (test infrastructure:
+only tests/, __graft_entry__.smoke() and bench.py's CPU arm may import this).
+
+    XrayConditioningModule.forward   models/diagnostic_losses.py:107-138
+    DirectCTRegression.forward       direct_regression/model_direct.py:59-85
+
+Functional over a state_dict, like oracle/vit_oracle.py; autograd gives the gradients.  Pinned against outputs of the real
+reference modules run in the authoring container (tests/golden/make_golden.py -> tests/golden/encoder.pt,
+tests/test_oracle_golden.py).
+"""
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import vit_oracle as V
+
+StateDict = Dict[str, Tensor]
+
+
+def _conv_bn_relu(x: Tensor, sd: StateDict, pfx: str, ci: int, bi: int, stride: int, pad: int, training: bool, momentum: float = 0.1,
+                  new_stats: Optional[dict] = None) -> Tensor:
+    """nn.Conv2d -> nn.BatchNorm2d -> nn.ReLU (diagnostic_losses.py:81-93).  Train mode normalises with batch statistics; the
+    updated running buffers are returned through `new_stats` instead of being written in place."""
+    x = F.conv2d(x, sd[f"{pfx}{ci}.weight"], sd[f"{pfx}{ci}.bias"], stride=stride, padding=pad)
+    rm, rv = sd[f"{pfx}{bi}.running_mean"], sd[f"{pfx}{bi}.running_var"]
+    if training:
+        rm2, rv2 = rm.detach().clone(), rv.detach().clone()
+        x = F.batch_norm(x, rm2, rv2, sd[f"{pfx}{bi}.weight"], sd[f"{pfx}{bi}.bias"], True, momentum, 1e-5)
+        if new_stats is not None:
+            new_stats[f"{pfx}{bi}.running_mean"], new_stats[f"{pfx}{bi}.running_var"] = rm2, rv2
+    else:
+        x = F.batch_norm(x, rm, rv, sd[f"{pfx}{bi}.weight"], sd[f"{pfx}{bi}.bias"], False, momentum, 1e-5)
+    return F.relu(x)
+
+
+def xray_conditioning(xrays: Tensor, t: Tensor, sd: StateDict, pfx: str = "", training: bool = True, new_stats: Optional[dict] = None):
+    """diagnostic_losses.py:107-138 -> (xray_context, time_xray_cond, xray_features_2d)."""
+    B, num_views = xrays.shape[0], xrays.shape[1]
+    e = pfx + "encoder."
+
+    def encoder(x):                                                            # :81-93
+        x = _conv_bn_relu(x, sd, e, 0, 1, 2, 3, training, new_stats=new_stats)
+        x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)
+        x = _conv_bn_relu(x, sd, e, 4, 5, 1, 1, training, new_stats=new_stats)
+        x = F.max_pool2d(x, kernel_size=2, stride=2)
+        return _conv_bn_relu(x, sd, e, 8, 9, 1, 1, training, new_stats=new_stats)
+
+    if num_views > 1:                                                          # :118-125
+        feats = encoder(xrays.reshape(B * num_views, *xrays.shape[2:]))
+        feats = feats.view(B, num_views, *feats.shape[1:]).mean(dim=1)
+    else:
+        feats = encoder(xrays[:, 0])                                           # :127
+    ctx = F.linear(feats.mean(dim=[-2, -1]), sd[pfx + "to_cond.weight"], sd[pfx + "to_cond.bias"])        # :130-131
+    h = F.silu(F.linear(t, sd[pfx + "time_mlp.0.weight"], sd[pfx + "time_mlp.0.bias"]))                  # :98-102, :134
+    time_embed = F.linear(h, sd[pfx + "time_mlp.2.weight"], sd[pfx + "time_mlp.2.bias"])
+    return ctx, time_embed + ctx, feats                                        # :135-137
+
+
+def direct_ct_regression(xrays: Tensor, sd: StateDict, cfg: V.BackboneConfig, training: bool = True, new_stats: Optional[dict] = None,
+                         attn_chunk: Optional[int] = None) -> Tensor:
+    """model_direct.py:59-85 (dropout off in the backbone)."""
+    B = xrays.shape[0]
+    dummy_t = torch.zeros(B, 256, device=xrays.device, dtype=xrays.dtype)      # :70
+    _, cond, feats = xray_conditioning(xrays, dummy_t, sd, "xray_encoder.", training, new_stats)   # :73
+    x = sd["initial_volume"].expand(B, -1, -1, -1, -1)                          # :76
+    bsd = {k[len("vit_backbone."):]: v for k, v in sd.items() if k.startswith("vit_backbone.")}
+    return V.backbone(x, feats.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)   # :79-84

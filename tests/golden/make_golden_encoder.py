@@ -1,0 +1,83 @@
+"""Golden fixtures for the X-ray encoder and the direct-regression model from the REAL reference (authoring container only).
+
+    python tests/golden/make_golden_encoder.py     ->  tests/golden/encoder.pt
+
+Imports XrayConditioningModule (models/diagnostic_losses.py) and DirectCTRegression (direct_regression/model_direct.py) from
+/root/reference, runs them on seeded inputs and stores weights, inputs, outputs, updated BatchNorm buffers and all gradients.
+BatchNorm is in train mode (what the trainers run); nn.Dropout is switched off (p = 0) and AdaLN re-randomised, as for the
+backbone fixtures.
+"""
+import os
+import sys
+
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(REF, "direct_regression"))
+
+from models.diagnostic_losses import XrayConditioningModule  # noqa: E402
+from model_direct import DirectCTRegression  # noqa: E402
+
+
+def grads(mod, outs_and_rs, leaves):
+    params = list(mod.parameters())
+    names = [n for n, _ in mod.named_parameters()]
+    loss = sum((o * r).sum() for o, r in outs_and_rs)
+    gs = torch.autograd.grad(loss, params + leaves, allow_unused=True)
+    pg = {n: (g if g is not None else torch.zeros_like(p)) for n, g, p in zip(names, gs, params)}
+    return pg, list(gs[len(params):])
+
+
+def main():
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    torch.manual_seed(0)
+    enc = XrayConditioningModule(img_size=64, in_channels=1, embed_dim=64, num_views=2, time_embed_dim=32, cond_dim=96,
+                                 share_view_weights=False).train()
+    sd0 = {k: v.clone() for k, v in enc.state_dict().items()}
+    xr = (torch.rand(2, 2, 1, 64, 64, generator=g) * 2 - 1).requires_grad_(True)
+    t = torch.randn(2, 32, generator=g)
+    ctx, cond, feats = enc(xr, t)
+    rs = [torch.randn(o.shape, generator=g) for o in (ctx, cond, feats)]
+    pg, ig = grads(enc, list(zip((ctx, cond, feats), rs)), [xr])
+    sd1 = {k: v.clone() for k, v in enc.state_dict().items() if "running" in k or "num_batches" in k}
+    enc.eval()
+    with torch.no_grad():
+        ectx, econd, efeats = enc(xr, t)
+    out["encoder"] = dict(sd=sd0, sd_after=sd1, xrays=xr.detach(), t=t, ctx=ctx.detach(), cond=cond.detach(), feats=feats.detach(),
+                          r=rs, pgrad=pg, xgrad=ig[0], eval_ctx=ectx, eval_cond=econd, eval_feats=efeats)
+
+    # one view (the else branch, diagnostic_losses.py:127)
+    torch.manual_seed(1)
+    enc1 = XrayConditioningModule(img_size=32, in_channels=1, embed_dim=32, num_views=1, time_embed_dim=16, cond_dim=48).train()
+    sd0 = {k: v.clone() for k, v in enc1.state_dict().items()}
+    xr1 = torch.rand(3, 1, 1, 32, 32, generator=g) * 2 - 1
+    t1 = torch.randn(3, 16, generator=g)
+    c1, d1, f1 = enc1(xr1, t1)
+    out["encoder_one_view"] = dict(sd=sd0, xrays=xr1, t=t1, ctx=c1.detach(), cond=d1.detach(), feats=f1.detach())
+
+    # DirectCTRegression, small
+    torch.manual_seed(2)
+    kw = dict(volume_size=(32, 32, 32), xray_img_size=64, voxel_dim=64, vit_depth=1, num_heads=1, xray_feature_dim=64)
+    m = DirectCTRegression(**kw).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "adaln.linear" in n:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    xr = torch.rand(2, 2, 1, 64, 64, generator=g) * 2 - 1
+    y = m(xr)
+    r = torch.randn(y.shape, generator=g)
+    pg, _ = grads(m, [(y, r)], [])
+    out["direct"] = dict(kwargs=kw, sd=sd0, xrays=xr, y=y.detach(), r=r, pgrad={k: v.bfloat16() for k, v in pg.items()})   # gradients are compared by cosine: bf16 storage
+    torch.save(out, os.path.join(HERE, "encoder.pt"))
+    print({k: list(v.keys()) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

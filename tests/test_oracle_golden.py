@@ -169,3 +169,52 @@ def test_flops_table_matches_survey():
     cfg = O.BackboneConfig(volume_size=(128,) * 3, voxel_dim=256, depth=4, num_heads=4, token_grid="conv")
     f = O.forward_flops(cfg, 4096)
     assert abs(f["total"] / 1e9 - 5270) < 10
+
+
+# ------------------------------------------------------------------ X-ray encoder / direct model
+
+def _enc_gold():
+    import os
+    return torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encoder.pt"), weights_only=False)
+
+
+def test_encoder_oracle_matches_reference_fixtures():
+    from oracle import encoder_oracle as E
+    c = _enc_gold()["encoder"]
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in c["sd"].items()}
+    xr = c["xrays"].clone().requires_grad_(True)
+    new = {}
+    ctx, cond, feats = E.xray_conditioning(xr, c["t"], sd, training=True, new_stats=new)
+    for a, b in ((ctx, c["ctx"]), (cond, c["cond"]), (feats, c["feats"])):
+        assert O.max_rel(a, b) <= 2e-6
+    for k, v in new.items():
+        assert O.max_rel(v, c["sd_after"][k]) <= 2e-6, k
+    loss = sum((o * r).sum() for o, r in zip((ctx, cond, feats), c["r"]))
+    loss.backward()
+    for k, g in c["pgrad"].items():
+        assert O.max_rel(sd[k].grad, g) <= 2e-5, k
+    assert O.max_rel(xr.grad, c["xgrad"]) <= 2e-5
+    sd_eval = dict(c["sd"], **{k: v for k, v in c["sd_after"].items()})
+    with torch.no_grad():
+        ectx, econd, efeats = E.xray_conditioning(c["xrays"], c["t"], sd_eval, training=False)
+    for a, b in ((ectx, c["eval_ctx"]), (econd, c["eval_cond"]), (efeats, c["eval_feats"])):
+        assert O.max_rel(a, b) <= 2e-6
+    c1 = _enc_gold()["encoder_one_view"]
+    with torch.no_grad():
+        a, b, f = E.xray_conditioning(c1["xrays"], c1["t"], c1["sd"], training=True)
+    assert O.max_rel(a, c1["ctx"]) <= 2e-6 and O.max_rel(b, c1["cond"]) <= 2e-6 and O.max_rel(f, c1["feats"]) <= 2e-6
+
+
+def test_direct_model_oracle_matches_reference_fixture():
+    from oracle import encoder_oracle as E
+    c = _enc_gold()["direct"]
+    kw = c["kwargs"]
+    cfg = O.BackboneConfig(volume_size=kw["volume_size"], in_channels=1, voxel_dim=kw["voxel_dim"], depth=kw["vit_depth"],
+                           num_heads=kw["num_heads"], context_dim=kw["xray_feature_dim"], cond_dim=1024)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in c["sd"].items()}
+    y = E.direct_ct_regression(c["xrays"], sd, cfg, training=True)
+    assert O.max_rel(y, c["y"]) <= 2e-6
+    (y * c["r"]).sum().backward()
+    for k, g in c["pgrad"].items():
+        if float(g.float().abs().max()) > 0:
+            assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
