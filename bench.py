@@ -40,6 +40,14 @@ WORKLOADS = {
     "stage2": dict(volume=(128, 128, 128), token_grid="conv", in_channels=32, voxel_dim=256, depth=6, heads=8, ctx_hw=32,
                    ctx_dim=512, cond_dim=1024, batch=2,
                    desc="progressive_cascade stage 2 ViT 128^3 (32 ch in, 32768 tokens, 1024 ctx tokens, d=32)"),
+    # the whole direct-regression model (model_direct.py: X-ray encoder -> context / cond -> backbone), X-rays in, volume out:
+    # the backbone workloads above plus the encoder of SURVEY 8(f) row 1
+    "direct128_model": dict(volume=(128, 128, 128), token_grid="conv", voxel_dim=256, depth=4, heads=4, ctx_hw=64, ctx_dim=512,
+                            cond_dim=1024, batch=8, full_model=True, xray=512,
+                            desc="DirectCTRegression 128^3: 2 x 512^2 X-rays -> encoder -> 3D ViT (32768 tokens, 4096 ctx tokens)"),
+    "direct64_model": dict(volume=(64, 64, 64), token_grid="reference", voxel_dim=256, depth=4, heads=4, ctx_hw=64, ctx_dim=512,
+                           cond_dim=1024, batch=8, full_model=True, xray=512,
+                           desc="DirectCTRegression 64^3: 2 x 512^2 X-rays -> encoder -> 3D ViT (4096 tokens, 4096 ctx tokens)"),
     "stage3": dict(volume=(256, 256, 256), token_grid="reference", in_channels=32, voxel_dim=256, depth=8, heads=8, ctx_hw=64,
                    ctx_dim=512, cond_dim=1024, batch=2, checkpoint=True,
                    desc="progressive_cascade stage 3 ViT 256^3 (32 ch in, 32768 tokens, 4096 ctx tokens, d=32, checkpointed)"),
@@ -68,6 +76,10 @@ def step_flops(w):
     """Algorithmic FLOPs of one sample, forward+backward (3 x forward)."""
     from oracle import vit_oracle as O
     f = O.forward_flops(oracle_cfg(w), w["ctx_hw"] ** 2)
+    if w.get("full_model"):     # X-ray encoder, per sample = 2 views: conv 7x7 1->64 s2, 3x3 64->128, 3x3 128->ctx_dim (+ small linears)
+        x = w["xray"]
+        enc = 2 * (2.0 * 49 * 64 * (x // 2) ** 2 + 2.0 * 576 * 128 * (x // 4) ** 2 + 2.0 * 1152 * w["ctx_dim"] * (x // 8) ** 2)
+        f = dict(f, encoder=enc, total=f["total"] + enc)
     return {k: 3.0 * v for k, v in f.items()}
 
 
@@ -175,15 +187,20 @@ def run_b200(args, w):
 
     torch.manual_seed(0)
     cin = w.get("in_channels", 1)
-    model = hvc.HybridViT3D(volume_size=w["volume"], in_channels=cin, voxel_dim=w["voxel_dim"], depth=w["depth"],
+    full = bool(w.get("full_model"))
+    model = hvc.DirectCTRegression(volume_size=w["volume"], xray_img_size=w["xray"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"],
+                                   num_heads=w["heads"], xray_feature_dim=w["ctx_dim"], token_grid=w["token_grid"]).to(dev) if full else \
+        hvc.HybridViT3D(volume_size=w["volume"], in_channels=cin, voxel_dim=w["voxel_dim"], depth=w["depth"],
                             num_heads=w["heads"], context_dim=w["ctx_dim"], cond_dim=w["cond_dim"],
                             token_grid=w["token_grid"]).to(dev)
     with torch.no_grad():
         for n, p in model.named_parameters():
             if "adaln.linear" in n:
                 p.normal_(0.0, 0.02)
-    direct = cin == 1
-    if direct:
+    direct = cin == 1 and not full
+    if full:
+        params = list(model.parameters())
+    elif direct:
         initial_volume = torch.nn.Parameter(torch.randn(1, 1, D, H, W, device=dev) * 0.01)   # model_direct.py:57
         params = list(model.parameters()) + [initial_volume]
     else:
@@ -194,7 +211,9 @@ def run_b200(args, w):
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     hw = w["ctx_hw"]
-    feat = torch.rand(B, w["ctx_dim"], hw, hw, device=dev, generator=g)          # encoder feature map (B, C, H', W')
+    # backbone workloads: the encoder feature map (B, C, H', W'); full-model workloads: the AP + lateral X-rays in [-1, 1]
+    feat = (torch.rand(B, 2, 1, w["xray"], w["xray"], device=dev, generator=g) * 2 - 1) if full else \
+        torch.rand(B, w["ctx_dim"], hw, hw, device=dev, generator=g)
     cond = torch.randn(B, w["cond_dim"], device=dev, generator=g)
     target = torch.rand(B, 1, D, H, W, device=dev, generator=g) * 2 - 1
     # cascade refiners: the ViT input is the (B, 32, D, H, W) output of the stage's upsample conv; its gradient is needed
@@ -205,6 +224,13 @@ def run_b200(args, w):
 
     def step(feat_, cond_, target_):
         gb.reset()
+        if full:
+            out = model(feat_)
+            loss = (out - target_).abs().mean()
+            loss.backward()
+            gb.finish()
+            opt.step()
+            return loss
         ctx = feat_.flatten(2).transpose(1, 2)                                    # model_direct.py:80 (a view, no copy)
         if direct:
             out = model(initial_volume.expand(B, -1, -1, -1, -1), ctx, cond_)
@@ -274,7 +300,7 @@ def run_b200(args, w):
 
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
-    h2d = sum(t.numel() * t.element_size() for t in (feat_h, cond_h, target_h))
+    h2d = sum(t.numel() * t.element_size() for t in ((feat_h, target_h) if full else (feat_h, cond_h, target_h)))
 
     if rank != 0:
         if world > 1:
@@ -303,7 +329,8 @@ def run_b200(args, w):
                 "peak_source": peak_src, "launches": len(big), "ms_per_launch": sum(t for t, _ in big) / len(big),
                 "frac_of_nominal_2250": ach / 2250.0}
     line = {
-        "metric": "train volumes/sec (3D ViT backbone fwd+bwd)", "value": value, "unit": "volumes/s", "n_gpus": world,
+        "metric": "train volumes/sec (DirectCTRegression fwd+bwd)" if full else "train volumes/sec (3D ViT backbone fwd+bwd)",
+        "value": value, "unit": "volumes/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": B * world, "voxel_dim": w["voxel_dim"],

@@ -41,6 +41,47 @@ __global__ void __launch_bounds__(256) im2col2d_kernel(const TIn* __restrict__ x
   else cols[idx] = __float2bfloat16(v);
 }
 
+// The same gather with the two-term operand split fused in: out[m, :] = [c0 | c1 | c0] (three blocks of Kp columns), c0 = bf16(v),
+// c1 = bf16(v - c0).  Against weights laid out [w0 | w0 | w1] one GEMM with K' = 3 Kp gives c0 w0 + c1 w0 + c0 w1 ~ the fp32
+// product to 2^-16; block 0 alone is the plain bf16 patch matrix the backward GEMMs read (a strided view, no second gather).
+__global__ void __launch_bounds__(256) im2col2d_split_kernel(const float* __restrict__ x, bf16* __restrict__ out, const Conv2dGeom g) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;      // one thread = 8 consecutive patch columns of one output pixel
+  const int kv = g.Kp >> 3;
+  const long long total = (long long)g.N * g.Ho * g.Wo * kv;
+  if (idx >= total) return;
+  const int kk0 = (int)(idx % kv) * 8;
+  const long long m0 = idx / kv;
+  long long m = m0;
+  const int ow = (int)(m % g.Wo); m /= g.Wo;
+  const int oh = (int)(m % g.Ho);
+  const int n = (int)(m / g.Ho);
+  const int k2 = g.k * g.k;
+  uint32_t c0[4], c1[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    float v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int kk = kk0 + e + u;
+      v[u] = 0.f;
+      if (kk < g.K) {
+        const int cin = kk / k2, tap = kk - cin * k2;
+        const int kh = tap / g.k, kw = tap - kh * g.k;
+        const int ih = oh * g.stride - g.pad + kh, iw = ow * g.stride - g.pad + kw;
+        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) v[u] = __ldg(x + n * g.sn + cin * g.sc + ih * g.sh + iw * g.sw);
+      }
+    }
+    const bf16 a0 = __float2bfloat16_rn(v[0]), b0 = __float2bfloat16_rn(v[1]);
+    const bf16 a1 = __float2bfloat16_rn(v[0] - __bfloat162float(a0)), b1 = __float2bfloat16_rn(v[1] - __bfloat162float(b0));
+    c0[e >> 1] = (uint32_t)__bfloat16_as_ushort(a0) | ((uint32_t)__bfloat16_as_ushort(b0) << 16);
+    c1[e >> 1] = (uint32_t)__bfloat16_as_ushort(a1) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+  }
+  bf16* row = out + m0 * (3LL * g.Kp) + kk0;
+  *reinterpret_cast<uint4*>(row) = make_uint4(c0[0], c0[1], c0[2], c0[3]);
+  *reinterpret_cast<uint4*>(row + g.Kp) = make_uint4(c1[0], c1[1], c1[2], c1[3]);
+  *reinterpret_cast<uint4*>(row + 2 * g.Kp) = make_uint4(c0[0], c0[1], c0[2], c0[3]);
+}
+
 // dx[n, c, h, w] = sum over the (output pixel, tap) pairs that read it of dcols[(n,oh,ow), c*k*k + tap]; c fastest (channels-last dx)
 __global__ void __launch_bounds__(256) col2im2d_kernel(const bf16* __restrict__ dcols, float* __restrict__ dx, const Conv2dGeom g) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -99,18 +140,19 @@ __global__ void __launch_bounds__(256) maxpool2d_fwd_kernel(const float* __restr
   y[idx] = best;
   arg[idx] = static_cast<uint8_t>(bi);
 }
-// dx[n,h,w,c] = sum of dy over the windows whose recorded maximum is this element
+// dx[n,h,w,c] = sum of dy over the windows whose recorded maximum is this element; four channels per thread (C % 4 == 0)
 __global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg, float* __restrict__ dx,
                                                             int N, int H, int W, int C, int Ho, int Wo, int k, int stride, int pad) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)N * H * W * C;
+  const int cv = C >> 2;
+  const long long total = (long long)N * H * W * cv;
   if (idx >= total) return;
   long long t = idx;
-  const int c = (int)(t % C); t /= C;
+  const int c = (int)(t % cv) * 4; t /= cv;
   const int w = (int)(t % W); t /= W;
   const int h = (int)(t % H);
   const int n = (int)(t / H);
-  float acc = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int kh = 0; kh < k; ++kh) {
     const int nh = h + pad - kh;
     if (nh < 0 || nh % stride) continue;
@@ -122,10 +164,16 @@ __global__ void __launch_bounds__(256) maxpool2d_bwd_kernel(const float* __restr
       const int ow = nw / stride;
       if (ow >= Wo) continue;
       const long long o = (((long long)n * Ho + oh) * Wo + ow) * C + c;
-      if (arg[o] == kh * k + kw) acc += dy[o];
+      const uchar4 a = *reinterpret_cast<const uchar4*>(arg + o);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dy + o));
+      const int me = kh * k + kw;
+      acc.x += a.x == me ? g.x : 0.f;
+      acc.y += a.y == me ? g.y : 0.f;
+      acc.z += a.z == me ? g.z : 0.f;
+      acc.w += a.w == me ? g.w : 0.f;
     }
   }
-  dx[idx] = acc;
+  *reinterpret_cast<float4*>(dx + (((long long)n * H + h) * W + w) * C + c) = acc;
 }
 
 // out[b, :] = mean_v x[b*V + v, :]   (n = pixels*C f32 elements per image; diagnostic_losses.py:125)
@@ -230,6 +278,17 @@ extern "C" int hvc_im2col2d(const void* x, int32_t x_is_bf16, const hvc_conv2d_g
   return HVC_OK;
 }
 
+extern "C" int hvc_im2col2d_split(const float* x, const hvc_conv2d_geom* geom, void* out, void* stream) {
+  HVC_CHECK_ARG(x && geom && out, "hvc_im2col2d_split: null operand");
+  Conv2dGeom g;
+  int rc = fill_geom2d(&g, geom);
+  if (rc) return rc;
+  const long long total = (long long)g.N * g.Ho * g.Wo * (g.Kp / 8);
+  im2col2d_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<bf16*>(out), g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
 extern "C" int hvc_col2im2d(const void* dcols, const hvc_conv2d_geom* geom, float* dx, void* stream) {
   HVC_CHECK_ARG(dcols && geom && dx, "hvc_col2im2d: null operand");
   Conv2dGeom g;
@@ -258,7 +317,8 @@ extern "C" int hvc_maxpool2d_bwd(const float* dy, const uint8_t* arg, float* dx,
   HVC_CHECK_ARG(dy && arg && dx && N > 0 && H > 0 && W > 0 && C > 0 && k >= 1 && k <= 3 && stride >= 1 && pad >= 0 && pad < k,
                 "hvc_maxpool2d_bwd: bad arguments");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  const long long total = (long long)N * H * W * C;
+  HVC_CHECK_ARG((C & 3) == 0, "hvc_maxpool2d_bwd: C must be a multiple of 4");
+  const long long total = (long long)N * H * W * (C / 4);
   maxpool2d_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, arg, dx, N, H, W, C, Ho, Wo, k,
                                                                                                             stride, pad);
   HVC_LAUNCH_CHECK();

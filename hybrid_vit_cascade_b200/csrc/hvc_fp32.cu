@@ -29,10 +29,14 @@ __device__ __forceinline__ void split3(float x, bf16& p0, bf16& p1, bf16& p2) {
   p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
 }
 
-// pattern 0 (A side): parts {0,1,2,0,1,0}; pattern 1 (B side): parts {0,0,0,1,1,2}
+// pattern 0 (A side): parts {0,1,2,0,1,0}; pattern 1 (B side): parts {0,0,0,1,1,2}   (six blocks, ~2^-24)
+// pattern 2 (A side): parts {0,1,0};        pattern 3 (B side): parts {0,0,1}           (three blocks: a0 b0 + a1 b0 + a0 b1, ~2^-16;
+//                                                                                         the X-ray encoder's forward convolutions)
 __device__ __forceinline__ int split_part(int pattern, int s) {
-  return pattern == 0 ? ((0x012010 >> (4 * (5 - s))) & 3) : ((0x000112 >> (4 * (5 - s))) & 3);
+  const uint32_t code = pattern == 0 ? 0x012010u : pattern == 1 ? 0x000112u : pattern == 2 ? 0x010000u : 0x001000u;
+  return (code >> (4 * (5 - s))) & 3;
 }
+__host__ __device__ __forceinline__ int split_blocks(int pattern) { return pattern < 2 ? 6 : 3; }
 
 // x f32 [R, C] (row pitch ldx) -> out bf16; one thread = 8 consecutive columns of one row.
 //   concat_rows == 0: out[r, s*C + c]      (out is [R, 6C], row pitch ldo)
@@ -54,8 +58,10 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x
 #pragma unroll
     for (int t = 0; t < 3; ++t) w[t][j >> 1] = (uint32_t)__bfloat16_as_ushort(a[t]) | ((uint32_t)__bfloat16_as_ushort(b[t]) << 16);
   }
+  const int nb = split_blocks(pattern);
 #pragma unroll
   for (int s = 0; s < 6; ++s) {
+    if (s >= nb) break;
     const int which = split_part(pattern, s);
     uint4 u;
     u.x = which == 0 ? w[0][0] : which == 1 ? w[1][0] : w[2][0];
@@ -152,8 +158,8 @@ extern "C" int hvc_epilogue_f32(const float* acc, int64_t lda, int32_t T, int32_
 extern "C" int hvc_split3(const float* x, int64_t ldx, int32_t R, int32_t C, void* out, int64_t ldo, int32_t pattern,
                           int32_t concat_rows, void* stream) {
   HVC_CHECK_ARG(x && out && R > 0 && C > 0, "hvc_split3: empty or null operand");
-  HVC_CHECK_ARG(pattern == 0 || pattern == 1, "hvc_split3: pattern must be 0 (A side) or 1 (B side)");
-  HVC_CHECK_ARG(concat_rows ? ldo >= C : ldo >= 6LL * C, "hvc_split3: output pitch too small");
+  HVC_CHECK_ARG(pattern >= 0 && pattern <= 3, "hvc_split3: pattern must be 0/1 (six-block A/B side) or 2/3 (three-block A/B side)");
+  HVC_CHECK_ARG(concat_rows ? ldo >= C : ldo >= (long long)split_blocks(pattern) * C, "hvc_split3: output pitch too small");
   const long long threads = (long long)R * ((C + 7) / 8);
   split3_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       x, ldx, R, C, reinterpret_cast<bf16*>(out), ldo, pattern, concat_rows);

@@ -420,14 +420,26 @@ __global__ void adaln_wgrad_kernel(const float* __restrict__ dp, const float* __
   dW[(long long)j * K + k] = t;
   if (k == 0 && db) db[j] = s;
 }
-// dcond[b,k] = sum_j dp[b,j] W[j,k]
-__global__ void adaln_dgrad_kernel(const float* __restrict__ dp, const float* __restrict__ W, float* __restrict__ dcond, int B, int K, int J) {
+// dcond[b,k] += sum_{j in this CTA's slab} dp[b,j] W[j,k]: W is read once (each CTA streams a slab of rows for every batch row,
+// up to 8 at a time in registers) instead of once per batch row by a handful of CTAs; dcond is zero-filled by the caller.
+__global__ void __launch_bounds__(128) adaln_dgrad_kernel(const float* __restrict__ dp, const float* __restrict__ W, float* __restrict__ dcond,
+                                                          int B, int K, int J, int rows_per_cta) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
+  const int j0 = blockIdx.y * rows_per_cta, j1 = min(j0 + rows_per_cta, J);
   if (k >= K) return;
-  float t = 0.f;
-  for (int j = 0; j < J; ++j) t = fmaf(__ldg(dp + (long long)b * J + j), __ldg(W + (long long)j * K + k), t);
-  dcond[(long long)b * K + k] = t;
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int nb = min(8, B - b0);
+    for (int j = j0; j < j1; ++j) {
+      const float w = __ldg(W + (long long)j * K + k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i < nb) t[i] = fmaf(__ldg(dp + (long long)(b0 + i) * J + j), w, t[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < nb) atomicAdd(dcond + (long long)(b0 + i) * K + k, t[i]);
+  }
 }
 
 static int pick_vpl(int C) { return C <= 128 ? 1 : C <= 256 ? 2 : C <= 512 ? 4 : C <= 1024 ? 8 : 0; }
@@ -570,7 +582,9 @@ extern "C" int hvc_adaln_bwd(const float* dparams, const float* cond, int64_t ld
     HVC_LAUNCH_CHECK();
   }
   if (dcond) {
-    adaln_dgrad_kernel<<<dim3((K + 127) / 128, B), 128, 0, st>>>(dparams, W, dcond, B, K, J);
+    HVC_CUDA(cudaMemsetAsync(dcond, 0, sizeof(float) * B * K, st));
+    const int rows_per_cta = 32;
+    adaln_dgrad_kernel<<<dim3((K + 127) / 128, (J + rows_per_cta - 1) / rows_per_cta), 128, 0, st>>>(dparams, W, dcond, B, K, J, rows_per_cta);
     HVC_LAUNCH_CHECK();
   }
   return HVC_OK;

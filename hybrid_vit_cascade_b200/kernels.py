@@ -456,10 +456,11 @@ def upsample3d_bwd(dout, B, grid, size):
 def split3(x, pattern, concat_rows=False):
     """x f32 2-D (unit inner stride) -> the six-term bf16 operand of hvc_fp32.cu: [R, 6C] or, with concat_rows, [6R, C]."""
     _need_cuda(x)
-    assert x.dtype == torch.float32 and pattern in (0, 1)
+    assert x.dtype == torch.float32 and pattern in (0, 1, 2, 3)
     ldx = _row_major_2d(x, "x")
     R, Cc = x.shape
-    out = torch.empty((6 * R, Cc) if concat_rows else (R, 6 * Cc), device=x.device, dtype=torch.bfloat16)
+    nb = 6 if pattern < 2 else 3
+    out = torch.empty((nb * R, Cc) if concat_rows else (R, nb * Cc), device=x.device, dtype=torch.bfloat16)
     _lib.check(_lib.lib().hvc_split3(_ptr(x), C.c_int64(ldx), R, Cc, _ptr(out), C.c_int64(out.stride(0)), pattern,
                                      int(concat_rows), _stream()), "hvc_split3")
     return out
@@ -523,6 +524,18 @@ def im2col2d(x, N, Cin, H, W, k, stride, pad, strides, out_dtype=torch.bfloat16)
     _lib.check(_lib.lib().hvc_im2col2d(_ptr(x), int(x.dtype == torch.bfloat16), C.byref(g), _ptr(cols), int(out_dtype == torch.float32),
                                        _stream()), "hvc_im2col2d")
     return cols
+
+
+def im2col2d_split(x, N, Cin, H, W, k, stride, pad, strides):
+    """f32 conv input -> bf16 [N*Ho*Wo, 3*Kp] = [c0 | c1 | c0] (two-term split fused into the gather)."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32
+    Ho, Wo = conv2d_out(H, k, stride, pad), conv2d_out(W, k, stride, pad)
+    Kp = (Cin * k * k + 7) // 8 * 8
+    out = torch.empty(N * Ho * Wo, 3 * Kp, device=x.device, dtype=torch.bfloat16)
+    g = _geom2d(N, Cin, H, W, k, stride, pad, strides)
+    _lib.check(_lib.lib().hvc_im2col2d_split(_ptr(x), C.byref(g), _ptr(out), _stream()), "hvc_im2col2d_split")
+    return out
 
 
 def col2im2d(dcols, N, Cin, H, W, k, stride, pad, out, strides):

@@ -5,8 +5,8 @@
 Same class names, constructor arguments, forward signatures and ``state_dict`` keys (``encoder.{0,1,4,5,8,9}.*`` incl. the
 BatchNorm running buffers, ``time_mlp.{0,2}.*``, ``to_cond.*``; ``xray_encoder.*``, ``vit_backbone.*``, ``initial_volume``).
 The ``nn.Conv2d`` / ``nn.BatchNorm2d`` / ``nn.Linear`` children are parameter containers; forward and backward run on
-libhvc_sm100a kernels: Conv2d = im2col + tcgen05 GEMM on channels-last activations (forward with the fp32-accurate three-term
-operand split, see ConvBnRelu), BatchNorm2d+ReLU = hvc_norm_act,
+libhvc_sm100a kernels: Conv2d = im2col + tcgen05 GEMM on channels-last activations (forward with a two-term operand split for
+near-fp32 products, see ConvBnRelu), BatchNorm2d+ReLU = hvc_norm_act,
 max-pool / view mean / pooling = hvc_encoder.cu, the small linears = the fp32 skinny-GEMM kernels.  The last stage emits the
 (B, H'W', C) token layout the backbone's cross-attention reads, so ``features.flatten(2).transpose(1, 2)`` is a free view.
 """
@@ -16,8 +16,22 @@ from torch.autograd import Function
 
 from . import kernels as K
 from . import ops
-from . import ops_fp32
 from .hybrid_vit_backbone import HybridViT3D
+
+
+_W3 = {}
+
+
+def _w3(p, pad_to):
+    """[w0 | w0 | w1] two-term B-side operand of a conv weight viewed [Cout, Cin*k*k] (zero-padded to pad_to); cached like ops.w16."""
+    t = ops._cache_get(_W3, p, pad_to)
+    if t is None:
+        src = p.detach().float().reshape(p.shape[0], -1)
+        padded = torch.zeros(src.shape[0], pad_to, device=src.device, dtype=torch.float32)
+        padded[:, :src.shape[1]] = src
+        t = K.split3(padded, 3)
+        ops._cache_put(_W3, p, pad_to, t)
+    return t
 
 
 class ConvBnRelu(Function):
@@ -34,13 +48,14 @@ class ConvBnRelu(Function):
         Cout = conv_w.shape[0]
         Ho, Wo = K.conv2d_out(H, k, stride, pad), K.conv2d_out(W, k, stride, pad)
         M = N * Ho * Wo
-        # fp32-accurate product (three-term bf16 split on the tensor cores, ops_fp32): ReLU and max-pool are discontinuous, and
-        # with plain bf16 products ~0.2 % of their masks differ from the fp32 reference -- enough to pull the gradient cosine
-        # of the early layers under 0.999.  The encoder is <1 % of the step, so the 6x tensor work is invisible.
-        cols32 = K.im2col2d(x, N, Cin, H, W, k, stride, pad, strides, out_dtype=torch.float32)
-        z = ops_fp32.linear(cols32, conv_w, conv_b, pad_to=cols32.shape[1])                            # [M, Cout] f32
-        cols = K.cast_bf16(cols32)                                                                     # operand of the backward GEMMs
-        del cols32
+        # Near-fp32 product on the bf16 tensor cores: the gather writes [c0 | c1 | c0] (two-term split of the f32 activation), the
+        # weight is [w0 | w0 | w1], and ONE GEMM with K' = 3 Kp sums c0 w0 + c1 w0 + c0 w1 (~2^-16).  ReLU and max-pool are
+        # discontinuous: with plain bf16 products ~0.2 % of their masks differ from the fp32 reference, enough to pull the gradient
+        # cosine of the early layers to 0.99.  Block 0 of the patch matrix is the plain bf16 operand of the backward GEMMs.
+        Kp = (Cin * k * k + 7) // 8 * 8
+        cols3 = K.im2col2d_split(x, N, Cin, H, W, k, stride, pad, strides)                             # [M, 3 Kp] bf16
+        z = K.gemm(cols3, _w3(conv_w, Kp), bias=conv_b, epilogue=K.EPI_F32)                            # [M, Cout] f32
+        cols = cols3[:, :Kp]
         out_dtype = torch.float32 if out_f32 else torch.bfloat16
         if training:
             y, mean, rstd = K.norm_act_fwd(z, bn_w, bn_b, 1, M, Cout, Cout, K.ACT_RELU, out_dtype)
@@ -67,7 +82,7 @@ class ConvBnRelu(Function):
         dconv_w = ops._wgrad(dz16, cols)[:, :Cin * k * k].reshape(conv_w.shape)
         dx = None
         if ctx.needs_input_grad[0]:
-            dcols = ops._dgrad(dz16, ops.w16(conv_w, pad_to=cols.shape[1]))
+            dcols = ops._dgrad(dz16, _w3(conv_w, cols.shape[1])[:, :cols.shape[1]])      # block 0 of [w0 | w0 | w1] = bf16(w)
             dx = torch.empty(x_shape, device=dy.device, dtype=torch.float32)     # same (contiguous) layout as the forward input
             K.col2im2d(dcols, N, Cin, H, W, k, stride, pad, dx, strides)
         return dx, dconv_w, dconv_b, dbn_w, dbn_b, None, None, None, None, None, None

@@ -259,6 +259,7 @@ int hvc_upsample3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int3
  * An fp32 operand is split into three bf16 terms x = x0 + x1 + x2; the six significant partial products are
  * laid out along K so ONE hvc_gemm with K' = 6K gives sum_k a_k b_k to ~fp32 accuracy:
  *   pattern 0 (A side): [x0 | x1 | x2 | x0 | x1 | x0]     pattern 1 (B side): [x0 | x0 | x0 | x1 | x1 | x2]
+ *   pattern 2 (A side): [x0 | x1 | x0]                    pattern 3 (B side): [x0 | x0 | x1]      (two terms, ~2^-16)
  * hvc_split3: x f32 [R, C] (pitch ldx) -> out bf16 [R, 6C] (concat_rows = 0; for K-major operands) or
  * [6R, C] (concat_rows = 1; for MN-major operands such as V in P V), pitch ldo.
  * hvc_softmax_rows: in place s[r,:] <- exp2(s[r,:] - max) / sum for f32 s [R, M] holding scores * scale * log2(e)
@@ -291,6 +292,10 @@ typedef struct hvc_conv2d_geom {
   int64_t sn, sc, sh, sw;
 } hvc_conv2d_geom;
 int hvc_im2col2d(const void* x, int32_t x_is_bf16, const hvc_conv2d_geom* geom, void* cols, int32_t cols_is_f32, void* stream);
+/* The gather with the two-term operand split fused in: out bf16 [M, 3*Kp] = [c0 | c1 | c0], c0 = bf16(v), c1 = bf16(v - c0); against
+ * weights split with hvc_split3 pattern 3 ([w0 | w0 | w1]) one hvc_gemm with K' = 3*Kp gives the product to ~2^-16.  Block 0 is the
+ * plain bf16 patch matrix (row pitch 3*Kp) that the backward GEMMs read. */
+int hvc_im2col2d_split(const float* x, const hvc_conv2d_geom* geom, void* out, void* stream);
 /* dx (f32, layout given by geom strides) = adjoint of im2col2d applied to dcols (bf16 [M, Kp]). */
 int hvc_col2im2d(const void* dcols, const hvc_conv2d_geom* geom, float* dx, void* stream);
 /* y = act(norm(x) * w + b) on f32 x [B, V, C] channels-last with `groups` groups per sample: activation 0 = SiLU (GroupNorm+SiLU
