@@ -6,9 +6,10 @@ reference (CPU) arm.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is one pass of the hot path over one batch: HybridViT3D forward (voxel embed, L x (AdaLN
-self-attention, cross-attention to the X-ray tokens, AdaLN MLP), LN/proj/upsample head) + L1 loss +
+self-attention, cross-attention to the X-ray tokens, AdaLN MLP), LN/proj/upsample head) + loss +
 backward of every parameter and of the learned input volume + (N>1) bucketed gradient all-reduce
-overlapped with backward + AdamW.  Workload = BASELINE.json configs[2]: direct_regression at 128^3,
+overlapped with backward + gradient-norm clip + AdamW (loss = DirectRegressionLoss L1 + 0.5 (1 - SSIM3D), clip 1.0, AdamW lr 1e-4 wd 0.01:
+config_direct.json).  Workload = BASELINE.json configs[2]: direct_regression at 128^3,
 C=256, 4 heads (d=64), depth 4, 32^3 = 32768 volume tokens (what the conv stack emits), 4096 X-ray
 context tokens x 512, batch 8 per GPU, synthetic inputs, random-init weights (AdaLN re-randomised so the
 self-attention and MLP branches are live).  Train-mode dropout is OFF in both arms.
@@ -219,6 +220,14 @@ def run_b200(args, w):
     # cascade refiners: the ViT input is the (B, 32, D, H, W) output of the stage's upsample conv; its gradient is needed
     vol_in = None if direct else (torch.randn(B, cin, D, H, W, device=dev, generator=g) * 0.5).requires_grad_(True)
     use_ckpt = bool(w.get("checkpoint"))
+    if args.loss == "direct":       # DirectRegressionLoss: L1 + 0.5 (1 - SSIM3D), model_direct.py:110-131 / config_direct.json
+        crit = hvc.DirectRegressionLoss(1.0, 0.5)
+
+        def loss_fn(out, tgt):
+            return crit(out, tgt)["total_loss"]
+    else:
+        def loss_fn(out, tgt):
+            return (out - tgt).abs().mean()
     if use_ckpt:
         from torch.utils.checkpoint import checkpoint
 
@@ -226,9 +235,11 @@ def run_b200(args, w):
         gb.reset()
         if full:
             out = model(feat_)
-            loss = (out - target_).abs().mean()
+            loss = loss_fn(out, target_)
             loss.backward()
             gb.finish()
+            if args.clip > 0:
+                torch.nn.utils.clip_grad_norm_(params, args.clip, foreach=True)
             opt.step()
             return loss
         ctx = feat_.flatten(2).transpose(1, 2)                                    # model_direct.py:80 (a view, no copy)
@@ -240,9 +251,11 @@ def run_b200(args, w):
         else:
             vol_in.grad = None
             out = model(vol_in, ctx, cond_)
-        loss = (out - target_).abs().mean()
+        loss = loss_fn(out, target_)
         loss.backward()
         gb.finish()
+        if args.clip > 0:
+            torch.nn.utils.clip_grad_norm_(params, args.clip, foreach=True)     # after the all-reduce, on the averaged gradients
         opt.step()
         return loss
 
@@ -335,7 +348,8 @@ def run_b200(args, w):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": B * world, "voxel_dim": w["voxel_dim"],
                    "heads": w["heads"], "depth": w["depth"], "tokens": oracle_cfg(w).num_tokens, "context_tokens": hw * hw,
-                   "parallelism": f"dp{world}", "dropout": 0.0, "optimizer": "AdamW(fused)", "loss": "L1",
+                   "parallelism": f"dp{world}", "dropout": 0.0, "optimizer": "AdamW(fused)", "grad_clip": args.clip,
+                   "loss": "L1 + 0.5*(1-SSIM3D) (DirectRegressionLoss, hvc_loss.cu)" if args.loss == "direct" else "L1",
                    "l2_note": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps, "loss": loss_val[0]},
@@ -364,6 +378,9 @@ def main():
     ap.add_argument("--workload", default="direct128", choices=sorted(WORKLOADS),
                     help="direct128 = BASELINE.json's metric configuration (default); the others are the remaining configs")
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--loss", default="direct", choices=["l1", "direct"],
+                    help="direct (default) = DirectRegressionLoss L1 + 0.5 (1 - SSIM3D) on the package's loss kernels (config_direct.json); l1 = plain L1")
+    ap.add_argument("--clip", type=float, default=1.0, help="gradient-norm clip (config_direct.json: 1.0; 0 = off)")
     ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -11,7 +11,8 @@ from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHead
                              SinusoidalTimeEmbedding, precision, set_dropout_policy, set_precision)
 from .hybrid_vit_backbone import HybridViT3D, HybridViTBlock3D  # noqa: F401
 from .xray_encoder import DirectCTRegression, XrayConditioningModule  # noqa: F401
+from .losses import DirectRegressionLoss, compute_ssim_loss  # noqa: F401
 
 __all__ = ["AdaLNModulation", "MultiHeadCrossAttention", "MultiHeadSelfAttention", "SinusoidalTimeEmbedding",
-           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "DirectCTRegression", "set_dropout_policy", "set_precision",
+           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "DirectCTRegression", "DirectRegressionLoss", "compute_ssim_loss", "set_dropout_policy", "set_precision",
            "precision"]

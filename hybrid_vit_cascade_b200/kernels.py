@@ -620,3 +620,31 @@ def silu(x, dy=None):
     out = torch.empty_like(x)
     _lib.check(_lib.lib().hvc_silu(_ptr(x), _ptr(dy), _ptr(out), C.c_int64(x.numel()), _stream()), "hvc_silu")
     return out
+
+
+# ------------------------------------------------------------------ direct-regression loss (hvc_loss.cu)
+
+def ssim_l1_fwd(pred, target, window=11):
+    """pred/target f32 (B, 1, D, H, W) contiguous -> (sums f64 [2] = {sum SSIM, sum |pred - target|}, filtered f32 [5n])."""
+    _need_cuda(pred, target)
+    assert pred.dtype == target.dtype == torch.float32 and pred.is_contiguous() and target.is_contiguous() and pred.shape == target.shape
+    B, D, H, W = pred.shape[0] * pred.shape[1], pred.shape[2], pred.shape[3], pred.shape[4]
+    n = pred.numel()
+    filtered = torch.empty(5 * n, device=pred.device, dtype=torch.float32)
+    scratch = torch.empty(10 * n, device=pred.device, dtype=torch.float32)
+    sums = torch.empty(2, device=pred.device, dtype=torch.float64)
+    _lib.check(_lib.lib().hvc_ssim_l1_fwd(_ptr(pred), _ptr(target), B, D, H, W, window, _ptr(filtered), _ptr(scratch), _ptr(sums), _stream()),
+               "hvc_ssim_l1_fwd")
+    return sums, filtered
+
+
+def ssim_l1_bwd(pred, target, filtered, c_ssim, c_l1, window=11, upstream=None):
+    _need_cuda(pred, target, filtered)
+    assert upstream is None or (upstream.is_cuda and upstream.dtype == torch.float32 and upstream.numel() == 1)
+    B, D, H, W = pred.shape[0] * pred.shape[1], pred.shape[2], pred.shape[3], pred.shape[4]
+    n = pred.numel()
+    scratch = torch.empty(9 * n, device=pred.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred)
+    _lib.check(_lib.lib().hvc_ssim_l1_bwd(_ptr(pred), _ptr(target), _ptr(filtered), B, D, H, W, window, C.c_float(c_ssim), C.c_float(c_l1),
+                                          _ptr(upstream), _ptr(scratch), _ptr(dpred), _stream()), "hvc_ssim_l1_bwd")
+    return dpred

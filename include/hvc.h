@@ -321,6 +321,19 @@ int hvc_view_mean_bwd(const float* dfeat, const float* dpooled, float* dx, int32
 /* out = silu(x) (dy == NULL) or dy * silu'(x): the nn.SiLU of the time MLP (diagnostic_losses.py:100). */
 int hvc_silu(const float* x, const float* dy, float* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Direct-regression training loss: DirectRegressionLoss = l1_weight * L1 + ssim_weight * (1 - mean SSIM3D),
+ * direct_regression/model_direct.py:88-131 (compute_ssim_loss: five F.avg_pool3d(window, stride 1, zero padding) box filters).
+ * pred / target: f32 [B, D, H, W] contiguous.  Forward: filtered f32 [5n] (box-filtered pred, target, pred^2, target^2, pred*target;
+ * kept for the backward), scratch f32 [10n], sums f64 [2] = {sum SSIM, sum |pred - target|} (n = B*D*H*W).
+ * Backward: dpred = upstream * (c_ssim * d(sum SSIM)/dpred + c_l1 * sign(pred - target)); upstream = one f32 in device memory (the
+ * gradient of the scalar loss; NULL = 1); scratch f32 [9n].
+ * ---------------------------------------------------------------------------------------------- */
+int hvc_ssim_l1_fwd(const float* pred, const float* target, int32_t B, int32_t D, int32_t H, int32_t W, int32_t window, float* filtered,
+                    float* scratch, double* sums, void* stream);
+int hvc_ssim_l1_bwd(const float* pred, const float* target, const float* filtered, int32_t B, int32_t D, int32_t H, int32_t W,
+                    int32_t window, float c_ssim, float c_l1, const float* upstream, float* scratch, float* dpred, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,3 +67,26 @@ def direct_ct_regression(xrays: Tensor, sd: StateDict, cfg: V.BackboneConfig, tr
     x = sd["initial_volume"].expand(B, -1, -1, -1, -1)                          # :76
     bsd = {k[len("vit_backbone."):]: v for k, v in sd.items() if k.startswith("vit_backbone.")}
     return V.backbone(x, feats.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)   # :79-84
+
+
+def ssim_loss(pred: Tensor, target: Tensor, window_size: int = 11) -> Tensor:
+    """compute_ssim_loss, model_direct.py:88-107."""
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    pad = window_size // 2
+
+    def box(x):
+        return F.avg_pool3d(x, window_size, stride=1, padding=pad)
+
+    mu_p, mu_t = box(pred), box(target)
+    s_pp = box(pred ** 2) - mu_p ** 2
+    s_tt = box(target ** 2) - mu_t ** 2
+    s_pt = box(pred * target) - mu_p * mu_t
+    ssim = ((2 * mu_p * mu_t + C1) * (2 * s_pt + C2)) / ((mu_p ** 2 + mu_t ** 2 + C1) * (s_pp + s_tt + C2))
+    return 1 - ssim.mean()
+
+
+def direct_regression_loss(pred: Tensor, target: Tensor, l1_weight: float = 1.0, ssim_weight: float = 0.5):
+    """DirectRegressionLoss.forward, model_direct.py:118-131."""
+    l1 = F.l1_loss(pred, target)
+    ss = ssim_loss(pred, target)
+    return {"total_loss": l1_weight * l1 + ssim_weight * ss, "l1_loss": l1, "ssim_loss": ss}

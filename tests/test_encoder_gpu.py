@@ -121,3 +121,22 @@ def test_direct_ct_regression_config_direct_shapes_run():
     y.abs().mean().backward()
     for n, p in m.named_parameters():
         assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+
+
+def test_direct_regression_loss_golden():
+    """DirectRegressionLoss (L1 + 0.5 (1 - SSIM3D), model_direct.py:88-131) against values and gradients from the real reference."""
+    import hybrid_vit_cascade_b200 as hvc
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "direct_loss.pt"), weights_only=False)
+    crit = hvc.DirectRegressionLoss(1.0, 0.5)
+    for name, c in gold.items():
+        pred = c["pred"].cuda().requires_grad_(True)
+        res = crit(pred, c["target"].cuda())
+        for k, ref in (("total_loss", c["total"]), ("l1_loss", c["l1"]), ("ssim_loss", c["ssim"])):
+            assert abs(float(res[k].detach()) - float(ref)) < 2e-5, (name, k, float(res[k].detach()), float(ref))
+        (3.0 * res["total_loss"]).backward()                  # a non-unit upstream gradient, applied on the device
+        assert O.max_rel(pred.grad, 3.0 * c["dpred"]) < 1e-4, (name, O.max_rel(pred.grad, 3.0 * c["dpred"]))
+        assert O.cosine(pred.grad, c["dpred"].cuda()) > 0.99999
+    # properties at the benchmark size: identical volumes -> SSIM = 1, loss = 0
+    v = torch.rand(2, 1, 64, 64, 64, device="cuda") * 2 - 1
+    res = crit(v, v.clone())
+    assert abs(float(res["total_loss"].detach())) < 1e-5

@@ -218,3 +218,15 @@ def test_direct_model_oracle_matches_reference_fixture():
     for k, g in c["pgrad"].items():
         if float(g.float().abs().max()) > 0:
             assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
+
+
+def test_direct_loss_oracle_matches_reference_fixture():
+    import os
+    from oracle import encoder_oracle as E
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "direct_loss.pt"), weights_only=False)
+    for name, c in gold.items():
+        pred = c["pred"].clone().requires_grad_(True)
+        res = E.direct_regression_loss(pred, c["target"])
+        assert abs(float(res["total_loss"]) - float(c["total"])) < 1e-6 and abs(float(res["ssim_loss"]) - float(c["ssim"])) < 1e-6
+        res["total_loss"].backward()
+        assert O.max_rel(pred.grad, c["dpred"]) < 1e-5, name
