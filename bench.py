@@ -208,7 +208,7 @@ def run_b200(args, w):
         params = list(model.parameters())
     gb = GradientBuckets(params)
     gb.broadcast_parameters(params)
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=bool(args.graph))
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     hw = w["ctx_hw"]
@@ -301,6 +301,38 @@ def run_b200(args, w):
     bwd = sorted(((a.elapsed_time(b), f) for a, b, f in prof.get("attn_bwd", [])), key=lambda z: -z[1])
     big = [z for z in bwd if z[1] == bwd[0][1]] if bwd else []
 
+    # ---- optional: the whole step (forward, loss, backward, clip, AdamW) captured once in a CUDA graph and replayed -- removes the
+    # host-side launch gaps that dominate the small 64^3 configuration (225 kernel launches in ~11 ms)
+    graph_info = None
+    if args.graph:
+        if world > 1:
+            raise SystemExit("--graph is a single-GPU measurement (the NCCL bucket hooks are not captured)")
+        s_feat, s_cond, s_target = feat.clone(), cond.clone(), target.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step(s_feat, s_cond, s_target)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            s_loss = step(s_feat, s_cond, s_target)
+
+        def step(f, c, t, _eager=step):                      # noqa: F811  (replaces the eager step from here on)
+            if f is not s_feat:
+                s_feat.copy_(f, non_blocking=True)
+                s_cond.copy_(c, non_blocking=True)
+                s_target.copy_(t, non_blocking=True)
+            cg.replay()
+            return s_loss
+
+        for _ in range(3):
+            step(s_feat, s_cond, s_target)
+        ms_graph = timed(lambda: step(s_feat, s_cond, s_target), args.steps)
+        graph_info = {"ms_per_step_eager": ms_total / args.steps, "ms_per_step": ms_graph / args.steps}
+        ms_total = ms_graph
+
     # ---- end-to-end: host buffers in, loss out, every step
     feat_h, cond_h, target_h = (t.cpu().pin_memory() for t in (feat, cond, target))
     loss_val = [0.0]
@@ -361,6 +393,9 @@ def run_b200(args, w):
         "kernels": kern,
         "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
     }
+    if graph_info:
+        line["cuda_graph"] = graph_info
+        line["config"]["step_launch"] = "one CUDA graph per step (value, e2e); roofline / kernels / clocks from the eager run before it"
     if world == 1 and not args.skip_cpu_baseline:
         cb = cpu_baseline(w, rows=args.cpu_rows)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -380,6 +415,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--loss", default="direct", choices=["l1", "direct"],
                     help="direct (default) = DirectRegressionLoss L1 + 0.5 (1 - SSIM3D) on the package's loss kernels (config_direct.json); l1 = plain L1")
+    ap.add_argument("--graph", action="store_true", help="capture the training step in a CUDA graph and time its replay (N=1)")
     ap.add_argument("--clip", type=float, default=1.0, help="gradient-norm clip (config_direct.json: 1.0; 0 = off)")
     ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")

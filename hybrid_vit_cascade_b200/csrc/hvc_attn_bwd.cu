@@ -9,7 +9,7 @@
 //        S^T  = K Q_i^T   (SS)      phase A: P^T = exp2(S^T*scale2 - lse2)          -> TMEM (bf16, own columns)
 //        dP^T = V dO_i^T  (SS)      phase B: dS^T = P^T * (dP^T - delta)            -> smem (bf16, swizzled, 2 buffers)
 //        dV  += P^T  dO_i (TS, dO MN-major)
-//        dK  += dS^T Q_i  (SS, dS^T K-major, Q MN-major)          (softmax scale applied in the epilogue)
+//        dK  += dS^T Q_i  (d=64: TS, dS^T as bf16 pairs in TMEM over the dP^T columns; d=32: SS, dS^T K-major; Q MN-major)   (scale in the epilogue)
 //        dQ_i = dS   K    (SS, dS^T read MN-major as A, K^T K-major) -> TMA reduce-add (fp32) into dq_accum
 //      320 threads: two elementwise warpgroups (thread == key row == TMEM lane; warpgroup x owns query columns
 //      [64x, 64x+64) of every tile), a TMA warp and an MMA warp.  Design points, each from a measurement on B200:
@@ -149,13 +149,14 @@ __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[kWgCols], uint3
 }
 // Phase B: dS^T = P^T * (dP^T - delta) -> four 16-byte chunks (chunk0 ..) of this thread's row in a swizzled sub-tile
 // DROP: dS = P * (keep ? dP / (1-p) : 0  -  delta), keep = sign of the stored P value.
-template <bool FULL, bool DROP>
+template <bool FULL, bool DROP, bool TSDK>
 __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[kWgCols], uint32_t delta_saddr, const float2 (&pv)[kWgCols / 2],
-                                            bool key_ok, int q_valid, uint32_t sub_saddr, int r, int chunk0, float inv_keep) {
+                                            bool key_ok, int q_valid, uint32_t sub_saddr, int r, int chunk0, float inv_keep, uint32_t t_ds) {
   const float2 neg1 = make_float2(-1.f, -1.f);
   const float2 rp2 = make_float2(inv_keep, inv_keep);
 #pragma unroll
   for (int g = 0; g < kWgCols; g += 4 * kDeltaPre) {
+    uint32_t dsp[2 * kDeltaPre];            // the group's dS^T as bf16 pairs: also written to TMEM (A operand of dK)
     float4 dq4[kDeltaPre];                  // delta of a column group, loaded ahead of the arithmetic (see phase A)
 #pragma unroll
     for (int u = 0; u < kDeltaPre; ++u) dq4[u] = lds_f4(delta_saddr + (g + 4 * u) * 4);
@@ -192,7 +193,10 @@ __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[kWgCols], uint3
         w4[2 * u + 1] = pack_bf16(x1.x, x1.y);
       }
       sts_u4(sub_saddr + sw128_offset(r, chunk0 + k), w4[0], w4[1], w4[2], w4[3]);
+      dsp[4 * kk] = w4[0]; dsp[4 * kk + 1] = w4[1]; dsp[4 * kk + 2] = w4[2]; dsp[4 * kk + 3] = w4[3];
     }
+    static_assert(kDeltaPre == 4, "one 8-column (16-query) TMEM store per group");
+    if (TSDK) tmem_st_32x8(t_ds + (g >> 1), dsp);
   }
 }
 
@@ -204,7 +208,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   static_assert(HD == 64 || HD == 32, "head_dim 64 (SWIZZLE_128B tiles) or 32 (SWIZZLE_64B tiles)");
   using L = BwdSmem<HD>;
   using SW = Swz<HD * 2>;        // Q / K / V / dO tiles as TMA delivers them: rows of HD*2 bytes
-  constexpr int kDCols = HD / kBwdWGs;     // d columns of dQ / dK / dV owned by one warpgroup (16 or 8)
+  constexpr int kDCols = HD / kBwdWGs;     // d columns of dQ / dK / dV owned by one warpgroup
+  // dK += dS^T Q with dS^T as a TMEM operand (bf16 pairs written over the dP^T columns by phase B) instead of the K-major smem tile:
+  // 53 vs 76 clk per MMA step at d = 64 (+1.6 % on the kernel); at d = 32 the smem form is the faster one (65 clk, no extra TMEM store)
+  constexpr bool kTsDk = HD == 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
@@ -306,13 +313,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                   SW::desc(sDO + (x * (kWgCols / 16) + k16) * SW::kMnStep, 8192), id_dv, (!first || k16 > 0) ? 1u : 0u);
       }
     };
-    auto issue_dk = [&](int x, int st, int buf, bool first) {   // dK += dS^T_x Q_x   (A = sub-tile x of the dS^T buffer, K-major; B = Q MN-major)
+    auto issue_dk = [&](int x, int st, int buf, bool first) {   // dK += dS^T_x Q_x   (B = Q MN-major)
       const uint32_t sQ = sQ0 + st * L::kQStage;
       if (leader) {
 #pragma unroll
-        for (int k16 = 0; k16 < kWgCols / 16; ++k16)
-          umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS0 + buf * L::kDSBuf + x * 16384 + k16 * 32, 16, 1024),
-                  SW::desc(sQ + (x * (kWgCols / 16) + k16) * SW::kMnStep, 8192), id_dv, (!first || k16 > 0) ? 1u : 0u);
+        for (int k16 = 0; k16 < kWgCols / 16; ++k16) {
+          const uint64_t bq = SW::desc(sQ + (x * (kWgCols / 16) + k16) * SW::kMnStep, 8192);
+          if constexpr (kTsDk)    // A = dS^T_x as bf16 pairs in TMEM (over the dP^T_x columns)
+            umma_ts(tmem_base + kColDK, tmem_base + kColDPt + x * kWgCols + k16 * 8, bq, id_dv, (!first || k16 > 0) ? 1u : 0u);
+          else                    // A = sub-tile x of the dS^T smem buffer, K-major
+            umma_ss(tmem_base + kColDK, make_sdesc_sw128(sDS0 + buf * L::kDSBuf + x * 16384 + k16 * 32, 16, 1024), bq, id_dv,
+                    (!first || k16 > 0) ? 1u : 0u);
+        }
       }
     };
     auto issue_dq = [&](int buf) {   // dQ = dS K   (A = both dS^T sub-tiles read MN-major: M = queries; B = K^T K-major: rows = d, two 64-key sub-tiles)
@@ -329,8 +341,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&bar[BB_DS + 1], t & 1, 25);
       tc_fence_after();
       if (leader) HVC_TR(2, t + 1, 2);
-      if (t + 1 < nQ) issue_dpt(1, (t + 1) % kQStages);
-      issue_dk(1, t % kQStages, t & 1, false);
+      if constexpr (kTsDk) {
+        issue_dk(1, t % kQStages, t & 1, false);                 // reads dS^T_1(t) from the dP^T_1 columns ...
+        if (t + 1 < nQ) issue_dpt(1, (t + 1) % kQStages);        // ... which dP^T_1(t+1) then overwrites (the tensor pipe runs in order)
+      } else {
+        if (t + 1 < nQ) issue_dpt(1, (t + 1) % kQStages);
+        issue_dk(1, t % kQStages, t & 1, false);
+      }
       if (t > 0) { mbar_wait(&bar[BB_DQFREE], (t - 1) & 1, 26); tc_fence_after(); }
       issue_dq(t & 1);
       commit(BB_QE + t % kQStages);
@@ -364,8 +381,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(&bar[BB_DS + 0], i & 1, 28);        // dS_0(i) in smem, dP^T_0(i) consumed
       tc_fence_after();
       if (leader) HVC_TR(2, i, 6);
-      if (more) issue_dpt(0, st1);
-      issue_dk(0, st, i & 1, i == 0);
+      if constexpr (kTsDk) {
+        issue_dk(0, st, i & 1, i == 0);
+        if (more) issue_dpt(0, st1);
+      } else {
+        if (more) issue_dpt(0, st1);
+        issue_dk(0, st, i & 1, i == 0);
+      }
       mbar_wait(&bar[BB_PT + 1], i & 1, 29);
       tc_fence_after();
       if (leader) HVC_TR(2, i, 7);
@@ -498,10 +520,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         if (wg_lead) HVC_TR(wg, i, 5);
         const uint32_t sub_saddr = sDS0 + (i & 1) * L::kDSBuf + wg * 16384;
-        if (full) bwd_phase_b<true, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, 0, inv_keep);
-        else      bwd_phase_b<false, DROP>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, 0, inv_keep);
+        const uint32_t t_ds = tmem_base + lane_base + kColDPt + wg * kWgCols;     // dS^T (bf16 pairs) over the dP^T columns just read
+        if (full) bwd_phase_b<true, DROP, kTsDk>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, 0, inv_keep, t_ds);
+        else      bwd_phase_b<false, DROP, kTsDk>(dv, delta_saddr, pv, key_ok, q_valid, sub_saddr, r, 0, inv_keep, t_ds);
       }
       if (wg_lead) HVC_TR(wg, i, 6);
+      if (kTsDk) tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive_warp(&bar[BB_DS + wg]);

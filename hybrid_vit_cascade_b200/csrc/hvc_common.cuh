@@ -277,6 +277,10 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v
       HVC_S4(v, 24), HVC_S4(v, 28)
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), HVC_S4(v, 0), HVC_S4(v, 4)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // byte offset of 16-byte chunk `chunk` of row `row` in a tile whose rows are ROWB bytes, swizzled the way TMA does for
