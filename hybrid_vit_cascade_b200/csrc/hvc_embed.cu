@@ -97,14 +97,15 @@ struct GnStatArgs {
   const float* w; const float* b;       // [C]
   float* S1; float* S2;                 // [B, C]
   int V, C, cpg, rows_per_block;
-  int act;                              // 0 = SiLU (GroupNorm+SiLU of the voxel embed), 1 = ReLU (BatchNorm2d+ReLU of the X-ray encoder)
+  int act;                              // 0 = SiLU (GroupNorm+SiLU of the voxel embed), 1 = ReLU (BatchNorm2d+ReLU of the X-ray encoder),
+                                        // 2 = GELU (GroupNorm+GELU of the cascade's multi-scale branches)
 };
-__device__ __forceinline__ float act_fwd(float z, int act) { return act == 0 ? z / (1.f + __expf(-z)) : fmaxf(z, 0.f); }
+__device__ __forceinline__ float act_fwd(float z, int act) { return act == 0 ? z / (1.f + __expf(-z)) : act == 1 ? fmaxf(z, 0.f) : gelu_erf(z); }
 __device__ __forceinline__ float silu_grad(float z) {
   const float s = 1.f / (1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
 }
-__device__ __forceinline__ float act_grad(float z, int act) { return act == 0 ? silu_grad(z) : (z > 0.f ? 1.f : 0.f); }
+__device__ __forceinline__ float act_grad(float z, int act) { return act == 0 ? silu_grad(z) : act == 1 ? (z > 0.f ? 1.f : 0.f) : gelu_erf_grad(z); }
 template <int MODE>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const GnStatArgs a) {
   __shared__ float4 red1[256], red2[256];
@@ -303,7 +304,7 @@ extern "C" int hvc_norm_act_fwd(const float* x, const float* w, const float* b, 
                                 float* scratch, void* stream) {
   HVC_CHECK_ARG(x && w && b && y && mean && rstd && (scratch || stats_given), "hvc_norm_act_fwd: null operand");
   HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_norm_act_fwd: bad shape C=%d G=%d", C, groups);
-  HVC_CHECK_ARG(activation == 0 || activation == 1, "hvc_norm_act_fwd: activation must be 0 (SiLU) or 1 (ReLU)");
+  HVC_CHECK_ARG(activation >= 0 && activation <= 2, "hvc_norm_act_fwd: activation must be 0 (SiLU), 1 (ReLU) or 2 (GELU)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int cpg = C / groups;
   if (!stats_given) {
@@ -337,7 +338,7 @@ extern "C" int hvc_norm_act_bwd(const float* dy, const float* x, const float* w,
                                 float* dw, float* db, float* scratch, void* stream) {
   HVC_CHECK_ARG(dy && x && w && b && mean && rstd && dx && dw && db && scratch, "hvc_norm_act_bwd: null operand");
   HVC_CHECK_ARG(B > 0 && V > 0 && C > 0 && (C & 3) == 0 && C <= 1024 && groups > 0 && C % groups == 0, "hvc_norm_act_bwd: bad shape");
-  HVC_CHECK_ARG(activation == 0 || activation == 1, "hvc_norm_act_bwd: activation must be 0 (SiLU) or 1 (ReLU)");
+  HVC_CHECK_ARG(activation >= 0 && activation <= 2, "hvc_norm_act_bwd: activation must be 0 (SiLU), 1 (ReLU) or 2 (GELU)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // scratch: T1 [B,C], T2 [B,C], A [B,G], Bq [B,G]
   HVC_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * B * C, st));

@@ -546,7 +546,7 @@ def col2im2d(dcols, N, Cin, H, W, k, stride, pad, out, strides):
     return out
 
 
-ACT_SILU, ACT_RELU = 0, 1
+ACT_SILU, ACT_RELU, ACT_GELU_ERF = 0, 1, 2
 
 
 def norm_act_fwd(x, w, b, B, V, Cc, groups, activation, out_dtype=torch.bfloat16, mean=None, rstd=None):

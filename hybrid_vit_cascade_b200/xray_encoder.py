@@ -218,3 +218,90 @@ class DirectCTRegression(nn.Module):
         x = self.initial_volume.expand(batch_size, -1, -1, -1, -1)
         return self.vit_backbone(x=x, context=xray_features_2d.flatten(2).transpose(1, 2), cond=time_xray_cond,
                                  prev_stage_embed=None)
+
+
+class ConvGnGelu(Function):
+    """gelu(group_norm(conv2d(x)))  -- one step of MultiScaleXrayEncoder.to_stage1 / to_stage2
+    (direct_regression/progressive_cascade/model_progressive.py:38-52): Conv2d(k3, stride 2, pad 1) + GroupNorm(32) + GELU.
+    x: f32 feature map addressed through `strides`; returns channels-last f32 [N*Ho*Wo, Cout].  All three pieces are smooth, so the
+    convolution is a plain bf16 tensor-core GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, gn_w, gn_b, geom, groups):
+        N, Cin, H, W, k, stride, pad, strides = geom
+        Cout = conv_w.shape[0]
+        Ho, Wo = K.conv2d_out(H, k, stride, pad), K.conv2d_out(W, k, stride, pad)
+        cols = K.im2col2d(x, N, Cin, H, W, k, stride, pad, strides)
+        z = K.gemm(cols, ops.w16(conv_w, pad_to=cols.shape[1]), bias=conv_b, epilogue=K.EPI_F32)
+        y, mean, rstd = K.norm_act_fwd(z, gn_w, gn_b, N, Ho * Wo, Cout, groups, K.ACT_GELU_ERF, torch.float32)
+        ctx.save_for_backward(cols, z, mean, rstd, conv_w, gn_w, gn_b)
+        ctx.meta = (geom, groups, Ho * Wo, Cout, tuple(x.shape), tuple(x.stride()))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, z, mean, rstd, conv_w, gn_w, gn_b = ctx.saved_tensors
+        (N, Cin, H, W, k, stride, pad, strides), groups, V, Cout, x_shape, x_strides = ctx.meta
+        dz, dgn_w, dgn_b = K.norm_act_bwd(dy.float().contiguous(), z, gn_w, gn_b, mean, rstd, N, V, Cout, groups, K.ACT_GELU_ERF)
+        dz16 = K.cast_bf16(dz)
+        dconv_b = K.colsum_bf16(dz16)
+        dconv_w = ops._wgrad(dz16, cols)[:, :Cin * k * k].reshape(conv_w.shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcols = ops._dgrad(dz16, ops.w16(conv_w, pad_to=cols.shape[1]))
+            dx = torch.empty_strided(x_shape, x_strides, device=dy.device, dtype=torch.float32)   # same memory layout as the input view
+            K.col2im2d(dcols, N, Cin, H, W, k, stride, pad, dx, strides)
+        return dx, dconv_w, dconv_b, dgn_w, dgn_b, None, None
+
+
+class MultiScaleXrayEncoder(nn.Module):
+    """reference: direct_regression/progressive_cascade/model_progressive.py:16-83"""
+
+    def __init__(self, img_size=512, in_channels=1, base_dim=512, num_views=2):
+        super().__init__()
+        self.xray_encoder = XrayConditioningModule(img_size=img_size, in_channels=in_channels, embed_dim=base_dim, num_views=num_views,
+                                                   time_embed_dim=256, cond_dim=1024, share_view_weights=False)
+        self.to_stage1 = nn.Sequential(
+            nn.Conv2d(base_dim, base_dim, 3, stride=2, padding=1), nn.GroupNorm(32, base_dim), nn.GELU(),
+            nn.Conv2d(base_dim, base_dim, 3, stride=2, padding=1), nn.GroupNorm(32, base_dim), nn.GELU())
+        self.to_stage2 = nn.Sequential(
+            nn.Conv2d(base_dim, base_dim, 3, stride=2, padding=1), nn.GroupNorm(32, base_dim), nn.GELU())
+
+    @staticmethod
+    def _down(feat, conv, gn):
+        """feat: (B, C, H, W) with channels-last memory (what XrayConditioningModule returns) or any strides -> same, halved."""
+        B, C, H, W = feat.shape
+        f = feat.float()
+        y = ConvGnGelu.apply(f, conv.weight, conv.bias, gn.weight, gn.bias, (B, C, H, W, 3, 2, 1, tuple(f.stride())), gn.num_groups)
+        Ho, Wo = K.conv2d_out(H, 3, 2, 1), K.conv2d_out(W, 3, 2, 1)
+        return y.view(B, Ho, Wo, conv.weight.shape[0]).permute(0, 3, 1, 2)
+
+    def forward(self, xrays, stage=1):
+        batch_size = xrays.shape[0]
+        dummy_t = torch.zeros(batch_size, 256, device=xrays.device)
+        xray_context, time_xray_cond, feats = self.xray_encoder(xrays, dummy_t)
+        if stage == 1:
+            feats = self._down(feats, self.to_stage1[0], self.to_stage1[1])
+            feats = self._down(feats, self.to_stage1[3], self.to_stage1[4])
+        elif stage == 2:
+            feats = self._down(feats, self.to_stage2[0], self.to_stage2[1])
+        return feats, time_xray_cond, xray_context
+
+
+class Stage1Base64(nn.Module):
+    """reference: direct_regression/progressive_cascade/model_progressive.py:86-150 (stage 1 of the cascade: 64^3 base volume)"""
+
+    def __init__(self, volume_size=(64, 64, 64), xray_img_size=512, voxel_dim=256, vit_depth=4, num_heads=4, xray_feature_dim=512):
+        super().__init__()
+        self.volume_size = volume_size
+        self.xray_encoder = MultiScaleXrayEncoder(img_size=xray_img_size, in_channels=1, base_dim=xray_feature_dim, num_views=2)
+        self.vit_backbone = HybridViT3D(volume_size=volume_size, in_channels=1, voxel_dim=voxel_dim, depth=vit_depth,
+                                        num_heads=num_heads, context_dim=xray_feature_dim, cond_dim=1024, use_prev_stage=False)
+        D, H, W = volume_size
+        self.initial_volume = nn.Parameter(torch.randn(1, 1, D, H, W) * 0.01)
+
+    def forward(self, xrays):
+        batch_size = xrays.shape[0]
+        feats, time_xray_cond, _ = self.xray_encoder(xrays, stage=1)
+        x = self.initial_volume.expand(batch_size, -1, -1, -1, -1)
+        return self.vit_backbone(x=x, context=feats.flatten(2).transpose(1, 2), cond=time_xray_cond, prev_stage_embed=None)

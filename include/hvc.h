@@ -300,7 +300,8 @@ int hvc_im2col2d_split(const float* x, const hvc_conv2d_geom* geom, void* out, v
 int hvc_col2im2d(const void* dcols, const hvc_conv2d_geom* geom, float* dx, void* stream);
 /* y = act(norm(x) * w + b) on f32 x [B, V, C] channels-last with `groups` groups per sample: activation 0 = SiLU (GroupNorm+SiLU
  * of the voxel embed; hvc_groupnorm_silu_* are the activation-0 forms), 1 = ReLU (BatchNorm2d+ReLU: B = 1, V = all rows,
- * groups = C, diagnostic_losses.py:81-93).  stats_given: mean/rstd [B, groups] are inputs (eval-mode BatchNorm) instead of outputs.
+ * groups = C, diagnostic_losses.py:81-93), 2 = exact-erf GELU (GroupNorm+GELU of MultiScaleXrayEncoder.to_stage1/2,
+ * progressive_cascade/model_progressive.py:38-52).  stats_given: mean/rstd [B, groups] are inputs (eval-mode BatchNorm) instead of outputs.
  * Backward: stats_frozen = 1 treats mean/rstd as constants.  Scratch sizes as for hvc_groupnorm_silu_*. */
 int hvc_norm_act_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C, int32_t groups,
                      int32_t activation, int32_t stats_given, void* y, int32_t y_is_bf16, float* mean, float* rstd,

@@ -90,3 +90,31 @@ def direct_regression_loss(pred: Tensor, target: Tensor, l1_weight: float = 1.0,
     l1 = F.l1_loss(pred, target)
     ss = ssim_loss(pred, target)
     return {"total_loss": l1_weight * l1 + ssim_weight * ss, "l1_loss": l1, "ssim_loss": ss}
+
+
+def multi_scale_xray_encoder(xrays: Tensor, sd: StateDict, pfx: str = "", stage: int = 1, training: bool = True,
+                             new_stats: Optional[dict] = None):
+    """MultiScaleXrayEncoder.forward, progressive_cascade/model_progressive.py:57-83 -> (features, time_xray_cond, xray_context)."""
+    B = xrays.shape[0]
+    dummy_t = torch.zeros(B, 256, device=xrays.device, dtype=xrays.dtype)                        # :70
+    ctx, cond, feats = xray_conditioning(xrays, dummy_t, sd, pfx + "xray_encoder.", training, new_stats)   # :73
+
+    def down(x, branch, ci, gi):                                                                  # Conv2d(s2) -> GroupNorm(32) -> GELU, :38-52
+        x = F.conv2d(x, sd[f"{pfx}{branch}.{ci}.weight"], sd[f"{pfx}{branch}.{ci}.bias"], stride=2, padding=1)
+        x = F.group_norm(x, 32, sd[f"{pfx}{branch}.{gi}.weight"], sd[f"{pfx}{branch}.{gi}.bias"], 1e-5)
+        return F.gelu(x)
+
+    if stage == 1:                                                                                # :76-78
+        feats = down(down(feats, "to_stage1", 0, 1), "to_stage1", 3, 4)
+    elif stage == 2:                                                                              # :79-81
+        feats = down(feats, "to_stage2", 0, 1)
+    return feats, cond, ctx
+
+
+def stage1_base64(xrays: Tensor, sd: StateDict, cfg: V.BackboneConfig, training: bool = True, attn_chunk: Optional[int] = None) -> Tensor:
+    """Stage1Base64.forward, progressive_cascade/model_progressive.py:125-150 (dropout off in the backbone)."""
+    B = xrays.shape[0]
+    feats, cond, _ = multi_scale_xray_encoder(xrays, sd, "xray_encoder.", 1, training)
+    x = sd["initial_volume"].expand(B, -1, -1, -1, -1)
+    bsd = {k[len("vit_backbone."):]: v for k, v in sd.items() if k.startswith("vit_backbone.")}
+    return V.backbone(x, feats.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)

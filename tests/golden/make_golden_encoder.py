@@ -19,6 +19,8 @@ sys.path.insert(0, os.path.join(REF, "direct_regression"))
 
 from models.diagnostic_losses import XrayConditioningModule  # noqa: E402
 from model_direct import DirectCTRegression  # noqa: E402
+sys.path.insert(0, os.path.join(REF, "direct_regression", "progressive_cascade"))
+from model_progressive import MultiScaleXrayEncoder, Stage1Base64  # noqa: E402
 
 
 def grads(mod, outs_and_rs, leaves):
@@ -28,6 +30,18 @@ def grads(mod, outs_and_rs, leaves):
     gs = torch.autograd.grad(loss, params + leaves, allow_unused=True)
     pg = {n: (g if g is not None else torch.zeros_like(p)) for n, g, p in zip(names, gs, params)}
     return pg, list(gs[len(params):])
+
+
+def randomise_adaln(m, seed):
+    ga = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "adaln.linear" in n:
+                p.copy_(torch.randn(p.shape, generator=ga) * 0.02)
+
+
+def weight_checksum(m):
+    return {k: float(v.double().sum()) for k, v in m.state_dict().items() if v.is_floating_point()}
 
 
 def main():
@@ -65,16 +79,49 @@ def main():
     for mod in m.modules():
         if isinstance(mod, torch.nn.Dropout):
             mod.p = 0.0
-    with torch.no_grad():
-        for n, p in m.named_parameters():
-            if "adaln.linear" in n:
-                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
-    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    randomise_adaln(m, 102)
+    wsum = weight_checksum(m)
     xr = torch.rand(2, 2, 1, 64, 64, generator=g) * 2 - 1
     y = m(xr)
     r = torch.randn(y.shape, generator=g)
     pg, _ = grads(m, [(y, r)], [])
-    out["direct"] = dict(kwargs=kw, sd=sd0, xrays=xr, y=y.detach(), r=r, pgrad={k: v.bfloat16() for k, v in pg.items()})   # gradients are compared by cosine: bf16 storage
+    # weights are not stored: the drop-in modules are built in the reference's order, so torch.manual_seed(seed) + the same
+    # AdaLN re-randomisation reproduces them bit for bit (checked through `wsum`); gradients are compared by cosine: bf16 storage
+    out["direct"] = dict(kwargs=kw, seed=2, adaln_seed=102, wsum=wsum, xrays=xr, y=y.detach(), r=r,
+                         pgrad={k: v.bfloat16() for k, v in pg.items()})
+    # MultiScaleXrayEncoder (cascade): the three stage branches, gradients through stage 1
+    torch.manual_seed(3)
+    ms = MultiScaleXrayEncoder(img_size=128, in_channels=1, base_dim=64, num_views=2).train()
+    sd0 = {k: v.clone() for k, v in ms.state_dict().items()}
+    ms_wsum = weight_checksum(ms)
+    xr = torch.rand(2, 2, 1, 128, 128, generator=g) * 2 - 1
+    res = {}
+    for stage in (1, 2, 3):
+        ms.load_state_dict(sd0)
+        f, c, x = ms(xr, stage=stage)
+        res[stage] = dict(feats=f.detach().clone(), cond=c.detach().clone(), ctx=x.detach().clone())
+        if stage == 1:
+            r = torch.randn(f.shape, generator=g)
+            pg, _ = grads(ms, [(f, r), (c, torch.ones_like(c) * 0.01)], [])
+            res["r1"], res["pgrad1"] = r, {k: v.bfloat16() for k, v in pg.items()}
+    out["multiscale"] = dict(seed=3, wsum=ms_wsum, xrays=xr, **{f"stage{k}": v for k, v in res.items() if isinstance(k, int)},
+                             r1=res["r1"], pgrad1=res["pgrad1"])
+
+    # Stage1Base64 (cascade stage 1), small
+    torch.manual_seed(4)
+    kw = dict(volume_size=(32, 32, 32), xray_img_size=128, voxel_dim=64, vit_depth=1, num_heads=1, xray_feature_dim=64)
+    m = Stage1Base64(**kw).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    randomise_adaln(m, 104)
+    wsum = weight_checksum(m)
+    xr = torch.rand(2, 2, 1, 128, 128, generator=g) * 2 - 1
+    y = m(xr)
+    r = torch.randn(y.shape, generator=g)
+    pg, _ = grads(m, [(y, r)], [])
+    out["stage1"] = dict(kwargs=kw, seed=4, adaln_seed=104, wsum=wsum, xrays=xr, y=y.detach(), r=r,
+                         pgrad={k: v.bfloat16() for k, v in pg.items()})
     torch.save(out, os.path.join(HERE, "encoder.pt"))
     print({k: list(v.keys()) for k, v in out.items()})
 

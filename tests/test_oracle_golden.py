@@ -206,17 +206,46 @@ def test_encoder_oracle_matches_reference_fixtures():
 
 
 def test_direct_model_oracle_matches_reference_fixture():
+    import hybrid_vit_cascade_b200 as hvc
+    from conftest import rebuild_from_seed
     from oracle import encoder_oracle as E
     c = _enc_gold()["direct"]
     kw = c["kwargs"]
     cfg = O.BackboneConfig(volume_size=kw["volume_size"], in_channels=1, voxel_dim=kw["voxel_dim"], depth=kw["vit_depth"],
                            num_heads=kw["num_heads"], context_dim=kw["xray_feature_dim"], cond_dim=1024)
-    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in c["sd"].items()}
+    sd0 = rebuild_from_seed(hvc.DirectCTRegression, c).state_dict()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
     y = E.direct_ct_regression(c["xrays"], sd, cfg, training=True)
     assert O.max_rel(y, c["y"]) <= 2e-6
     (y * c["r"]).sum().backward()
     for k, g in c["pgrad"].items():
         if float(g.float().abs().max()) > 0:
+            assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
+
+
+def test_cascade_stage1_oracle_matches_reference_fixtures():
+    """MultiScaleXrayEncoder (all three stage branches) and Stage1Base64, progressive_cascade/model_progressive.py:16-150."""
+    import hybrid_vit_cascade_b200 as hvc
+    from conftest import rebuild_from_seed
+    from oracle import encoder_oracle as E
+    c = _enc_gold()["multiscale"]
+    sd0 = rebuild_from_seed(hvc.MultiScaleXrayEncoder, c, img_size=128, in_channels=1, base_dim=64, num_views=2).state_dict()
+    for stage in (1, 2, 3):
+        with torch.no_grad():
+            f, cond, ctx = E.multi_scale_xray_encoder(c["xrays"], sd0, "", stage, training=True)
+        ref = c[f"stage{stage}"]
+        assert O.max_rel(f, ref["feats"]) <= 2e-6 and O.max_rel(cond, ref["cond"]) <= 2e-6 and O.max_rel(ctx, ref["ctx"]) <= 2e-6
+    c = _enc_gold()["stage1"]
+    kw = c["kwargs"]
+    cfg = O.BackboneConfig(volume_size=kw["volume_size"], in_channels=1, voxel_dim=kw["voxel_dim"], depth=kw["vit_depth"],
+                           num_heads=kw["num_heads"], context_dim=kw["xray_feature_dim"], cond_dim=1024)
+    sd0 = rebuild_from_seed(hvc.Stage1Base64, c).state_dict()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd0.items()}
+    y = E.stage1_base64(c["xrays"], sd, cfg, training=True)
+    assert O.max_rel(y, c["y"]) <= 2e-6
+    (y * c["r"]).sum().backward()
+    for k, g in c["pgrad"].items():
+        if float(g.float().abs().max()) > 1e-6:
             assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
 
 
