@@ -49,6 +49,11 @@ WORKLOADS = {
     "direct64_model": dict(volume=(64, 64, 64), token_grid="reference", voxel_dim=256, depth=4, heads=4, ctx_hw=64, ctx_dim=512,
                            cond_dim=1024, batch=8, full_model=True, xray=512,
                            desc="DirectCTRegression 64^3: 2 x 512^2 X-rays -> encoder -> 3D ViT (4096 tokens, 4096 ctx tokens)"),
+    # the whole Stage2Refiner128 (model_progressive.py:153-215): 64^3 volume -> trilinear x2 -> Conv3d(1->32)+GroupNorm+GELU -> refiner
+    # ViT -> residual blend; the stage-1 volume and the encoder features are inputs (stage 1 is frozen in the reference trainer)
+    "stage2_model": dict(volume=(128, 128, 128), token_grid="conv", in_channels=32, voxel_dim=256, depth=6, heads=8, ctx_hw=32,
+                         ctx_dim=512, cond_dim=1024, batch=2, stage2_wrapper=True,
+                         desc="Stage2Refiner128: 64^3 volume -> upsample + Conv3d/GN/GELU -> ViT 128^3 (32768 tokens, 1024 ctx tokens, d=32) -> blend"),
     "stage3": dict(volume=(256, 256, 256), token_grid="reference", in_channels=32, voxel_dim=256, depth=8, heads=8, ctx_hw=64,
                    ctx_dim=512, cond_dim=1024, batch=2, checkpoint=True,
                    desc="progressive_cascade stage 3 ViT 256^3 (32 ch in, 32768 tokens, 4096 ctx tokens, d=32, checkpointed)"),
@@ -189,7 +194,10 @@ def run_b200(args, w):
     torch.manual_seed(0)
     cin = w.get("in_channels", 1)
     full = bool(w.get("full_model"))
-    model = hvc.DirectCTRegression(volume_size=w["volume"], xray_img_size=w["xray"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"],
+    wrap2 = bool(w.get("stage2_wrapper"))
+    model = hvc.Stage2Refiner128(volume_size=w["volume"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"], num_heads=w["heads"],
+                                 xray_feature_dim=w["ctx_dim"], token_grid=w["token_grid"]).to(dev) if wrap2 else \
+        hvc.DirectCTRegression(volume_size=w["volume"], xray_img_size=w["xray"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"],
                                    num_heads=w["heads"], xray_feature_dim=w["ctx_dim"], token_grid=w["token_grid"]).to(dev) if full else \
         hvc.HybridViT3D(volume_size=w["volume"], in_channels=cin, voxel_dim=w["voxel_dim"], depth=w["depth"],
                             num_heads=w["heads"], context_dim=w["ctx_dim"], cond_dim=w["cond_dim"],
@@ -218,7 +226,9 @@ def run_b200(args, w):
     cond = torch.randn(B, w["cond_dim"], device=dev, generator=g)
     target = torch.rand(B, 1, D, H, W, device=dev, generator=g) * 2 - 1
     # cascade refiners: the ViT input is the (B, 32, D, H, W) output of the stage's upsample conv; its gradient is needed
-    vol_in = None if direct else (torch.randn(B, cin, D, H, W, device=dev, generator=g) * 0.5).requires_grad_(True)
+    vol_in = None if (direct or full) else \
+        (torch.rand(B, 1, D // 2, H // 2, W // 2, device=dev, generator=g) * 2 - 1) if wrap2 else \
+        (torch.randn(B, cin, D, H, W, device=dev, generator=g) * 0.5).requires_grad_(True)
     use_ckpt = bool(w.get("checkpoint"))
     if args.loss == "direct":       # DirectRegressionLoss: L1 + 0.5 (1 - SSIM3D), model_direct.py:110-131 / config_direct.json
         crit = hvc.DirectRegressionLoss(1.0, 0.5)
@@ -235,6 +245,15 @@ def run_b200(args, w):
         gb.reset()
         if full:
             out = model(feat_)
+            loss = loss_fn(out, target_)
+            loss.backward()
+            gb.finish()
+            if args.clip > 0:
+                torch.nn.utils.clip_grad_norm_(params, args.clip, foreach=True)
+            opt.step()
+            return loss
+        if wrap2:
+            out = model(vol_in, feat_, cond_)
             loss = loss_fn(out, target_)
             loss.backward()
             gb.finish()

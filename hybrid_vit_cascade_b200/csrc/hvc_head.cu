@@ -53,10 +53,11 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float* __restrict__
   }
 }
 
-struct UpGeom { int B, Di, Hi, Wi, Do, Ho, Wo; float sd, sh, sw; };
+struct UpGeom { int B, Di, Hi, Wi, Do, Ho, Wo; float sd, sh, sw; float half; };   // half = 0.5 for align_corners=False, 0 for True
 
-__device__ __forceinline__ void up_coord(int o, float scale, int in, int& i0, int& i1, float& l1) {
-  const float src = scale * o;
+// align_corners=True: src = o * (in-1)/(out-1); align_corners=False: src = max((o + 0.5) * in/out - 0.5, 0)  (PyTorch's area_pixel rule)
+__device__ __forceinline__ void up_coord(int o, float scale, float half, int in, int& i0, int& i1, float& l1) {
+  const float src = fmaxf(scale * (o + half) - half, 0.f);
   i0 = static_cast<int>(src);
   if (i0 > in - 1) i0 = in - 1;
   i1 = i0 + (i0 < in - 1 ? 1 : 0);
@@ -74,9 +75,9 @@ __global__ void __launch_bounds__(256) upsample_fwd_kernel(const float* __restri
   const int b = (int)(t / g.Do);
   int d0, d1, h0, h1, w0, w1;
   float ld, lh, lw;
-  up_coord(d, g.sd, g.Di, d0, d1, ld);
-  up_coord(h, g.sh, g.Hi, h0, h1, lh);
-  up_coord(w, g.sw, g.Wi, w0, w1, lw);
+  up_coord(d, g.sd, g.half, g.Di, d0, d1, ld);
+  up_coord(h, g.sh, g.half, g.Hi, h0, h1, lh);
+  up_coord(w, g.sw, g.half, g.Wi, w0, w1, lw);
   const float* p = v + (long long)b * g.Di * g.Hi * g.Wi;
   auto at = [&](int dd, int hh, int ww) { return __ldg(p + ((long long)dd * g.Hi + hh) * g.Wi + ww); };
   const float c00 = at(d0, h0, w0) * (1.f - lw) + at(d0, h0, w1) * lw;
@@ -98,9 +99,9 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
   const int b = (int)(t / g.Do);
   int d0, d1, h0, h1, w0, w1;
   float ld, lh, lw;
-  up_coord(d, g.sd, g.Di, d0, d1, ld);
-  up_coord(h, g.sh, g.Hi, h0, h1, lh);
-  up_coord(w, g.sw, g.Wi, w0, w1, lw);
+  up_coord(d, g.sd, g.half, g.Di, d0, d1, ld);
+  up_coord(h, g.sh, g.half, g.Hi, h0, h1, lh);
+  up_coord(w, g.sw, g.half, g.Wi, w0, w1, lw);
   const float go = __ldg(dout + idx);
   float* p = dv + (long long)b * g.Di * g.Hi * g.Wi;
   auto add = [&](int dd, int hh, int ww, float wt) { atomicAdd(p + ((long long)dd * g.Hi + hh) * g.Wi + ww, go * wt); };
@@ -134,12 +135,18 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const float* __restrict_
   *reinterpret_cast<float4*>(out + i) = s;
 }
 
-static UpGeom make_up(int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo) {
+static UpGeom make_up(int B, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int align_corners = 1) {
   UpGeom g;
   g.B = B; g.Di = Di; g.Hi = Hi; g.Wi = Wi; g.Do = Do; g.Ho = Ho; g.Wo = Wo;
-  g.sd = Do > 1 ? (float)(Di - 1) / (float)(Do - 1) : 0.f;
-  g.sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
-  g.sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  if (align_corners) {
+    g.sd = Do > 1 ? (float)(Di - 1) / (float)(Do - 1) : 0.f;
+    g.sh = Ho > 1 ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+    g.sw = Wo > 1 ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+    g.half = 0.f;
+  } else {
+    g.sd = (float)Di / (float)Do; g.sh = (float)Hi / (float)Ho; g.sw = (float)Wi / (float)Wo;
+    g.half = 0.5f;
+  }
   return g;
 }
 
@@ -177,6 +184,29 @@ extern "C" int hvc_upsample3d_bwd(const float* dout, float* dv, int32_t B, int32
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   HVC_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)B * Di * Hi * Wi, st));
   const UpGeom g = make_up(B, Di, Hi, Wi, Do, Ho, Wo);
+  const long long total = (long long)B * Do * Ho * Wo;
+  upsample_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dout, dv, g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+// trilinear resize with either corner convention (align_corners = 0: nn.Upsample / F.interpolate of the cascade's stage wrappers,
+// progressive_cascade/model_progressive.py:169,211-212)
+extern "C" int hvc_interp3d_fwd(const float* v, float* out, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho,
+                                int32_t Wo, int32_t align_corners, void* stream) {
+  HVC_CHECK_ARG(v && out && B > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "hvc_interp3d_fwd: bad arguments");
+  const UpGeom g = make_up(B, Di, Hi, Wi, Do, Ho, Wo, align_corners);
+  const long long total = (long long)B * Do * Ho * Wo;
+  upsample_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(v, out, g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+extern "C" int hvc_interp3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho,
+                                int32_t Wo, int32_t align_corners, void* stream) {
+  HVC_CHECK_ARG(dout && dv && B > 0 && Di > 0 && Hi > 0 && Wi > 0 && Do > 0 && Ho > 0 && Wo > 0, "hvc_interp3d_bwd: bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  HVC_CUDA(cudaMemsetAsync(dv, 0, sizeof(float) * (size_t)B * Di * Hi * Wi, st));
+  const UpGeom g = make_up(B, Di, Hi, Wi, Do, Ho, Wo, align_corners);
   const long long total = (long long)B * Do * Ho * Wo;
   upsample_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dout, dv, g);
   HVC_LAUNCH_CHECK();

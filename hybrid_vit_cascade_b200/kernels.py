@@ -648,3 +648,22 @@ def ssim_l1_bwd(pred, target, filtered, c_ssim, c_l1, window=11, upstream=None):
     _lib.check(_lib.lib().hvc_ssim_l1_bwd(_ptr(pred), _ptr(target), _ptr(filtered), B, D, H, W, window, C.c_float(c_ssim), C.c_float(c_l1),
                                           _ptr(upstream), _ptr(scratch), _ptr(dpred), _stream()), "hvc_ssim_l1_bwd")
     return dpred
+
+
+# ------------------------------------------------------------------ cascade stage wrappers
+
+def interp3d_fwd(v, B, grid, size, align_corners):
+    """v f32 [B, Di,Hi,Wi] contiguous -> f32 [B, Do,Ho,Wo] trilinear (either corner convention)."""
+    _need_cuda(v)
+    assert v.dtype == torch.float32 and v.is_contiguous()
+    out = torch.empty(B, *size, device=v.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_interp3d_fwd(_ptr(v), _ptr(out), B, *grid, *size, int(align_corners), _stream()), "hvc_interp3d_fwd")
+    return out
+
+
+def interp3d_bwd(dout, B, grid, size, align_corners):
+    _need_cuda(dout)
+    assert dout.dtype == torch.float32 and dout.is_contiguous()
+    dv = torch.empty(B, *grid, device=dout.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_interp3d_bwd(_ptr(dout), _ptr(dv), B, *grid, *size, int(align_corners), _stream()), "hvc_interp3d_bwd")
+    return dv

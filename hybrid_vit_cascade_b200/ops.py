@@ -419,6 +419,7 @@ class VoxelEmbed(Function):
         tokens = K.add_pos(z.view(xB, n), pos_embed.contiguous().view(-1), B)
         ctx.save_for_backward(*saved, *params)
         ctx.meta = (plan, geoms, xB, B, tuple(x.shape), len(saved), n, Cout)
+        ctx.in_strides = tuple(xin.stride())
         return tokens.view(B * Dd * Hd * Wd, Cout)
 
     @staticmethod
@@ -462,7 +463,9 @@ class VoxelEmbed(Function):
                     K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, d_act, strides)
                     dz = d_act
                 else:
-                    dx1 = torch.empty((xB,) + tuple(xshape[1:]), device=dtok.device, dtype=torch.float32)
+                    # same memory layout as the forward input (e.g. the channels-last view a stage wrapper hands over)
+                    dx1 = torch.empty_strided((xB,) + tuple(xshape[1:]), ctx.in_strides, device=dtok.device, dtype=torch.float32) \
+                        if xB == B else torch.empty((xB,) + tuple(xshape[1:]), device=dtok.device, dtype=torch.float32)
                     K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, dx1, tuple(dx1.stride()))
                     if xB != B:
                         dx = torch.zeros(xshape, device=dtok.device, dtype=torch.float32)

@@ -305,3 +305,84 @@ class Stage1Base64(nn.Module):
         feats, time_xray_cond, _ = self.xray_encoder(xrays, stage=1)
         x = self.initial_volume.expand(batch_size, -1, -1, -1, -1)
         return self.vit_backbone(x=x, context=feats.flatten(2).transpose(1, 2), cond=time_xray_cond, prev_stage_embed=None)
+
+
+# ------------------------------------------------------------------ cascade stage 2 (model_progressive.py:153-215)
+
+class Interp3d(Function):
+    """F.interpolate(x, size, mode="trilinear", align_corners=...) on (B, 1, D, H, W)."""
+
+    @staticmethod
+    def forward(ctx, x, size, align_corners):
+        B, C, D, H, W = x.shape
+        ctx.meta = (B * C, (D, H, W), tuple(size), bool(align_corners), x.dtype, tuple(x.shape))
+        return K.interp3d_fwd(x.float().contiguous().view(B * C, D, H, W), B * C, (D, H, W), tuple(size), align_corners).view(B, C, *size)
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, grid, size, ac, dt, x_shape = ctx.meta
+        dv = K.interp3d_bwd(dy.float().contiguous().view(n, *size), n, grid, size, ac)
+        return dv.view(x_shape).to(dt), None, None
+
+
+class Conv3dGnGelu(Function):
+    """gelu(group_norm(conv3d(x)))  -- Conv3d(k3, pad 1) + GroupNorm + GELU of the stage wrappers (model_progressive.py:170-172).
+    x: (B, Cin, D, H, W) any strides; returns the channels-last buffer viewed as (B, Cout, D, H, W), which is the layout the
+    refiner ViT's voxel embedding gathers from directly."""
+
+    @staticmethod
+    def forward(ctx, x, conv_w, conv_b, gn_w, gn_b, groups):
+        B, Cin, D, H, W = x.shape
+        Cout = conv_w.shape[0]
+        xf = x.float()
+        cols = K.im2col3d(xf, B, Cin, D, H, W, 1, tuple(xf.stride()))
+        z = K.gemm(cols, ops.w16(conv_w, pad_to=cols.shape[1]), bias=conv_b, epilogue=K.EPI_F32)            # [B*V, Cout]
+        V = D * H * W
+        y, mean, rstd = K.norm_act_fwd(z, gn_w, gn_b, B, V, Cout, groups, K.ACT_GELU_ERF, torch.float32)
+        ctx.save_for_backward(cols, z, mean, rstd, conv_w, gn_w, gn_b)
+        ctx.meta = (B, Cin, D, H, W, Cout, groups, tuple(x.shape), tuple(xf.stride()))
+        return y.view(B, D, H, W, Cout).permute(0, 4, 1, 2, 3)
+
+    @staticmethod
+    def backward(ctx, dy):
+        cols, z, mean, rstd, conv_w, gn_w, gn_b = ctx.saved_tensors
+        B, Cin, D, H, W, Cout, groups, x_shape, x_strides = ctx.meta
+        V = D * H * W
+        dy_cl = dy.float().permute(0, 2, 3, 4, 1).contiguous().view(B * V, Cout)       # a no-op when dy already is channels-last
+        dz, dgn_w, dgn_b = K.norm_act_bwd(dy_cl, z, gn_w, gn_b, mean, rstd, B, V, Cout, groups, K.ACT_GELU_ERF)
+        dz16 = K.cast_bf16(dz)
+        dconv_b = K.colsum_bf16(dz16)
+        dconv_w = ops._wgrad(dz16, cols)[:, :Cin * 27].reshape(conv_w.shape)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dcols = ops._dgrad(dz16, ops.w16(conv_w, pad_to=cols.shape[1]))
+            dx = torch.empty_strided(x_shape, x_strides, device=dy.device, dtype=torch.float32)
+            K.col2im3d(dcols, B, Cin, D, H, W, 1, dx, x_strides)
+        return dx, dconv_w, dconv_b, dgn_w, dgn_b, None
+
+
+class Stage2Refiner128(nn.Module):
+    """reference: direct_regression/progressive_cascade/model_progressive.py:153-215 (64^3 -> 128^3 refinement)"""
+
+    def __init__(self, volume_size=(128, 128, 128), voxel_dim=256, vit_depth=6, num_heads=8, xray_feature_dim=512, token_grid="reference"):
+        super().__init__()
+        self.volume_size = volume_size
+        self.upsample_from_64 = nn.Sequential(nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False),
+                                              nn.Conv3d(1, 32, 3, padding=1), nn.GroupNorm(8, 32), nn.GELU())
+        self.vit_refiner = HybridViT3D(volume_size=volume_size, in_channels=32, voxel_dim=voxel_dim, depth=vit_depth,
+                                       num_heads=num_heads, context_dim=xray_feature_dim, cond_dim=1024, use_prev_stage=False,
+                                       token_grid=token_grid)
+        self.residual_weight = nn.Parameter(torch.ones(1) * 0.5)
+
+    def forward(self, volume_64, xray_features_2d, time_xray_cond):
+        """volume_64: (B, 1, D/2, H/2, W/2); xray_features_2d: (B, C, h, w); time_xray_cond: (B, 1024) -> (B, 1, D, H, W)"""
+        D2, H2, W2 = volume_64.shape[2:]
+        up = Interp3d.apply(volume_64, (2 * D2, 2 * H2, 2 * W2), False)          # nn.Upsample(scale_factor=2, align_corners=False), :169
+        conv, gn = self.upsample_from_64[1], self.upsample_from_64[2]
+        x = Conv3dGnGelu.apply(up, conv.weight, conv.bias, gn.weight, gn.bias, gn.num_groups)
+        refinement = self.vit_refiner(x=x, context=xray_features_2d.flatten(2).transpose(1, 2), cond=time_xray_cond,
+                                      prev_stage_embed=None)
+        # :211-213 -- F.interpolate(volume_64, size=volume_size, align_corners=False) is the same resize as `up` when volume_size is
+        # twice the input (the only way the reference runs); the blend with the learned scalar is a two-op elementwise epilogue
+        base = up if tuple(self.volume_size) == tuple(up.shape[2:]) else Interp3d.apply(volume_64, tuple(self.volume_size), False)
+        return base + self.residual_weight * refinement

@@ -253,6 +253,12 @@ int hvc_upsample3d_fwd(const float* v, float* out, int32_t B, int32_t Di, int32_
                        int32_t Ho, int32_t Wo, void* stream);
 int hvc_upsample3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do,
                        int32_t Ho, int32_t Wo, void* stream);
+/* The same with either corner convention: align_corners = 0 is nn.Upsample(scale_factor=2, mode="trilinear") / F.interpolate(...,
+ * align_corners=False) of the cascade's stage wrappers (progressive_cascade/model_progressive.py:169,211-212). */
+int hvc_interp3d_fwd(const float* v, float* out, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho,
+                     int32_t Wo, int32_t align_corners, void* stream);
+int hvc_interp3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho,
+                     int32_t Wo, int32_t align_corners, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * fp32 verification mode (the 1e-4 fp32 parity bar): fp32-accurate products on the bf16 tensor cores.

@@ -118,3 +118,15 @@ def stage1_base64(xrays: Tensor, sd: StateDict, cfg: V.BackboneConfig, training:
     x = sd["initial_volume"].expand(B, -1, -1, -1, -1)
     bsd = {k[len("vit_backbone."):]: v for k, v in sd.items() if k.startswith("vit_backbone.")}
     return V.backbone(x, feats.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)
+
+
+def stage2_refiner128(volume_64: Tensor, xray_features_2d: Tensor, cond: Tensor, sd: StateDict, cfg: V.BackboneConfig,
+                      attn_chunk: Optional[int] = None) -> Tensor:
+    """Stage2Refiner128.forward, progressive_cascade/model_progressive.py:193-215 (dropout off in the refiner ViT)."""
+    x = F.interpolate(volume_64, scale_factor=2, mode="trilinear", align_corners=False)            # nn.Upsample, :169
+    x = F.conv3d(x, sd["upsample_from_64.1.weight"], sd["upsample_from_64.1.bias"], padding=1)     # :170
+    x = F.gelu(F.group_norm(x, 8, sd["upsample_from_64.2.weight"], sd["upsample_from_64.2.bias"], 1e-5))   # :171-172
+    bsd = {k[len("vit_refiner."):]: v for k, v in sd.items() if k.startswith("vit_refiner.")}
+    refinement = V.backbone(x, xray_features_2d.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)   # :203-208
+    up = F.interpolate(volume_64, size=tuple(cfg.volume_size), mode="trilinear", align_corners=False)     # :211-212
+    return up + sd["residual_weight"] * refinement                                                 # :213

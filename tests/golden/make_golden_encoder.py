@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(REF, "direct_regression"))
 from models.diagnostic_losses import XrayConditioningModule  # noqa: E402
 from model_direct import DirectCTRegression  # noqa: E402
 sys.path.insert(0, os.path.join(REF, "direct_regression", "progressive_cascade"))
-from model_progressive import MultiScaleXrayEncoder, Stage1Base64  # noqa: E402
+from model_progressive import MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128  # noqa: E402
 
 
 def grads(mod, outs_and_rs, leaves):
@@ -122,6 +122,23 @@ def main():
     pg, _ = grads(m, [(y, r)], [])
     out["stage1"] = dict(kwargs=kw, seed=4, adaln_seed=104, wsum=wsum, xrays=xr, y=y.detach(), r=r,
                          pgrad={k: v.bfloat16() for k, v in pg.items()})
+    # Stage2Refiner128 (cascade stage 2), small: 16^3 -> 32^3, 8 x 8 context tokens, two heads of 32
+    torch.manual_seed(5)
+    kw = dict(volume_size=(32, 32, 32), voxel_dim=64, vit_depth=1, num_heads=2, xray_feature_dim=64)
+    m = Stage2Refiner128(**kw).train()
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    randomise_adaln(m, 105)
+    wsum = weight_checksum(m)
+    v64 = (torch.rand(2, 1, 16, 16, 16, generator=g) * 2 - 1).requires_grad_(True)
+    feats = torch.randn(2, 64, 8, 8, generator=g).requires_grad_(True)
+    cond = torch.randn(2, 1024, generator=g).requires_grad_(True)
+    y = m(v64, feats, cond)
+    r = torch.randn(y.shape, generator=g)
+    pg, ig = grads(m, [(y, r)], [v64, feats, cond])
+    out["stage2"] = dict(kwargs=kw, seed=5, adaln_seed=105, wsum=wsum, volume_64=v64.detach(), feats=feats.detach(), cond=cond.detach(),
+                         y=y.detach(), r=r, pgrad={k: v.bfloat16() for k, v in pg.items()}, vgrad=ig[0], fgrad=ig[1], cgrad=ig[2])
     torch.save(out, os.path.join(HERE, "encoder.pt"))
     print({k: list(v.keys()) for k, v in out.items()})
 

@@ -171,3 +171,26 @@ def test_direct_regression_loss_golden():
     v = torch.rand(2, 1, 64, 64, 64, device="cuda") * 2 - 1
     res = crit(v, v.clone())
     assert abs(float(res["total_loss"].detach())) < 1e-5
+
+
+def test_cascade_stage2_refiner_golden():
+    """Stage2Refiner128 (model_progressive.py:153-215): trilinear x2 (align_corners=False) -> Conv3d(1->32)+GroupNorm+GELU -> refiner ViT
+    (32 input channels, heads of 32) -> base + residual_weight * refinement; forward, parameter and input gradients."""
+    import hybrid_vit_cascade_b200 as hvc
+    from conftest import rebuild_from_seed
+    c = _gold()["stage2"]
+    m = rebuild_from_seed(hvc.Stage2Refiner128, c).cuda().train()
+    hvc.set_dropout_policy("ignore")
+    try:
+        v64, feats, cond = (c[k].cuda().requires_grad_(True) for k in ("volume_64", "feats", "cond"))
+        y = m(v64, feats, cond)
+        assert y.shape == c["y"].shape
+        err = O.max_rel(y, c["y"])
+        assert err <= FWD_TOL, err
+        (y * c["r"].cuda()).sum().backward()
+        grads = {k: p.grad for k, p in m.named_parameters()}
+        _check_grads(grads, c["pgrad"], "stage2")
+        for a, b, n in ((v64.grad, c["vgrad"], "volume_64"), (feats.grad, c["fgrad"], "feats"), (cond.grad, c["cgrad"], "cond")):
+            assert O.cosine(a, b.cuda()) >= COS_TOL, (n, O.cosine(a, b.cuda()))
+    finally:
+        hvc.set_dropout_policy("apply")

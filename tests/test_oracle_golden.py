@@ -259,3 +259,24 @@ def test_direct_loss_oracle_matches_reference_fixture():
         assert abs(float(res["total_loss"]) - float(c["total"])) < 1e-6 and abs(float(res["ssim_loss"]) - float(c["ssim"])) < 1e-6
         res["total_loss"].backward()
         assert O.max_rel(pred.grad, c["dpred"]) < 1e-5, name
+
+
+def test_cascade_stage2_oracle_matches_reference_fixture():
+    """Stage2Refiner128, progressive_cascade/model_progressive.py:153-215."""
+    import hybrid_vit_cascade_b200 as hvc
+    from conftest import rebuild_from_seed
+    from oracle import encoder_oracle as E
+    c = _enc_gold()["stage2"]
+    kw = c["kwargs"]
+    cfg = O.BackboneConfig(volume_size=kw["volume_size"], in_channels=32, voxel_dim=kw["voxel_dim"], depth=kw["vit_depth"],
+                           num_heads=kw["num_heads"], context_dim=kw["xray_feature_dim"], cond_dim=1024)
+    sd0 = rebuild_from_seed(hvc.Stage2Refiner128, c).state_dict()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd0.items()}
+    v64 = c["volume_64"].clone().requires_grad_(True)
+    y = E.stage2_refiner128(v64, c["feats"], c["cond"], sd, cfg)
+    assert O.max_rel(y, c["y"]) <= 2e-6
+    (y * c["r"]).sum().backward()
+    assert O.max_rel(v64.grad, c["vgrad"]) <= 2e-5
+    for k, g in c["pgrad"].items():
+        if float(g.float().abs().max()) > 1e-6:
+            assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
