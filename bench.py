@@ -52,8 +52,13 @@ WORKLOADS = {
     # the whole Stage2Refiner128 (model_progressive.py:153-215): 64^3 volume -> trilinear x2 -> Conv3d(1->32)+GroupNorm+GELU -> refiner
     # ViT -> residual blend; the stage-1 volume and the encoder features are inputs (stage 1 is frozen in the reference trainer)
     "stage2_model": dict(volume=(128, 128, 128), token_grid="conv", in_channels=32, voxel_dim=256, depth=6, heads=8, ctx_hw=32,
-                         ctx_dim=512, cond_dim=1024, batch=2, stage2_wrapper=True,
+                         ctx_dim=512, cond_dim=1024, batch=2, stage_wrapper=2,
                          desc="Stage2Refiner128: 64^3 volume -> upsample + Conv3d/GN/GELU -> ViT 128^3 (32768 tokens, 1024 ctx tokens, d=32) -> blend"),
+    # the whole Stage3Refiner256 (model_progressive.py:218-315): 128^3 volume -> trilinear x2 -> Conv3d(1->32)+GN+GELU -> refiner ViT, plus
+    # the detail_enhancer CNN (Conv3d 1->64->32->1 at 256^3) and the three-way blend; no recomputation (fits the 180 GB)
+    "stage3_model": dict(volume=(256, 256, 256), token_grid="reference", in_channels=32, voxel_dim=256, depth=8, heads=8, ctx_hw=64,
+                         ctx_dim=512, cond_dim=1024, batch=2, stage_wrapper=3,
+                         desc="Stage3Refiner256: 128^3 volume -> upsample + Conv3d/GN/GELU -> ViT 256^3 (32768 tokens, 4096 ctx tokens, d=32) + detail_enhancer CNN -> blend"),
     "stage3": dict(volume=(256, 256, 256), token_grid="reference", in_channels=32, voxel_dim=256, depth=8, heads=8, ctx_hw=64,
                    ctx_dim=512, cond_dim=1024, batch=2, checkpoint=True,
                    desc="progressive_cascade stage 3 ViT 256^3 (32 ch in, 32768 tokens, 4096 ctx tokens, d=32, checkpointed)"),
@@ -86,6 +91,10 @@ def step_flops(w):
         x = w["xray"]
         enc = 2 * (2.0 * 49 * 64 * (x // 2) ** 2 + 2.0 * 576 * 128 * (x // 4) ** 2 + 2.0 * 1152 * w["ctx_dim"] * (x // 8) ** 2)
         f = dict(f, encoder=enc, total=f["total"] + enc)
+    if w.get("stage_wrapper"):  # stage wrapper convs at full resolution: Conv3d 1->32 (k3); stage 3 adds the detail CNN 1->64->32 (k3) ->1 (k1)
+        V = w["volume"][0] * w["volume"][1] * w["volume"][2]
+        wr = 2.0 * 27 * 32 * V + (2.0 * 27 * 64 * V + 2.0 * 1728 * 32 * V + 2.0 * 32 * V if w["stage_wrapper"] == 3 else 0.0)
+        f = dict(f, wrapper=wr, total=f["total"] + wr)
     return {k: 3.0 * v for k, v in f.items()}
 
 
@@ -194,8 +203,8 @@ def run_b200(args, w):
     torch.manual_seed(0)
     cin = w.get("in_channels", 1)
     full = bool(w.get("full_model"))
-    wrap2 = bool(w.get("stage2_wrapper"))
-    model = hvc.Stage2Refiner128(volume_size=w["volume"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"], num_heads=w["heads"],
+    wrap2 = bool(w.get("stage_wrapper"))
+    model = (hvc.Stage2Refiner128 if w.get("stage_wrapper") == 2 else hvc.Stage3Refiner256)(volume_size=w["volume"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"], num_heads=w["heads"],
                                  xray_feature_dim=w["ctx_dim"], token_grid=w["token_grid"]).to(dev) if wrap2 else \
         hvc.DirectCTRegression(volume_size=w["volume"], xray_img_size=w["xray"], voxel_dim=w["voxel_dim"], vit_depth=w["depth"],
                                    num_heads=w["heads"], xray_feature_dim=w["ctx_dim"], token_grid=w["token_grid"]).to(dev) if full else \

@@ -10,10 +10,10 @@ library or off sm_100 the modules raise.
 from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHeadSelfAttention,  # noqa: F401
                              SinusoidalTimeEmbedding, precision, set_dropout_policy, set_precision)
 from .hybrid_vit_backbone import HybridViT3D, HybridViTBlock3D  # noqa: F401
-from .xray_encoder import (DirectCTRegression, MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128,  # noqa: F401
+from .xray_encoder import (DirectCTRegression, MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128, Stage3Refiner256, ProgressiveCascadeModel,  # noqa: F401
                            XrayConditioningModule)
 from .losses import DirectRegressionLoss, compute_ssim_loss  # noqa: F401
 
 __all__ = ["AdaLNModulation", "MultiHeadCrossAttention", "MultiHeadSelfAttention", "SinusoidalTimeEmbedding",
-           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "MultiScaleXrayEncoder", "DirectCTRegression", "Stage1Base64", "Stage2Refiner128", "DirectRegressionLoss", "compute_ssim_loss", "set_dropout_policy", "set_precision",
+           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "MultiScaleXrayEncoder", "DirectCTRegression", "Stage1Base64", "Stage2Refiner128", "Stage3Refiner256", "ProgressiveCascadeModel", "DirectRegressionLoss", "compute_ssim_loss", "set_dropout_policy", "set_precision",
            "precision"]

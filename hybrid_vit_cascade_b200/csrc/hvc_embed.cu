@@ -88,6 +88,81 @@ __global__ void __launch_bounds__(256) col2im3d_kernel(const bf16* __restrict__ 
   dx[b * g.sb + c * g.sc + d * g.sd + h * g.sh + w * g.sw] = acc;
 }
 
+// ---- channels-last, tap-major variants (k = tap*Cin + c; sc == 1, Cin % 8 == 0) ----------------------------------------------
+// The cin-major column order above follows weight.view(Cout, Cin*27); on a channels-last input it makes both kernels touch 2 useful
+// bytes per 54-byte stride.  With the weight matrix permuted to [Cout, 27, Cin] instead, a patch row is 27 contiguous runs of Cin
+// channels: one thread moves 8 channels (a 16-byte store / load), a warp a whole 256-channel run.
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2col3d_cl_kernel(const TIn* __restrict__ x, bf16* __restrict__ cols, const Conv3dGeom g) {
+  const int c8n = g.Cin >> 3;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * 27 * c8n;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % c8n);
+  long long m = idx / c8n;
+  const int tap = (int)(m % 27); m /= 27;
+  const int kd = tap / 9, kh = (tap - kd * 9) / 3, kw = tap - kd * 9 - kh * 3;
+  const int ow = (int)(m % g.Wo); m /= g.Wo;
+  const int oh = (int)(m % g.Ho); m /= g.Ho;
+  const int od = (int)(m % g.Do);
+  const int b = (int)(m / g.Do);
+  const int id = od * g.stride - 1 + kd, ih = oh * g.stride - 1 + kh, iw = ow * g.stride - 1 + kw;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (id >= 0 && id < g.D && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+    const TIn* src = x + b * g.sb + id * g.sd + ih * g.sh + iw * g.sw + c8 * 8;
+    if constexpr (sizeof(TIn) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), c = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+    } else {
+      o = __ldg(reinterpret_cast<const uint4*>(src));
+    }
+  }
+  reinterpret_cast<uint4*>(cols)[idx] = o;
+}
+
+__global__ void __launch_bounds__(256) col2im3d_cl_kernel(const bf16* __restrict__ dcols, float* __restrict__ dx, const Conv3dGeom g) {
+  const int c8n = g.Cin >> 3;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)g.B * g.D * g.H * g.W * c8n;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % c8n);
+  long long t = idx / c8n;
+  const int w = (int)(t % g.W); t /= g.W;
+  const int h = (int)(t % g.H); t /= g.H;
+  const int d = (int)(t % g.D);
+  const int b = (int)(t / g.D);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    const int nd = d + 1 - kd;
+    if (nd < 0 || nd % g.stride) continue;
+    const int od = nd / g.stride;
+    if (od >= g.Do) continue;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int nh = h + 1 - kh;
+      if (nh < 0 || nh % g.stride) continue;
+      const int oh = nh / g.stride;
+      if (oh >= g.Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int nw = w + 1 - kw;
+        if (nw < 0 || nw % g.stride) continue;
+        const int ow = nw / g.stride;
+        if (ow >= g.Wo) continue;
+        const long long m = (((long long)b * g.Do + od) * g.Ho + oh) * g.Wo + ow;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(dcols + m * g.Kp + (kd * 9 + kh * 3 + kw) * g.Cin + c8 * 8));
+        const float2 p0 = unpack_bf16(v.x), p1 = unpack_bf16(v.y), p2 = unpack_bf16(v.z), p3 = unpack_bf16(v.w);
+        acc[0] += p0.x; acc[1] += p0.y; acc[2] += p1.x; acc[3] += p1.y;
+        acc[4] += p2.x; acc[5] += p2.y; acc[6] += p3.x; acc[7] += p3.y;
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(dx + b * g.sb + d * g.sd + h * g.sh + w * g.sw + c8 * 8);
+  dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 // ------------------------------------------------------------------ per-(batch, channel) sums over voxels
 // MODE 0: S1 = sum x,        S2 = sum x^2                          (GroupNorm forward statistics)
 // MODE 1: S1 = sum ds,       S2 = sum ds * xhat   with ds = dy * silu'(z), z = xhat*w + b   (backward)
@@ -289,6 +364,42 @@ extern "C" int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, floa
   if (rc) return rc;
   const long long total = (long long)g.B * g.Cin * g.D * g.H * g.W;
   col2im3d_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(dcols), dx, g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+static int check_cl_geom(const hvc_conv3d_geom* geom, const void* p, int elem_bytes) {
+  HVC_CHECK_ARG(geom->sc == 1 && geom->Cin % 8 == 0, "hvc_*3d_cl: needs a channels-last tensor (sc == 1) with Cin % 8 == 0");
+  HVC_CHECK_ARG(geom->sb % 8 == 0 && geom->sd % 8 == 0 && geom->sh % 8 == 0 && geom->sw % 8 == 0 &&
+                reinterpret_cast<uintptr_t>(p) % (8 * elem_bytes) == 0, "hvc_*3d_cl: strides / base must keep 8-channel runs aligned");
+  return HVC_OK;
+}
+
+extern "C" int hvc_im2col3d_cl(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream) {
+  HVC_CHECK_ARG(x && geom && cols, "hvc_im2col3d_cl: null operand");
+  int rc = check_cl_geom(geom, x, x_is_bf16 ? 2 : 4);
+  if (rc) return rc;
+  Conv3dGeom g;
+  rc = fill_geom(&g, geom);
+  if (rc) return rc;
+  const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * 27 * (g.Cin / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (x_is_bf16) im2col3d_cl_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(cols), g);
+  else im2col3d_cl_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(cols), g);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_col2im3d_cl(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream) {
+  HVC_CHECK_ARG(dcols && geom && dx, "hvc_col2im3d_cl: null operand");
+  int rc = check_cl_geom(geom, dx, 4);
+  if (rc) return rc;
+  Conv3dGeom g;
+  rc = fill_geom(&g, geom);
+  if (rc) return rc;
+  const long long total = (long long)g.B * g.D * g.H * g.W * (g.Cin / 8);
+  col2im3d_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(dcols), dx, g);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

@@ -258,6 +258,69 @@ static int fill_geom2d(Conv2dGeom* g, const hvc_conv2d_geom* a) {
   return HVC_OK;
 }
 
+
+// ---- Conv3d(C -> 1, kernel 1): the last layer of Stage3Refiner256.detail_enhancer (model_progressive.py:266) ------------------
+// y: f32 [M, C] channels-last (one 128-byte row per voxel at C = 32).  out[m] = bias + sum_c y[m,c] w[c].
+template <int C>
+__global__ void __launch_bounds__(256) chan_dot_fwd_kernel(const float* __restrict__ y, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out, long long M) {
+  __shared__ float ws[C];
+  if (threadIdx.x < C) ws[threadIdx.x] = w[threadIdx.x];
+  __syncthreads();
+  const float b = bias ? bias[0] : 0.f;
+  for (long long m = (long long)blockIdx.x * 256 + threadIdx.x; m < M; m += (long long)gridDim.x * 256) {
+    const float4* row = reinterpret_cast<const float4*>(y + m * C);
+    float acc = b;
+#pragma unroll
+    for (int j = 0; j < C / 4; ++j) {
+      const float4 v = row[j];
+      acc += v.x * ws[4 * j] + v.y * ws[4 * j + 1] + v.z * ws[4 * j + 2] + v.w * ws[4 * j + 3];
+    }
+    out[m] = acc;
+  }
+}
+
+// dy[m,c] = dout[m] w[c];  dw[c] += sum_m dout[m] y[m,c];  db += sum_m dout[m]   (dw, db zero-filled by the caller)
+template <int C>
+__global__ void __launch_bounds__(256) chan_dot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                                           const float* __restrict__ w, float* __restrict__ dy,
+                                                           float* __restrict__ dw, float* __restrict__ db, long long M) {
+  __shared__ float ws[C];
+  __shared__ float red[C + 1];
+  if (threadIdx.x < C) ws[threadIdx.x] = w[threadIdx.x];
+  if (threadIdx.x <= C) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[C];
+  float accb = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+  for (long long m = (long long)blockIdx.x * 256 + threadIdx.x; m < M; m += (long long)gridDim.x * 256) {
+    const float g = dout[m];
+    accb += g;
+    const float4* row = reinterpret_cast<const float4*>(y + m * C);
+    float4* drow = reinterpret_cast<float4*>(dy + m * C);
+#pragma unroll
+    for (int j = 0; j < C / 4; ++j) {
+      const float4 v = row[j];
+      acc[4 * j] += g * v.x; acc[4 * j + 1] += g * v.y; acc[4 * j + 2] += g * v.z; acc[4 * j + 3] += g * v.w;
+      drow[j] = make_float4(g * ws[4 * j], g * ws[4 * j + 1], g * ws[4 * j + 2], g * ws[4 * j + 3]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float v = acc[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[c], v);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&red[C], accb);
+  __syncthreads();
+  if (threadIdx.x < C) atomicAdd(&dw[threadIdx.x], red[threadIdx.x]);
+  if (threadIdx.x == C) atomicAdd(db, red[C]);
+}
+
 }  // namespace hvc
 
 using namespace hvc;
@@ -354,6 +417,29 @@ extern "C" int hvc_view_mean_bwd(const float* dfeat, const float* dpooled, float
 extern "C" int hvc_silu(const float* x, const float* dy, float* out, int64_t n, void* stream) {
   HVC_CHECK_ARG(x && out && n > 0, "hvc_silu: bad arguments");
   silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(x, dy, out, n);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_chan_dot_fwd(const float* y, const float* w, const float* bias, float* out, int64_t M, int32_t C, void* stream) {
+  HVC_CHECK_ARG(y && w && out && M > 0, "hvc_chan_dot_fwd: bad arguments");
+  HVC_CHECK_ARG(C == 32 || C == 64, "hvc_chan_dot_fwd: C must be 32 or 64");
+  const unsigned blocks = (unsigned)std::min<long long>((M + 255) / 256, 148 * 16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 32) chan_dot_fwd_kernel<32><<<blocks, 256, 0, st>>>(y, w, bias, out, M);
+  else chan_dot_fwd_kernel<64><<<blocks, 256, 0, st>>>(y, w, bias, out, M);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_chan_dot_bwd(const float* dout, const float* y, const float* w, float* dy, float* dw, float* db, int64_t M,
+                                int32_t C, void* stream) {
+  HVC_CHECK_ARG(dout && y && w && dy && dw && db && M > 0, "hvc_chan_dot_bwd: bad arguments");
+  HVC_CHECK_ARG(C == 32 || C == 64, "hvc_chan_dot_bwd: C must be 32 or 64");
+  const unsigned blocks = (unsigned)std::min<long long>((M + 255) / 256, 148 * 4);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (C == 32) chan_dot_bwd_kernel<32><<<blocks, 256, 0, st>>>(dout, y, w, dy, dw, db, M);
+  else chan_dot_bwd_kernel<64><<<blocks, 256, 0, st>>>(dout, y, w, dy, dw, db, M);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

@@ -356,25 +356,26 @@ def conv_out(n, stride):
     return (n - 1) // stride + 1
 
 
-def im2col3d(x, B, Cin, D, H, W, stride, strides):
+def im2col3d(x, B, Cin, D, H, W, stride, strides, tap_major=False):
     """x: f32|bf16 tensor holding the conv input with element strides (sb, sc, sd, sh, sw).
-    Returns bf16 [B*Do*Ho*Wo, Kp]."""
+    Returns bf16 [B*Do*Ho*Wo, Kp], column cin*27 + tap, or tap*Cin + cin with tap_major (channels-last x, Cin % 8 == 0)."""
     _need_cuda(x)
     Do, Ho, Wo = conv_out(D, stride), conv_out(H, stride), conv_out(W, stride)
     Kp = (Cin * 27 + 7) // 8 * 8
     cols = torch.empty(B * Do * Ho * Wo, Kp, device=x.device, dtype=torch.bfloat16)
     g = _geom(B, Cin, D, H, W, stride, strides)
-    _lib.check(_lib.lib().hvc_im2col3d(_ptr(x), int(x.dtype == torch.bfloat16), C.byref(g), _ptr(cols), _stream()),
-               "hvc_im2col3d")
+    fn, name = (_lib.lib().hvc_im2col3d_cl, "hvc_im2col3d_cl") if tap_major else (_lib.lib().hvc_im2col3d, "hvc_im2col3d")
+    _lib.check(fn(_ptr(x), int(x.dtype == torch.bfloat16), C.byref(g), _ptr(cols), _stream()), name)
     return cols
 
 
-def col2im3d(dcols, B, Cin, D, H, W, stride, out, strides):
+def col2im3d(dcols, B, Cin, D, H, W, stride, out, strides, tap_major=False):
     """Adjoint of im2col3d into `out` (f32, pre-allocated, every element written)."""
     _need_cuda(dcols, out)
     assert dcols.dtype == torch.bfloat16 and dcols.is_contiguous() and out.dtype == torch.float32
     g = _geom(B, Cin, D, H, W, stride, strides)
-    _lib.check(_lib.lib().hvc_col2im3d(_ptr(dcols), C.byref(g), _ptr(out), _stream()), "hvc_col2im3d")
+    fn, name = (_lib.lib().hvc_col2im3d_cl, "hvc_col2im3d_cl") if tap_major else (_lib.lib().hvc_col2im3d, "hvc_col2im3d")
+    _lib.check(fn(_ptr(dcols), C.byref(g), _ptr(out), _stream()), name)
     return out
 
 
@@ -667,3 +668,25 @@ def interp3d_bwd(dout, B, grid, size, align_corners):
     dv = torch.empty(B, *grid, device=dout.device, dtype=torch.float32)
     _lib.check(_lib.lib().hvc_interp3d_bwd(_ptr(dout), _ptr(dv), B, *grid, *size, int(align_corners), _stream()), "hvc_interp3d_bwd")
     return dv
+
+
+def chan_dot_fwd(y, w, bias):
+    """Conv3d(C -> 1, kernel 1) on channels-last y f32 [M, C]: out[m] = bias + sum_c y[m,c] w[c]."""
+    _need_cuda(y, w)
+    assert y.dtype == torch.float32 and y.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous() and w.numel() == y.shape[1]
+    M, Cc = y.shape
+    out = torch.empty(M, device=y.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_chan_dot_fwd(_ptr(y), _ptr(w), _ptr(bias), _ptr(out), C.c_int64(M), Cc, _stream()), "hvc_chan_dot_fwd")
+    return out
+
+
+def chan_dot_bwd(dout, y, w):
+    """-> (dy f32 [M, C], dw f32 [C], db f32 [1])"""
+    _need_cuda(dout, y, w)
+    assert dout.dtype == torch.float32 and dout.is_contiguous() and y.is_contiguous() and dout.numel() == y.shape[0]
+    M, Cc = y.shape
+    dy = torch.empty_like(y)
+    dwb = torch.zeros(Cc + 1, device=y.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_chan_dot_bwd(_ptr(dout), _ptr(y), _ptr(w), _ptr(dy), _ptr(dwb), C.c_void_p(dwb.data_ptr() + 4 * Cc),
+                                           C.c_int64(M), Cc, _stream()), "hvc_chan_dot_bwd")
+    return dy, dwb[:Cc], dwb[Cc:]

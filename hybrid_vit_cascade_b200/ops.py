@@ -63,6 +63,18 @@ def w16(p, pad_to=None):
     return t
 
 
+def w16_taps(p):
+    """bf16 [Cout, 27*Cin] copy of a Conv3d weight (Cout, Cin, 3, 3, 3) in tap-major column order (kd, kh, kw, cin): the operand of
+    the channels-last patch matrix (hvc_im2col3d_cl).  Cached like w16."""
+    t = _cache_get(_W16, p, "taps")
+    if t is not None:
+        return t
+    src = p.detach().float().permute(0, 2, 3, 4, 1).reshape(p.shape[0], -1).contiguous()
+    t = K.cast_bf16(src)
+    _cache_put(_W16, p, "taps", t)
+    return t
+
+
 def clear_weight_cache():
     _W16.clear()
 

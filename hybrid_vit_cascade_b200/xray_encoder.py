@@ -325,40 +325,127 @@ class Interp3d(Function):
         return dv.view(x_shape).to(dt), None, None
 
 
+# patch-matrix budget of one Conv3d: above it the conv runs in depth slabs (one batch element, a range of output planes plus a
+# one-plane halo each side), and the backward rebuilds each slab's patches instead of keeping them
+CONV3D_COLS_BYTES = 8 << 30
+
+
+def _conv3d_slabs(B, Cin, D, H, W):
+    Kp = (Cin * 27 + 7) // 8 * 8
+    plane = H * W * Kp * 2
+    if B * D * plane <= CONV3D_COLS_BYTES:
+        return None
+    n = max(1, CONV3D_COLS_BYTES // plane - 2)
+    return [(b, d0, min(D, d0 + n)) for b in range(B) for d0 in range(0, D, n)]
+
+
+def _slab_cols(xf, b, d0, d1, Cin, D, H, W, tm):
+    """Patch rows of output planes [d0, d1) of batch element b: im2col of the input planes [d0-1, d1+1) (clipped to the volume, where
+    the kernel's own zero padding is the right one), minus the halo planes' rows."""
+    lo, hi = max(d0 - 1, 0), min(d1 + 1, D)
+    xs = xf[b:b + 1, :, lo:hi]
+    cols = K.im2col3d(xs, 1, Cin, hi - lo, H, W, 1, tuple(xs.stride()), tap_major=tm)
+    return cols[(d0 - lo) * H * W:(d1 - lo) * H * W], lo, hi
+
+
+def _tap_major(x, Cin):
+    """Channels-last inputs with whole 8-channel runs use the tap-major patch matrix (16-byte accesses in im2col and col2im)."""
+    return Cin % 8 == 0 and x.stride(1) == 1 and all(s % 8 == 0 for i, s in enumerate(x.stride()) if i != 1)
+
+
 class Conv3dGnGelu(Function):
-    """gelu(group_norm(conv3d(x)))  -- Conv3d(k3, pad 1) + GroupNorm + GELU of the stage wrappers (model_progressive.py:170-172).
-    x: (B, Cin, D, H, W) any strides; returns the channels-last buffer viewed as (B, Cout, D, H, W), which is the layout the
-    refiner ViT's voxel embedding gathers from directly."""
+    """gelu(group_norm(conv3d(x)))  -- Conv3d(k3, pad 1) + GroupNorm + GELU of the stage wrappers (model_progressive.py:170-172,
+    :240-242, :260-265).  x: (B, Cin, D, H, W) any strides; returns the channels-last buffer viewed as (B, Cout, D, H, W), which is
+    the layout the refiner ViT's voxel embedding (and the next Conv3dGnGelu) gathers from directly."""
 
     @staticmethod
     def forward(ctx, x, conv_w, conv_b, gn_w, gn_b, groups):
         B, Cin, D, H, W = x.shape
         Cout = conv_w.shape[0]
-        xf = x.float()
-        cols = K.im2col3d(xf, B, Cin, D, H, W, 1, tuple(xf.stride()))
-        z = K.gemm(cols, ops.w16(conv_w, pad_to=cols.shape[1]), bias=conv_b, epilogue=K.EPI_F32)            # [B*V, Cout]
         V = D * H * W
+        xf = x.float()
+        tm = _tap_major(xf, Cin)
+        Kp = (Cin * 27 + 7) // 8 * 8
+        w_16 = ops.w16_taps(conv_w) if tm else ops.w16(conv_w, pad_to=Kp)
+        slabs = _conv3d_slabs(B, Cin, D, H, W)
+        if slabs is None:
+            cols = K.im2col3d(xf, B, Cin, D, H, W, 1, tuple(xf.stride()), tap_major=tm)
+            z = K.gemm(cols, w_16, bias=conv_b, epilogue=K.EPI_F32)                                             # [B*V, Cout]
+        else:
+            cols = None
+            z = torch.empty(B * V, Cout, device=x.device, dtype=torch.float32)
+            for (b, d0, d1) in slabs:
+                rows, _, _ = _slab_cols(xf, b, d0, d1, Cin, D, H, W, tm)
+                K.gemm(rows, w_16, bias=conv_b, epilogue=K.EPI_F32, out=z[(b * D + d0) * H * W:(b * D + d1) * H * W])
+                del rows
         y, mean, rstd = K.norm_act_fwd(z, gn_w, gn_b, B, V, Cout, groups, K.ACT_GELU_ERF, torch.float32)
-        ctx.save_for_backward(cols, z, mean, rstd, conv_w, gn_w, gn_b)
-        ctx.meta = (B, Cin, D, H, W, Cout, groups, tuple(x.shape), tuple(xf.stride()))
+        ctx.save_for_backward(cols if slabs is None else xf, z, mean, rstd, conv_w, gn_w, gn_b)
+        ctx.meta = (B, Cin, D, H, W, Cout, groups, tuple(x.shape), tuple(xf.stride()), slabs, tm)
         return y.view(B, D, H, W, Cout).permute(0, 4, 1, 2, 3)
 
     @staticmethod
     def backward(ctx, dy):
         cols, z, mean, rstd, conv_w, gn_w, gn_b = ctx.saved_tensors
-        B, Cin, D, H, W, Cout, groups, x_shape, x_strides = ctx.meta
-        V = D * H * W
+        B, Cin, D, H, W, Cout, groups, x_shape, x_strides, slabs, tm = ctx.meta
+        V, HW = D * H * W, H * W
+        Kp = (Cin * 27 + 7) // 8 * 8
         dy_cl = dy.float().permute(0, 2, 3, 4, 1).contiguous().view(B * V, Cout)       # a no-op when dy already is channels-last
         dz, dgn_w, dgn_b = K.norm_act_bwd(dy_cl, z, gn_w, gn_b, mean, rstd, B, V, Cout, groups, K.ACT_GELU_ERF)
         dz16 = K.cast_bf16(dz)
+        del dz
         dconv_b = K.colsum_bf16(dz16)
-        dconv_w = ops._wgrad(dz16, cols)[:, :Cin * 27].reshape(conv_w.shape)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dcols = ops._dgrad(dz16, ops.w16(conv_w, pad_to=cols.shape[1]))
-            dx = torch.empty_strided(x_shape, x_strides, device=dy.device, dtype=torch.float32)
-            K.col2im3d(dcols, B, Cin, D, H, W, 1, dx, x_strides)
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_strided(x_shape, x_strides, device=dy.device, dtype=torch.float32) if need_dx else None
+        w_16 = ops.w16_taps(conv_w) if tm else ops.w16(conv_w, pad_to=Kp)
+        if slabs is None:
+            dw = ops._wgrad(dz16, cols)
+            if need_dx:
+                K.col2im3d(ops._dgrad(dz16, w_16), B, Cin, D, H, W, 1, dx, x_strides, tap_major=tm)
+        else:
+            xf = cols                                                                   # the slab path saved the input instead
+            dw = torch.zeros(Cout, Kp, device=dy.device, dtype=torch.float32)
+            for (b, d0, d1) in slabs:
+                rows, lo, hi = _slab_cols(xf, b, d0, d1, Cin, D, H, W, tm)
+                T = (d1 - d0) * HW
+                splits = max(1, min((T + 63) // 64, (4 * ops._sms(dy.device)) // max(((Cout + 127) // 128) * ((Kp + 127) // 128), 1)))
+                K.gemm(dz16[(b * D + d0) * HW:(b * D + d1) * HW], rows, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC,
+                       k_splits=splits, out=dw)
+                del rows
+                if need_dx:
+                    # dx planes [d0, d1) gather from the patch gradients of output planes [d0-1, d1+1): col2im on that halo'd slab is
+                    # exact for its interior planes, which are the ones copied out
+                    dcols = ops._dgrad(dz16[(b * D + lo) * HW:(b * D + hi) * HW], w_16)
+                    tmp = torch.empty(1, hi - lo, H, W, Cin, device=dy.device, dtype=torch.float32).permute(0, 4, 1, 2, 3)
+                    K.col2im3d(dcols, 1, Cin, hi - lo, H, W, 1, tmp, tuple(tmp.stride()), tap_major=tm)
+                    dx[b:b + 1, :, d0:d1].copy_(tmp[:, :, d0 - lo:d1 - lo])
+                    del dcols, tmp
+        if tm:
+            dconv_w = dw.view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3).contiguous()
+        else:
+            dconv_w = dw[:, :Cin * 27].reshape(conv_w.shape)
         return dx, dconv_w, dconv_b, dgn_w, dgn_b, None
+
+
+class ChanDot(Function):
+    """Conv3d(C -> 1, kernel 1) on a channels-last activation (model_progressive.py:266).  y: (B, C, D, H, W) viewed from a
+    channels-last buffer -> (B, 1, D, H, W)."""
+
+    @staticmethod
+    def forward(ctx, y, w, b):
+        B, Cc, D, H, W = y.shape
+        y2 = y.permute(0, 2, 3, 4, 1).contiguous().view(-1, Cc)                        # a view of the channels-last buffer
+        w1 = w.reshape(-1).float().contiguous()
+        out = K.chan_dot_fwd(y2, w1, b)
+        ctx.save_for_backward(y2, w1)
+        ctx.shape = (B, Cc, D, H, W, tuple(w.shape))
+        return out.view(B, 1, D, H, W)
+
+    @staticmethod
+    def backward(ctx, dout):
+        y2, w1 = ctx.saved_tensors
+        B, Cc, D, H, W, w_shape = ctx.shape
+        dy, dw, db = K.chan_dot_bwd(dout.float().contiguous().view(-1), y2, w1)
+        return dy.view(B, D, H, W, Cc).permute(0, 4, 1, 2, 3), dw.view(w_shape), db
 
 
 class Stage2Refiner128(nn.Module):
@@ -386,3 +473,94 @@ class Stage2Refiner128(nn.Module):
         # twice the input (the only way the reference runs); the blend with the learned scalar is a two-op elementwise epilogue
         base = up if tuple(self.volume_size) == tuple(up.shape[2:]) else Interp3d.apply(volume_64, tuple(self.volume_size), False)
         return base + self.residual_weight * refinement
+
+
+class Stage3Refiner256(nn.Module):
+    """reference: direct_regression/progressive_cascade/model_progressive.py:218-315 (128^3 -> 256^3 refinement + high-frequency
+    detail branch).  `use_gradient_checkpointing` is accepted for signature compatibility and changes nothing: the flash-style
+    attention never stores the (B, h, N, M) probability matrices the reference checkpoints away (:286-293), and a B = 2 step fits
+    the 180 GB of HBM without recomputation."""
+
+    def __init__(self, volume_size=(256, 256, 256), voxel_dim=256, vit_depth=8, num_heads=8, xray_feature_dim=512,
+                 use_gradient_checkpointing=True, token_grid="reference"):
+        super().__init__()
+        self.volume_size = volume_size
+        self.use_gradient_checkpointing = use_gradient_checkpointing
+        self.upsample_from_128 = nn.Sequential(nn.Upsample(scale_factor=2, mode='trilinear', align_corners=False),
+                                               nn.Conv3d(1, 32, 3, padding=1), nn.GroupNorm(8, 32), nn.GELU())
+        self.vit_refiner = HybridViT3D(volume_size=volume_size, in_channels=32, voxel_dim=voxel_dim, depth=vit_depth,
+                                       num_heads=num_heads, context_dim=xray_feature_dim, cond_dim=1024, use_prev_stage=False,
+                                       token_grid=token_grid)
+        self.detail_enhancer = nn.Sequential(nn.Conv3d(1, 64, 3, padding=1), nn.GroupNorm(16, 64), nn.GELU(),
+                                             nn.Conv3d(64, 32, 3, padding=1), nn.GroupNorm(8, 32), nn.GELU(), nn.Conv3d(32, 1, 1))
+        self.residual_weight = nn.Parameter(torch.ones(1) * 0.5)
+        self.detail_weight = nn.Parameter(torch.ones(1) * 0.3)
+
+    def forward(self, volume_128, xray_features_2d, time_xray_cond):
+        """volume_128: (B, 1, D/2, H/2, W/2); xray_features_2d: (B, C, h, w); time_xray_cond: (B, 1024) -> (B, 1, D, H, W)"""
+        D2, H2, W2 = volume_128.shape[2:]
+        up = Interp3d.apply(volume_128, (2 * D2, 2 * H2, 2 * W2), False)               # nn.Upsample(scale_factor=2), :239
+        conv, gn = self.upsample_from_128[1], self.upsample_from_128[2]
+        x = Conv3dGnGelu.apply(up, conv.weight, conv.bias, gn.weight, gn.bias, gn.num_groups)
+        refinement = self._vit_forward(x, xray_features_2d, time_xray_cond)
+        # :296-297 -- the same resize as `up` whenever volume_size is twice the input (the only way the reference runs)
+        base = up if tuple(self.volume_size) == tuple(up.shape[2:]) else Interp3d.apply(volume_128, tuple(self.volume_size), False)
+        de = self.detail_enhancer
+        d = Conv3dGnGelu.apply(base, de[0].weight, de[0].bias, de[1].weight, de[1].bias, de[1].num_groups)     # :260-262
+        d = Conv3dGnGelu.apply(d, de[3].weight, de[3].bias, de[4].weight, de[4].bias, de[4].num_groups)        # :263-265
+        details = ChanDot.apply(d, de[6].weight, de[6].bias)                                                   # :266
+        return base + self.residual_weight * refinement + self.detail_weight * details                        # :303-305
+
+    def _vit_forward(self, x, xray_features_2d, time_xray_cond):
+        return self.vit_refiner(x=x, context=xray_features_2d.flatten(2).transpose(1, 2), cond=time_xray_cond, prev_stage_embed=None)
+
+
+class ProgressiveCascadeModel(nn.Module):
+    """reference: direct_regression/progressive_cascade/model_progressive.py:318-432 (64^3 -> 128^3 -> 256^3; train stage by stage or
+    end to end).  `stage2_token_grid`: the committed reference cannot run its stage 2 (HybridViT3D at 128^3 sizes pos_embed for 25^3
+    tokens while the conv stack emits 32^3); "reference" keeps that behaviour (max_stage >= 2 raises the same
+    shape error), "conv" or an int (16 = the author's recorded fix) makes the stage runnable."""
+
+    def __init__(self, xray_img_size=512, xray_feature_dim=512, voxel_dim=256, use_gradient_checkpointing=True,
+                 stage2_token_grid="reference"):
+        super().__init__()
+        self.xray_encoder = MultiScaleXrayEncoder(img_size=xray_img_size, in_channels=1, base_dim=xray_feature_dim, num_views=2)
+        self.stage1 = Stage1Base64(volume_size=(64, 64, 64), xray_img_size=xray_img_size, voxel_dim=voxel_dim, vit_depth=4, num_heads=4,
+                                   xray_feature_dim=xray_feature_dim)
+        self.stage2 = Stage2Refiner128(volume_size=(128, 128, 128), voxel_dim=voxel_dim, vit_depth=6, num_heads=8,
+                                       xray_feature_dim=xray_feature_dim, token_grid=stage2_token_grid)
+        self.stage3 = Stage3Refiner256(volume_size=(256, 256, 256), voxel_dim=voxel_dim, vit_depth=8, num_heads=8,
+                                       xray_feature_dim=xray_feature_dim, use_gradient_checkpointing=use_gradient_checkpointing)
+
+    def forward(self, xrays, return_intermediate=False, max_stage=3):
+        """xrays: (B, 2, 1, S, S) -> the volume of `max_stage`, or {'stage1': ..., 'stage2': ..., 'stage3': ...} up to it"""
+        outputs = {}
+        volume_64 = self.stage1(xrays)
+        outputs['stage1'] = volume_64
+        if max_stage == 1:
+            return outputs if return_intermediate else volume_64
+        feats2, cond, _ = self.xray_encoder(xrays, stage=2)
+        volume_128 = self.stage2(volume_64, feats2, cond)
+        outputs['stage2'] = volume_128
+        if max_stage == 2:
+            return outputs if return_intermediate else volume_128
+        feats3, cond, _ = self.xray_encoder(xrays, stage=3)
+        volume_256 = self.stage3(volume_128, feats3, cond)
+        outputs['stage3'] = volume_256
+        return outputs if return_intermediate else volume_256
+
+    def _set_stage(self, stage, flag):
+        for p in getattr(self, f"stage{stage}").parameters():
+            p.requires_grad = flag
+
+    def freeze_stage(self, stage):
+        """reference :404-418"""
+        if stage in (1, 2, 3):
+            self._set_stage(stage, False)
+            print(f"Stage {stage} ({(64, 128, 256)[stage - 1]}\u00b3) frozen")
+
+    def unfreeze_stage(self, stage):
+        """reference :420-434"""
+        if stage in (1, 2, 3):
+            self._set_stage(stage, True)
+            print(f"Stage {stage} ({(64, 128, 256)[stage - 1]}\u00b3) unfrozen")

@@ -228,6 +228,11 @@ typedef struct hvc_conv3d_geom {
 int hvc_im2col3d(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream);
 /* dx (f32, layout given by geom strides) = adjoint of im2col applied to dcols (bf16 [M, Kp]). */
 int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream);
+/* Channels-last variants (geom->sc == 1, Cin % 8 == 0, strides multiples of 8): column k = (kd*9 + kh*3 + kw)*Cin + cin, i.e. the
+ * order of weight.permute(0,2,3,4,1).reshape(Cout, 27*Cin); every access is a 16-byte run of 8 channels.  Used by the full-resolution
+ * convs of the cascade's detail_enhancer (progressive_cascade/model_progressive.py:263). */
+int hvc_im2col3d_cl(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream);
+int hvc_col2im3d_cl(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream);
 /* y [B,V,C] (bf16, or f32 when it feeds the token stream) = SiLU(GroupNorm(x f32 [B,V,C])); mean/rstd f32
  * [B,groups] saved; scratch f32 [2*B*C]. */
 int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C,
@@ -259,6 +264,15 @@ int hvc_interp3d_fwd(const float* v, float* out, int32_t B, int32_t Di, int32_t 
                      int32_t Wo, int32_t align_corners, void* stream);
 int hvc_interp3d_bwd(const float* dout, float* dv, int32_t B, int32_t Di, int32_t Hi, int32_t Wi, int32_t Do, int32_t Ho,
                      int32_t Wo, int32_t align_corners, void* stream);
+
+/* Conv3d(C -> 1, kernel 1) on a channels-last activation y f32 [M, C] (C = 32 | 64): the last layer of
+ * Stage3Refiner256.detail_enhancer (progressive_cascade/model_progressive.py:266).
+ * fwd: out[m] = bias[0] + sum_c y[m,c] w[c].   bwd: dy[m,c] = dout[m] w[c]; dw[c] += sum_m dout[m] y[m,c]; db[0] += sum_m dout[m]
+ * (dw, db are accumulated into: zero-fill them first). */
+int hvc_chan_dot_fwd(const float* y, const float* w, const float* bias, float* out, int64_t M, int32_t C, void* stream);
+int hvc_chan_dot_bwd(const float* dout, const float* y, const float* w, float* dy, float* dw, float* db, int64_t M, int32_t C,
+                     void* stream);
+
 
 /* ------------------------------------------------------------------------------------------------
  * fp32 verification mode (the 1e-4 fp32 parity bar): fp32-accurate products on the bf16 tensor cores.

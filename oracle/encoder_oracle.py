@@ -130,3 +130,39 @@ def stage2_refiner128(volume_64: Tensor, xray_features_2d: Tensor, cond: Tensor,
     refinement = V.backbone(x, xray_features_2d.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)   # :203-208
     up = F.interpolate(volume_64, size=tuple(cfg.volume_size), mode="trilinear", align_corners=False)     # :211-212
     return up + sd["residual_weight"] * refinement                                                 # :213
+
+
+def stage3_refiner256(volume_128: Tensor, xray_features_2d: Tensor, cond: Tensor, sd: StateDict, cfg: V.BackboneConfig,
+                      attn_chunk: Optional[int] = None) -> Tensor:
+    """Stage3Refiner256.forward, progressive_cascade/model_progressive.py:273-307 (dropout off in the refiner ViT; gradient
+    checkpointing, :286-293, changes memory only)."""
+    x = F.interpolate(volume_128, scale_factor=2, mode="trilinear", align_corners=False)           # nn.Upsample, :239
+    x = F.conv3d(x, sd["upsample_from_128.1.weight"], sd["upsample_from_128.1.bias"], padding=1)   # :240
+    x = F.gelu(F.group_norm(x, 8, sd["upsample_from_128.2.weight"], sd["upsample_from_128.2.bias"], 1e-5))   # :241-242
+    bsd = {k[len("vit_refiner."):]: v for k, v in sd.items() if k.startswith("vit_refiner.")}
+    refinement = V.backbone(x, xray_features_2d.flatten(2).transpose(1, 2), cond, bsd, cfg, attn_chunk=attn_chunk)   # :309-315
+    up = F.interpolate(volume_128, size=tuple(cfg.volume_size), mode="trilinear", align_corners=False)    # :296-297
+    d = F.conv3d(up, sd["detail_enhancer.0.weight"], sd["detail_enhancer.0.bias"], padding=1)      # :260
+    d = F.gelu(F.group_norm(d, 16, sd["detail_enhancer.1.weight"], sd["detail_enhancer.1.bias"], 1e-5))    # :261-262
+    d = F.conv3d(d, sd["detail_enhancer.3.weight"], sd["detail_enhancer.3.bias"], padding=1)       # :263
+    d = F.gelu(F.group_norm(d, 8, sd["detail_enhancer.4.weight"], sd["detail_enhancer.4.bias"], 1e-5))     # :264-265
+    d = F.conv3d(d, sd["detail_enhancer.6.weight"], sd["detail_enhancer.6.bias"])                  # :266
+    return up + sd["residual_weight"] * refinement + sd["detail_weight"] * d                       # :303-305
+
+
+def progressive_cascade(xrays: Tensor, sd: StateDict, cfgs: Dict[int, V.BackboneConfig], max_stage: int = 3, training: bool = True,
+                        attn_chunk: Optional[int] = None) -> Dict[str, Tensor]:
+    """ProgressiveCascadeModel.forward(return_intermediate=True), progressive_cascade/model_progressive.py:371-407.  cfgs[k] is the
+    backbone configuration of stage k's ViT.  Stage 1 runs its own encoder (:135), stages 2 and 3 the shared one, once per stage
+    on the same X-rays (:386,:394) -- in training mode every one of those calls updates that encoder's BatchNorm statistics, which
+    does not change any output of this forward."""
+    def sub(p):
+        return {k[len(p):]: v for k, v in sd.items() if k.startswith(p)}
+    out = {"stage1": stage1_base64(xrays, sub("stage1."), cfgs[1], training=training, attn_chunk=attn_chunk)}
+    if max_stage >= 2:
+        f2, c2, _ = multi_scale_xray_encoder(xrays, sd, "xray_encoder.", stage=2, training=training)
+        out["stage2"] = stage2_refiner128(out["stage1"], f2, c2, sub("stage2."), cfgs[2], attn_chunk=attn_chunk)
+    if max_stage >= 3:
+        f3, c3, _ = multi_scale_xray_encoder(xrays, sd, "xray_encoder.", stage=3, training=training)
+        out["stage3"] = stage3_refiner256(out["stage2"], f3, c3, sub("stage3."), cfgs[3], attn_chunk=attn_chunk)
+    return out

@@ -20,7 +20,7 @@ sys.path.insert(0, os.path.join(REF, "direct_regression"))
 from models.diagnostic_losses import XrayConditioningModule  # noqa: E402
 from model_direct import DirectCTRegression  # noqa: E402
 sys.path.insert(0, os.path.join(REF, "direct_regression", "progressive_cascade"))
-from model_progressive import MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128  # noqa: E402
+from model_progressive import MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128, Stage3Refiner256  # noqa: E402
 
 
 def grads(mod, outs_and_rs, leaves):
@@ -138,6 +138,23 @@ def main():
     r = torch.randn(y.shape, generator=g)
     pg, ig = grads(m, [(y, r)], [v64, feats, cond])
     out["stage2"] = dict(kwargs=kw, seed=5, adaln_seed=105, wsum=wsum, volume_64=v64.detach(), feats=feats.detach(), cond=cond.detach(),
+                         y=y.detach(), r=r, pgrad={k: v.bfloat16() for k, v in pg.items()}, vgrad=ig[0], fgrad=ig[1], cgrad=ig[2])
+    # Stage3Refiner256 (cascade stage 3), small: 16^3 -> 32^3 with the detail branch, 8 x 8 context tokens, two heads of 32
+    torch.manual_seed(6)
+    kw = dict(volume_size=(32, 32, 32), voxel_dim=64, vit_depth=1, num_heads=2, xray_feature_dim=64)
+    m = Stage3Refiner256(**kw).train()                 # train(): the torch.utils.checkpoint branch (:286-293) is the one that runs
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    randomise_adaln(m, 106)
+    wsum = weight_checksum(m)
+    v128 = (torch.rand(2, 1, 16, 16, 16, generator=g) * 2 - 1).requires_grad_(True)
+    feats = torch.randn(2, 64, 8, 8, generator=g).requires_grad_(True)
+    cond = torch.randn(2, 1024, generator=g).requires_grad_(True)
+    y = m(v128, feats, cond)
+    r = torch.randn(y.shape, generator=g)
+    pg, ig = grads(m, [(y, r)], [v128, feats, cond])
+    out["stage3"] = dict(kwargs=kw, seed=6, adaln_seed=106, wsum=wsum, volume_128=v128.detach(), feats=feats.detach(), cond=cond.detach(),
                          y=y.detach(), r=r, pgrad={k: v.bfloat16() for k, v in pg.items()}, vgrad=ig[0], fgrad=ig[1], cgrad=ig[2])
     torch.save(out, os.path.join(HERE, "encoder.pt"))
     print({k: list(v.keys()) for k, v in out.items()})

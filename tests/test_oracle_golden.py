@@ -280,3 +280,44 @@ def test_cascade_stage2_oracle_matches_reference_fixture():
     for k, g in c["pgrad"].items():
         if float(g.float().abs().max()) > 1e-6:
             assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
+
+
+def test_cascade_stage3_oracle_matches_reference_fixture():
+    """Stage3Refiner256, progressive_cascade/model_progressive.py:218-315 (incl. the detail_enhancer branch)."""
+    import hybrid_vit_cascade_b200 as hvc
+    from conftest import rebuild_from_seed
+    from oracle import encoder_oracle as E
+    c = _enc_gold()["stage3"]
+    kw = c["kwargs"]
+    cfg = O.BackboneConfig(volume_size=kw["volume_size"], in_channels=32, voxel_dim=kw["voxel_dim"], depth=kw["vit_depth"],
+                           num_heads=kw["num_heads"], context_dim=kw["xray_feature_dim"], cond_dim=1024)
+    sd0 = rebuild_from_seed(hvc.Stage3Refiner256, c).state_dict()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd0.items()}
+    v128 = c["volume_128"].clone().requires_grad_(True)
+    y = E.stage3_refiner256(v128, c["feats"], c["cond"], sd, cfg)
+    assert O.max_rel(y, c["y"]) <= 2e-6
+    (y * c["r"]).sum().backward()
+    assert O.max_rel(v128.grad, c["vgrad"]) <= 2e-5
+    for k, g in c["pgrad"].items():
+        if float(g.float().abs().max()) > 1e-6:
+            assert O.cosine(sd[k].grad, g.float()) > 0.9999, k
+
+
+def test_progressive_cascade_module_layout_and_stage_freezing():
+    """ProgressiveCascadeModel (model_progressive.py:318-432): same parameter names and shapes as the reference's constructor
+    produces (recorded in the fixture of each stage), freeze/unfreeze switch requires_grad of one stage only."""
+    import hybrid_vit_cascade_b200 as hvc
+    m = hvc.ProgressiveCascadeModel(xray_img_size=64, xray_feature_dim=64, voxel_dim=64, stage2_token_grid=16)
+    keys = set(m.state_dict().keys())
+    for pfx, sub in (("xray_encoder.", m.xray_encoder), ("stage1.", m.stage1), ("stage2.", m.stage2), ("stage3.", m.stage3)):
+        assert all(pfx + k in keys for k in sub.state_dict())
+    assert len(m.stage1.vit_backbone.blocks) == 4 and len(m.stage2.vit_refiner.blocks) == 6 and len(m.stage3.vit_refiner.blocks) == 8
+    assert m.stage2.vit_refiner.downsampled_size == (16, 16, 16) and m.stage3.vit_refiner.downsampled_size == (32, 32, 32)
+    m.freeze_stage(2)
+    assert not any(p.requires_grad for p in m.stage2.parameters())
+    assert all(p.requires_grad for p in m.stage1.parameters()) and all(p.requires_grad for p in m.stage3.parameters())
+    m.unfreeze_stage(2)
+    assert all(p.requires_grad for p in m.stage2.parameters())
+    # the committed reference cannot run stage 2 (SURVEY.md section 1 item 2): the default keeps its token rule
+    ref = hvc.ProgressiveCascadeModel(xray_img_size=64, xray_feature_dim=64, voxel_dim=64)
+    assert ref.stage2.vit_refiner.downsampled_size == (25, 25, 25)
