@@ -23,6 +23,10 @@ class Dropout(C.Structure):
     _fields_ = [("seed", C.c_void_p), ("site", C.c_uint32), ("p", C.c_float)]
 
 
+class ConvTaps(C.Structure):
+    _fields_ = [("side", C.c_int32), ("cin", C.c_int32), ("sd", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("size", C.c_uint32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
@@ -38,6 +42,7 @@ class GemmArgs(C.Structure):
         ("aux", C.c_void_p), ("ldaux", C.c_int64),
         ("alpha", C.c_float), ("k_splits", C.c_int32),
         ("drop", Dropout),
+        ("taps", ConvTaps),
     ]
 
 

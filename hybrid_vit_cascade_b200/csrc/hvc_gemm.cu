@@ -48,13 +48,29 @@ struct GemmKArgs {
   float alpha;
   DropArg drop;   // fused nn.Dropout on the epilogue value (seed == nullptr: off)
   int v256;       // every epilogue operand (out, out2, resid, aux) is 32-byte aligned with a 32-byte-multiple row pitch
+  // implicit 3x3x3 convolution over a zero-padded channels-last volume (hvc_gemm_args::taps): the operand on `taps_side` is a
+  // [padded voxels, tap_cin] matrix read with a per-tap row shift instead of a materialised patch matrix
+  int taps_side, tap_cin, tap_sd, tap_sh, tap_sw;
 };
+
+// row shift of tap = kd*9 + kh*3 + kw: (kd-1)*sd + (kh-1)*sh + (kw-1)*sw
+__device__ __forceinline__ int tap_shift(const GemmKArgs& p, int tap) {
+  const int kd = tap / 9, kh = (tap - kd * 9) / 3, kw = tap - kd * 9 - kh * 3;
+  return (kd - 1) * p.tap_sd + (kh - 1) * p.tap_sh + (kw - 1) * p.tap_sw;
+}
 
 struct WorkItem {
   int m0, n0, kb0, kb1;
 };
 __device__ __forceinline__ WorkItem decode_work(const GemmKArgs& p, int w) {
+#ifdef HVC_GEMM_SPLIT_FASTEST
   const int tile = w / p.k_splits, split = w - tile * p.k_splits;
+#else
+  // tile-fastest: the CTAs in flight at any time cover ALL output tiles of a few K ranges, so each K range of A and B comes from
+  // HBM once and is shared through L2 (split-fastest re-read A once per N tile and B once per M tile)
+  const int tiles = p.m_blocks * p.n_blocks;
+  const int split = w / tiles, tile = w - split * tiles;
+#endif
   const int mb = tile / p.n_blocks, nb = tile - mb * p.n_blocks;
   WorkItem it;
   it.m0 = mb * BM;
@@ -244,13 +260,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* sB = sA + kTileBytes;
           mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
           if (A_MAJOR == kMajorK) {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, it.m0);
+            if (p.taps_side == 1) {   // k-block kb lies inside one tap (tap_cin % BK == 0): columns of that tap, rows shifted
+              const int k = kb * BK, tap = k / p.tap_cin;
+              tma_load_2d(sA, &tmA, &full_bar[stage], k - tap * p.tap_cin, it.m0 + tap_shift(p, tap));
+            } else {
+              tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, it.m0);
+            }
           } else {
             tma_load_2d(sA, &tmA, &full_bar[stage], it.m0, kb * BK);
             tma_load_2d(sA + kTileBytes / 2, &tmA, &full_bar[stage], it.m0 + 64, kb * BK);
           }
           if (B_MAJOR == kMajorK) {
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, it.n0);
+          } else if (p.taps_side == 2) {   // each 64-column half lies inside one tap (tap_cin % 64 == 0): K rows shifted per tap
+            const int t0 = it.n0 / p.tap_cin, t1 = (it.n0 + 64) / p.tap_cin;
+            tma_load_2d(sB, &tmB, &full_bar[stage], it.n0 - t0 * p.tap_cin, kb * BK + tap_shift(p, t0));
+            tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64 - t1 * p.tap_cin, kb * BK + tap_shift(p, t1));
           } else {
             tma_load_2d(sB, &tmB, &full_bar[stage], it.n0, kb * BK);
             tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64, kb * BK);
@@ -365,13 +390,20 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   const int k_splits_req = a->k_splits < 1 ? 1 : a->k_splits;
   HVC_CHECK_ARG(k_splits_req == 1 || a->epilogue == HVC_EPI_F32_ATOMIC, "hvc_gemm: k_splits>1 needs the atomic epilogue");
 
+  const hvc_conv_taps& tp = a->taps;
+  HVC_CHECK_ARG(tp.side >= 0 && tp.side <= 2, "hvc_gemm: taps.side must be 0, 1 or 2");
+  if (tp.side == 1) HVC_CHECK_ARG(a->a_major == 0 && tp.cin > 0 && tp.cin % BK == 0 && a->K == 27 * tp.cin,
+                                  "hvc_gemm: taps on A need a K-major A, cin %% 64 == 0 and K == 27*cin");
+  if (tp.side == 2) HVC_CHECK_ARG(a->b_major == 1 && tp.cin > 0 && tp.cin % 64 == 0 && a->N == 27 * tp.cin,
+                                  "hvc_gemm: taps on B need an MN-major B, cin %% 64 == 0 and N == 27*cin");
+
   CUtensorMap tmA, tmB;
   int rc;
-  if (a->a_major == 0) rc = make_tmap_2d(&tmA, a->A, 2, a->M, a->K, a->lda, BK, BM, true);
+  if (a->a_major == 0) rc = make_tmap_2d(&tmA, a->A, 2, a->M, tp.side == 1 ? tp.cin : a->K, a->lda, BK, BM, true);
   else                 rc = make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, 64, BK, true);
   if (rc) return rc;
   if (a->b_major == 0) rc = make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, BK, BN, true);
-  else                 rc = make_tmap_2d(&tmB, a->B, 2, a->K, a->N, a->ldb, 64, BK, true);
+  else                 rc = make_tmap_2d(&tmB, a->B, 2, a->K, tp.side == 2 ? tp.cin : a->N, a->ldb, 64, BK, true);
   if (rc) return rc;
 
   GemmKArgs ka;
@@ -389,6 +421,7 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   ka.aux = reinterpret_cast<const bf16*>(a->aux); ka.ldaux = a->ldaux;
   ka.alpha = a->alpha;
   ka.drop = make_drop(a->drop);
+  ka.taps_side = tp.side; ka.tap_cin = tp.cin; ka.tap_sd = tp.sd; ka.tap_sh = tp.sh; ka.tap_sw = tp.sw;
   {
     auto ok32 = [](const void* ptr, long long ld, int esz) {
       return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31u) == 0 && ((ld * esz) & 31) == 0);

@@ -86,16 +86,24 @@ def _row_major_2d(t, name):
 
 def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epilogue=EPI_BF16,
          activation=ACT_NONE, bias=None, out2=None, resid=None, gate=None, gate_ld=0, rows_per_batch=0,
-         aux=None, alpha=1.0, k_splits=1, drop=None):
+         aux=None, alpha=1.0, k_splits=1, drop=None, taps=None):
     """D[M,N] = alpha * sum_k A(m,k) B(n,k) with a fused epilogue (see include/hvc.h).
 
     a: bf16, stored [M,K] (a_major=0) or [K,M] (a_major=1); b: bf16, stored [N,K] or [K,N].
+    taps = (side, cin, sd, sh, sw): implicit 3x3x3 convolution, the operand on `side` (1 = a, 2 = b) is the zero-padded channels-last
+    volume [padded voxels, cin] and stands for its 27*cin-wide patch matrix (hvc_conv_taps in include/hvc.h).
     """
     _need_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb = _row_major_2d(a, "a"), _row_major_2d(b, "b")
     M, K = (a.shape if a_major == 0 else (a.shape[1], a.shape[0]))
     N, Kb = (b.shape if b_major == 0 else (b.shape[1], b.shape[0]))
+    if taps is not None and taps[0] == 1:
+        assert a_major == 0 and K == taps[1]
+        K = 27 * K
+    if taps is not None and taps[0] == 2:
+        assert b_major == 1 and N == taps[1]
+        N = 27 * N
     assert K == Kb, (a.shape, b.shape, a_major, b_major)
     if out is None:
         if epilogue == EPI_BF16:
@@ -128,6 +136,8 @@ def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epil
     args.alpha = alpha
     args.k_splits = k_splits
     _set_drop(args, drop)
+    if taps is not None:
+        args.taps.side, args.taps.cin, args.taps.sd, args.taps.sh, args.taps.sw = taps
     with _timed("gemm", 2.0 * M * N * K):
         _lib.check(_lib.lib().hvc_gemm(C.byref(args), _stream()), "hvc_gemm")
     return out

@@ -75,6 +75,21 @@ def w16_taps(p):
     return t
 
 
+def w16_taps_t(p, cout_pad):
+    """bf16 [Cin, 27*cout_pad] transposed filter of a Conv3d weight (Cout, Cin, 3, 3, 3): column (kd, kh, kw, co), co zero-padded to
+    cout_pad -- the B operand of the implicit-GEMM data gradient (hvc_conv_taps side 1 on the padded output gradient)."""
+    key = ("taps_t", cout_pad)
+    t = _cache_get(_W16, p, key)
+    if t is not None:
+        return t
+    Cout, Cin = p.shape[0], p.shape[1]
+    src = torch.zeros(Cin, 27, cout_pad, device=p.device, dtype=torch.float32)
+    src[:, :, :Cout] = p.detach().float().reshape(Cout, Cin, 27).permute(1, 2, 0)
+    t = K.cast_bf16(src.view(Cin, 27 * cout_pad))
+    _cache_put(_W16, p, key, t)
+    return t
+
+
 def clear_weight_cache():
     _W16.clear()
 

@@ -330,6 +330,17 @@ class Interp3d(Function):
 CONV3D_COLS_BYTES = 8 << 30
 
 
+# Conv3d with Cin % 64 == 0 runs as an implicit GEMM on the zero-padded channels-last volume (hvc_conv_taps): no patch matrix at all
+CONV3D_IMPLICIT = True
+
+
+def _pad_cl(src_cl, B, D, H, W, Cc, Cp):
+    """(B, D, H, W, Cc) view (any float dtype) -> zero-padded bf16 (B, D+2, H+2, W+2, Cp) buffer, Cc <= Cp."""
+    out = torch.zeros(B, D + 2, H + 2, W + 2, Cp, device=src_cl.device, dtype=torch.bfloat16)
+    out[:, 1:-1, 1:-1, 1:-1, :Cc].copy_(src_cl)
+    return out
+
+
 def _conv3d_slabs(B, Cin, D, H, W):
     Kp = (Cin * 27 + 7) // 8 * 8
     plane = H * W * Kp * 2
@@ -366,9 +377,16 @@ class Conv3dGnGelu(Function):
         xf = x.float()
         tm = _tap_major(xf, Cin)
         Kp = (Cin * 27 + 7) // 8 * 8
-        w_16 = ops.w16_taps(conv_w) if tm else ops.w16(conv_w, pad_to=Kp)
-        slabs = _conv3d_slabs(B, Cin, D, H, W)
-        if slabs is None:
+        implicit = CONV3D_IMPLICIT and Cin % 64 == 0
+        w_16 = ops.w16_taps(conv_w) if (tm or implicit) else ops.w16(conv_w, pad_to=Kp)
+        slabs = None if implicit else _conv3d_slabs(B, Cin, D, H, W)
+        if implicit:
+            # rows = padded voxels; a tap (kd, kh, kw) is a shift of (kd-1)*(H+2)*(W+2) + (kh-1)*(W+2) + (kw-1) rows
+            cols = _pad_cl(xf.permute(0, 2, 3, 4, 1), B, D, H, W, Cin, Cin)
+            zpad = K.gemm(cols.view(-1, Cin), w_16, bias=conv_b, epilogue=K.EPI_F32, taps=(1, Cin, (H + 2) * (W + 2), W + 2, 1))
+            z = zpad.view(B, D + 2, H + 2, W + 2, Cout)[:, 1:-1, 1:-1, 1:-1].reshape(B * V, Cout)
+            del zpad
+        elif slabs is None:
             cols = K.im2col3d(xf, B, Cin, D, H, W, 1, tuple(xf.stride()), tap_major=tm)
             z = K.gemm(cols, w_16, bias=conv_b, epilogue=K.EPI_F32)                                             # [B*V, Cout]
         else:
@@ -380,13 +398,13 @@ class Conv3dGnGelu(Function):
                 del rows
         y, mean, rstd = K.norm_act_fwd(z, gn_w, gn_b, B, V, Cout, groups, K.ACT_GELU_ERF, torch.float32)
         ctx.save_for_backward(cols if slabs is None else xf, z, mean, rstd, conv_w, gn_w, gn_b)
-        ctx.meta = (B, Cin, D, H, W, Cout, groups, tuple(x.shape), tuple(xf.stride()), slabs, tm)
+        ctx.meta = (B, Cin, D, H, W, Cout, groups, tuple(x.shape), tuple(xf.stride()), slabs, tm, implicit)
         return y.view(B, D, H, W, Cout).permute(0, 4, 1, 2, 3)
 
     @staticmethod
     def backward(ctx, dy):
         cols, z, mean, rstd, conv_w, gn_w, gn_b = ctx.saved_tensors
-        B, Cin, D, H, W, Cout, groups, x_shape, x_strides, slabs, tm = ctx.meta
+        B, Cin, D, H, W, Cout, groups, x_shape, x_strides, slabs, tm, implicit = ctx.meta
         V, HW = D * H * W, H * W
         Kp = (Cin * 27 + 7) // 8 * 8
         dy_cl = dy.float().permute(0, 2, 3, 4, 1).contiguous().view(B * V, Cout)       # a no-op when dy already is channels-last
@@ -396,6 +414,21 @@ class Conv3dGnGelu(Function):
         dconv_b = K.colsum_bf16(dz16)
         need_dx = ctx.needs_input_grad[0]
         dx = torch.empty_strided(x_shape, x_strides, device=dy.device, dtype=torch.float32) if need_dx else None
+        if implicit:
+            # padded output gradient (zero rows at the padding positions, channels padded to a whole 64-wide k-block)
+            Cp = (Cout + 63) // 64 * 64
+            sd, sh = (H + 2) * (W + 2), W + 2
+            dzp = _pad_cl(dz16.view(B, D, H, W, Cout), B, D, H, W, Cout, Cp).view(-1, Cp)
+            del dz16
+            tiles = (27 * Cin + 127) // 128
+            splits = max(1, min(dzp.shape[0] // 64, (16 * ops._sms(dy.device)) // tiles))     # short fp32 accumulation chains
+            dw = K.gemm(dzp, cols.view(-1, Cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=splits,
+                        taps=(2, Cin, sd, sh, 1))[:Cout]
+            if need_dx:
+                dxp = K.gemm(dzp, ops.w16_taps_t(conv_w, Cp), epilogue=K.EPI_F32, taps=(1, Cp, -sd, -sh, -1))
+                dx.permute(0, 2, 3, 4, 1).copy_(dxp.view(B, D + 2, H + 2, W + 2, Cin)[:, 1:-1, 1:-1, 1:-1])
+                del dxp
+            return dx, dw.view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3).contiguous(), dconv_b, dgn_w, dgn_b, None
         w_16 = ops.w16_taps(conv_w) if tm else ops.w16(conv_w, pad_to=Kp)
         if slabs is None:
             dw = ops._wgrad(dz16, cols)

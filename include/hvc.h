@@ -86,6 +86,20 @@ typedef enum hvc_activation {
   HVC_ACT_GELU_GRAD = 2   /* out = acc * gelu'(aux)  (backward of the MLP hidden activation)          */
 } hvc_activation;
 
+/* Implicit Conv3d(k3, pad 1, stride 1) through hvc_gemm: the activation is a zero-padded channels-last volume viewed as a matrix
+ * [rows = B*(D+2)*(H+2)*(W+2) padded voxels, cin] (bf16); moving one voxel along w / h / d moves sw / sh / sd rows, so a filter tap
+ * (kd, kh, kw) is a ROW SHIFT of (kd-1)*sd + (kh-1)*sh + (kw-1)*sw, which the TMA producer adds to the tile coordinate (rows outside the
+ * matrix read as zero).  No patch matrix exists in HBM.  Column/row index of tap t = kd*9 + kh*3 + kw along the tapped dimension:
+ * [t*cin, (t+1)*cin), i.e. weight.permute(0,2,3,4,1).reshape(Cout, 27*cin).
+ *   side 1: A is the padded volume (a_major 0, K = 27*cin): out[r, n] = sum_t sum_c A[r + shift(t), c] B[n, t*cin + c]   (forward conv,
+ *           and the data gradient with negated strides and the transposed filter); rows r at padding positions hold don't-care values.
+ *   side 2: B is the padded volume (b_major 1, N = 27*cin, K = rows): out[m, t*cin + c] = sum_r A(r, m) B[r + shift(t), c]
+ *           (weight gradient; A = padded output gradient with zero rows at the padding positions).
+ * cin % 64 == 0.  side 0: a plain GEMM. */
+typedef struct hvc_conv_taps {
+  int32_t side, cin, sd, sh, sw;
+} hvc_conv_taps;
+
 typedef struct hvc_gemm_args {
   uint32_t size;
   int32_t M, N, K;
@@ -104,6 +118,7 @@ typedef struct hvc_gemm_args {
   int32_t k_splits;             /* >= 1; > 1 only with HVC_EPI_F32_ATOMIC */
   hvc_dropout drop;             /* applied to act(alpha*acc + bias) before the residual/gate (EPI_BF16, EPI_RESIDUAL, EPI_F32); with
                                    HVC_ACT_GELU_GRAD it masks the incoming gradient: out = drop(acc) * gelu'(aux) */
+  hvc_conv_taps taps;           /* implicit 3x3x3 convolution (see above); zero-filled = plain GEMM */
 } hvc_gemm_args;
 
 int hvc_gemm(const hvc_gemm_args* args, void* stream);

@@ -224,9 +224,10 @@ def test_cascade_stage3_refiner_golden():
         hvc.set_dropout_policy("apply")
 
 
-def _conv_gn_gelu_case(Cin, channels_last):
+def _conv_gn_gelu_case(Cin, channels_last, implicit):
     import torch.nn.functional as F
     from hybrid_vit_cascade_b200 import xray_encoder as X
+    X.CONV3D_IMPLICIT, implicit_default = implicit, X.CONV3D_IMPLICIT
     g = torch.Generator(device="cuda").manual_seed(77 + Cin)
     B, Cout, D, H, W, groups = 2, 32, 12, 16, 16, 8
     x = torch.randn(B, D, H, W, Cin, device="cuda", generator=g).permute(0, 4, 1, 2, 3) if channels_last else \
@@ -251,15 +252,18 @@ def _conv_gn_gelu_case(Cin, channels_last):
         slab = run(lambda a, w, b, g1, g2: X.Conv3dGnGelu.apply(a, w, b, g1, g2, groups))
     finally:
         X.CONV3D_COLS_BYTES = budget
+        X.CONV3D_IMPLICIT = implicit_default
     return ref, one, slab
 
 
-@pytest.mark.parametrize("Cin,channels_last", [(64, True), (16, True), (5, False), (1, False)])
-def test_conv3d_gn_gelu_single_pass_and_depth_slabs(Cin, channels_last):
+@pytest.mark.parametrize("Cin,channels_last,implicit", [(64, True, True), (128, False, True), (64, True, False), (16, True, False),
+                                                        (5, False, False), (1, False, False)])
+def test_conv3d_gn_gelu_single_pass_and_depth_slabs(Cin, channels_last, implicit):
     """Conv3d(k3, p1)+GroupNorm+GELU of the stage wrappers / detail_enhancer (model_progressive.py:170-172,260-265) against the plain
-    fp32 torch ops, for the cin-major and the channels-last tap-major patch layouts, in one pass and in depth slabs with one-plane
-    halos (the path a conv takes when its patch matrix exceeds CONV3D_COLS_BYTES -- Conv3d(64->32) at 256^3 is 58 GB per sample)."""
-    ref, one, slab = _conv_gn_gelu_case(Cin, channels_last)
+    fp32 torch ops: the implicit GEMM on the padded volume (Cin % 64 == 0; forward, weight gradient, data gradient), and the patch-matrix
+    paths with the cin-major and the channels-last tap-major layouts, in one pass and in depth slabs with one-plane halos (the path a
+    conv with another channel count takes when its patch matrix exceeds CONV3D_COLS_BYTES)."""
+    ref, one, slab = _conv_gn_gelu_case(Cin, channels_last, implicit)
     names = ("y", "dx", "dconv_w", "dconv_b", "dgn_w", "dgn_b")
     for n, a, b, c in zip(names, ref, one, slab):
         assert a.shape == b.shape == c.shape, n
