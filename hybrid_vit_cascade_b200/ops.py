@@ -415,11 +415,14 @@ class VoxelEmbed(Function):
         for li, (cin, cout, stride, groups) in enumerate(plan):
             _, Dc, Hc, Wc = dims
             weight, bias = params[pi], params[pi + 1]
-            cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides)
+            # channels-last inputs (every layer after the first, and the stage wrappers' 32-channel volume) use the tap-major patch
+            # matrix: whole 8-channel runs per access in im2col and col2im (hvc_im2col3d_cl)
+            tm = cin % 8 == 0 and strides[1] == 1 and all(s % 8 == 0 for s in strides[:1] + strides[2:]) and (li > 0 or xB == B)
+            cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides, tap_major=tm)
             Do, Ho, Wo = K.conv_out(Dc, stride), K.conv_out(Hc, stride), K.conv_out(Wc, stride)
-            z = K.gemm(cols, w16(weight, pad_to=cols.shape[1]), bias=bias, epilogue=K.EPI_F32)   # [xB*V, cout] channels-last
+            z = K.gemm(cols, w16_taps(weight) if tm else w16(weight, pad_to=cols.shape[1]), bias=bias, epilogue=K.EPI_F32)   # [xB*V, cout] channels-last
             V = Do * Ho * Wo
-            geoms.append((cin, Dc, Hc, Wc, stride, strides, V))
+            geoms.append((cin, Dc, Hc, Wc, stride, strides, V, tm))
             if groups:
                 gw, gb = params[pi + 2], params[pi + 3]
                 last = li == len(plan) - 1          # a stack that ends in GN+SiLU feeds the fp32 token stream
@@ -464,7 +467,7 @@ class VoxelEmbed(Function):
         dx = None
         for li in range(len(plan) - 1, -1, -1):
             cin, cout, stride, groups = plan[li]
-            cin_, Dc, Hc, Wc, stride_, strides, V = geoms[li]
+            cin_, Dc, Hc, Wc, stride_, strides, V, tm = geoms[li]
             if groups:
                 cols, z, mean, rstd = saved[si - 4:si]
                 si -= 4
@@ -480,20 +483,20 @@ class VoxelEmbed(Function):
             dz16 = K.cast_bf16(dz.contiguous())
             grads[pi + 1] = K.colsum_bf16(dz16)
             dwp = _wgrad(dz16, cols)                                    # [cout, Kp]
-            grads[pi] = dwp[:, :cin * 27].reshape(weight.shape)
+            grads[pi] = dwp.view(cout, 3, 3, 3, cin).permute(0, 4, 1, 2, 3).contiguous() if tm else dwp[:, :cin * 27].reshape(weight.shape)
             need_dx = li > 0 or ctx.needs_input_grad[0]
             if need_dx:
-                dcols = _dgrad(dz16, w16(weight, pad_to=cols.shape[1]))
+                dcols = _dgrad(dz16, w16_taps(weight) if tm else w16(weight, pad_to=cols.shape[1]))
                 if li > 0:
                     prev_c = plan[li - 1][1]
                     d_act = torch.empty(xB * Dc * Hc * Wc, prev_c, device=dtok.device, dtype=torch.float32)
-                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, d_act, strides)
+                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, d_act, strides, tap_major=tm)
                     dz = d_act
                 else:
                     # same memory layout as the forward input (e.g. the channels-last view a stage wrapper hands over)
                     dx1 = torch.empty_strided((xB,) + tuple(xshape[1:]), ctx.in_strides, device=dtok.device, dtype=torch.float32) \
                         if xB == B else torch.empty((xB,) + tuple(xshape[1:]), device=dtok.device, dtype=torch.float32)
-                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, dx1, tuple(dx1.stride()))
+                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, dx1, tuple(dx1.stride()), tap_major=tm)
                     if xB != B:
                         dx = torch.zeros(xshape, device=dtok.device, dtype=torch.float32)
                         dx[0] = dx1[0]
