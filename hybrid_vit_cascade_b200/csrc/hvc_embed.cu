@@ -43,6 +43,88 @@ __global__ void __launch_bounds__(256) im2col3d_kernel(const TIn* __restrict__ x
   else cols[idx] = __float2bfloat16(v);
 }
 
+// Cin == 1 (the first conv of every stack: K = 27, Kp = 32): one thread builds one whole 64-byte patch row -- 27 reads that are
+// coalesced along w across the warp, four 16-byte stores -- instead of one thread (and three divisions) per element.
+template <typename TIn>
+__global__ void __launch_bounds__(256) im2col3d_c1_kernel(const TIn* __restrict__ x, bf16* __restrict__ cols, const Conv3dGeom g) {
+  long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)g.B * g.Do * g.Ho * g.Wo;
+  if (m >= total) return;
+  uint4* dst = reinterpret_cast<uint4*>(cols + m * 32);
+  const int ow = (int)(m % g.Wo); m /= g.Wo;
+  const int oh = (int)(m % g.Ho); m /= g.Ho;
+  const int od = (int)(m % g.Do);
+  const int b = (int)(m / g.Do);
+  const TIn* xb = x + b * g.sb;
+  float v[28];
+  v[27] = 0.f;
+#pragma unroll
+  for (int kd = 0; kd < 3; ++kd) {
+    const int id = od * g.stride - 1 + kd;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * g.stride - 1 + kh;
+      const bool ok = id >= 0 && id < g.D && ih >= 0 && ih < g.H;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * g.stride - 1 + kw;
+        v[kd * 9 + kh * 3 + kw] = (ok && iw >= 0 && iw < g.W) ? static_cast<float>(xb[id * g.sd + ih * g.sh + iw * g.sw]) : 0.f;
+      }
+    }
+  }
+  uint32_t u[16];
+#pragma unroll
+  for (int j = 0; j < 14; ++j) u[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+  u[14] = 0u; u[15] = 0u;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dst[j] = make_uint4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
+}
+
+// ---- zero-padded channels-last volumes for the implicit-GEMM conv (hvc_conv_taps) -----------------------------------------------
+// pad: src (B, D, H, W, Cs) f32|bf16, dense channels-last  ->  dst bf16 (B, D+2, H+2, W+2, Cp), Cs <= Cp, both multiples of 8; the
+// border voxels and the channels [Cs, Cp) are written as zeros (no separate memset).  One thread = one 8-channel run.
+template <typename TIn>
+__global__ void __launch_bounds__(256) pad3d_cl_kernel(const TIn* __restrict__ src, bf16* __restrict__ dst, int B, int D, int H, int W,
+                                                       int Cs, int Cp) {
+  const int c8n = Cp >> 3;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * (D + 2) * (H + 2) * (W + 2) * c8n;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % c8n);
+  long long t = idx / c8n;
+  const int w = (int)(t % (W + 2)) - 1; t /= (W + 2);
+  const int h = (int)(t % (H + 2)) - 1; t /= (H + 2);
+  const int d = (int)(t % (D + 2)) - 1;
+  const int b = (int)(t / (D + 2));
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D && c8 * 8 < Cs) {
+    const TIn* p = src + ((((long long)b * D + d) * H + h) * W + w) * Cs + c8 * 8;
+    if constexpr (sizeof(TIn) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+    } else {
+      o = __ldg(reinterpret_cast<const uint4*>(p));
+    }
+  }
+  reinterpret_cast<uint4*>(dst)[idx] = o;
+}
+// unpad: src f32 (B, D+2, H+2, W+2, C) -> dst f32 (B, D, H, W, C) dense, the interior voxels.  One thread = 4 channels.
+__global__ void __launch_bounds__(256) unpad3d_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int D, int H, int W,
+                                                         int C) {
+  const int c4n = C >> 2;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * D * H * W * c4n;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % c4n);
+  long long t = idx / c4n;
+  const int w = (int)(t % W); t /= W;
+  const int h = (int)(t % H); t /= H;
+  const int d = (int)(t % D);
+  const int b = (int)(t / D);
+  const long long prow = (((long long)b * (D + 2) + d + 1) * (H + 2) + h + 1) * (W + 2) + w + 1;
+  reinterpret_cast<float4*>(dst)[idx] = __ldg(reinterpret_cast<const float4*>(src + prow * C) + c4);
+}
+
 // dx[b, c, d, h, w] = sum over taps/outputs that read it of dcols[(b,od,oh,ow), c*27 + tap]
 __global__ void __launch_bounds__(256) col2im3d_kernel(const bf16* __restrict__ dcols, float* __restrict__ dx, const Conv3dGeom g) {
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*D*H*W*Cin, c fastest when channels-last
@@ -270,48 +352,63 @@ __global__ void gn_bwd_finalize_kernel(const float* T1, const float* T2, const f
     Bq[idx] = (float)(a2 / n);
   }
 }
-// forward apply: y = silu(xhat*w + b) (bf16 channels-last).  backward apply: dx = rstd*(ds*w - A - xhat*Bq)
+// forward apply: y = act(xhat*w + b) (bf16 or f32, channels-last).  backward apply: dx = rstd*(ds*w - A - xhat*Bq).
+// A thread keeps one 4-channel group (its statistics and affine terms live in registers) and walks rows_per_block rows of one
+// batch element with four independent 16-byte loads in flight.
 template <int MODE>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
                                                        const float* __restrict__ rstd, const float* __restrict__ w, const float* __restrict__ b,
                                                        const float* __restrict__ A, const float* __restrict__ Bq, bf16* __restrict__ y,
-                                                       float* __restrict__ dx, int B, int V, int C, int cpg, int y_f32, int act) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;   // over B*V*C/4
-  const int tpr = C >> 2;
-  const long long total = (long long)B * V * tpr;
-  if (idx >= total) return;
-  const int cv = (int)(idx % tpr);
-  const long long row = idx / tpr;
-  const int bb = (int)(row / V);
-  const int G = C / cpg;
-  const long long off = row * C + 4 * cv;
-  const float4 xv = __ldg(reinterpret_cast<const float4*>(x + off));
-  const float4 wv = *reinterpret_cast<const float4*>(w + 4 * cv), bv = *reinterpret_cast<const float4*>(b + 4 * cv);
-  const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ws[4] = {wv.x, wv.y, wv.z, wv.w}, bs[4] = {bv.x, bv.y, bv.z, bv.w};
-  float out[4];
-  float dys[4] = {0, 0, 0, 0};
-  if (MODE == 1) {
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + off));
-    dys[0] = d.x; dys[1] = d.y; dys[2] = d.z; dys[3] = d.w;
-  }
+                                                       float* __restrict__ dx, int V, int C, int cpg, int y_f32, int act, int rows_per_block) {
+  const int tpr = C >> 2;                   // threads per row (C/4 <= 256)
+  const int rpp = 256 / tpr;                // rows per pass
+  const int rin = threadIdx.x / tpr, cv = threadIdx.x - rin * tpr;
+  if (rin >= rpp) return;
+  const int bb = blockIdx.y, G = C / cpg;
+  float mu[4], rs[4], ag[4] = {0, 0, 0, 0}, bq[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int g = (4 * cv + e) / cpg;
-    const float mu = mean[bb * G + g], rs = rstd[bb * G + g];
-    const float xh = (xs[e] - mu) * rs;
-    const float z = xh * ws[e] + bs[e];
-    if (MODE == 0) {
-      out[e] = act_fwd(z, act);
-    } else {
-      const float ds = dys[e] * act_grad(z, act);
-      out[e] = rs * (ds * ws[e] - A[bb * G + g] - xh * Bq[bb * G + g]);
-    }
+    const int g = bb * G + (4 * cv + e) / cpg;
+    mu[e] = mean[g];
+    rs[e] = rstd[g];
+    if (MODE == 1) { ag[e] = A[g]; bq[e] = Bq[g]; }
   }
-  if (MODE == 0) {
-    if (y_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + off) = make_float4(out[0], out[1], out[2], out[3]);
-    else *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_bf16(out[0], out[1]), pack_bf16(out[2], out[3]));
-  } else {
-    *reinterpret_cast<float4*>(dx + off) = make_float4(out[0], out[1], out[2], out[3]);
+  const float4 wv = *reinterpret_cast<const float4*>(w + 4 * cv), bv = *reinterpret_cast<const float4*>(b + 4 * cv);
+  const float ws[4] = {wv.x, wv.y, wv.z, wv.w}, bs[4] = {bv.x, bv.y, bv.z, bv.w};
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, V);
+  for (int r = r0 + rin; r < r1; r += 4 * rpp) {
+    float4 xv[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * rpp;
+      if (rr < r1) {
+        const long long off = ((long long)bb * V + rr) * C + 4 * cv;
+        xv[u] = __ldg(reinterpret_cast<const float4*>(x + off));
+        if (MODE == 1) dv[u] = __ldg(reinterpret_cast<const float4*>(dy + off));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int rr = r + u * rpp;
+      if (rr >= r1) break;
+      const long long off = ((long long)bb * V + rr) * C + 4 * cv;
+      const float xs[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      const float dys[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+      float out[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float xh = (xs[e] - mu[e]) * rs[e];
+        const float z = xh * ws[e] + bs[e];
+        if (MODE == 0) out[e] = act_fwd(z, act);
+        else out[e] = rs[e] * (dys[e] * act_grad(z, act) * ws[e] - ag[e] - xh * bq[e]);
+      }
+      if (MODE == 0) {
+        if (y_f32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + off) = make_float4(out[0], out[1], out[2], out[3]);
+        else *reinterpret_cast<uint2*>(y + off) = make_uint2(pack_bf16(out[0], out[1]), pack_bf16(out[2], out[3]));
+      } else {
+        *reinterpret_cast<float4*>(dx + off) = make_float4(out[0], out[1], out[2], out[3]);
+      }
+    }
   }
 }
 
@@ -337,8 +434,15 @@ extern "C" int hvc_im2col3d(const void* x, int32_t x_is_bf16, const hvc_conv3d_g
   const long long total = (long long)g.B * g.Do * g.Ho * g.Wo * g.Kp;
   const unsigned blocks = (unsigned)((total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (x_is_bf16) im2col3d_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(cols), g);
-  else im2col3d_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(cols), g);
+  if (g.Cin == 1) {
+    const unsigned rb = (unsigned)(((long long)g.B * g.Do * g.Ho * g.Wo + 255) / 256);
+    if (x_is_bf16) im2col3d_c1_kernel<bf16><<<rb, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(cols), g);
+    else im2col3d_c1_kernel<float><<<rb, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(cols), g);
+  } else if (x_is_bf16) {
+    im2col3d_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(cols), g);
+  } else {
+    im2col3d_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<bf16*>(cols), g);
+  }
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
@@ -404,6 +508,27 @@ extern "C" int hvc_col2im3d_cl(const void* dcols, const hvc_conv3d_geom* geom, f
   return HVC_OK;
 }
 
+extern "C" int hvc_pad3d_cl(const void* src, int32_t src_is_bf16, void* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cs,
+                            int32_t Cp, void* stream) {
+  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0, "hvc_pad3d_cl: bad arguments");
+  HVC_CHECK_ARG(Cs > 0 && Cs % 8 == 0 && Cp % 8 == 0 && Cs <= Cp, "hvc_pad3d_cl: channel counts must be multiples of 8, Cs <= Cp");
+  const long long total = (long long)B * (D + 2) * (H + 2) * (W + 2) * (Cp / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (src_is_bf16) pad3d_cl_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, Cs, Cp);
+  else pad3d_cl_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, Cs, Cp);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_unpad3d_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream) {
+  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hvc_unpad3d_cl: bad arguments");
+  const long long total = (long long)B * D * H * W * (C / 4);
+  unpad3d_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, B, D, H, W, C);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
 static int gn_rows_per_block(int B, int V) {
   int rpb = 1024;
   while (rpb > 32 && (long long)B * ((V + rpb - 1) / rpb) < 4LL * device_sm_count()) rpb >>= 1;
@@ -428,9 +553,9 @@ extern "C" int hvc_norm_act_fwd(const float* x, const float* w, const float* b, 
     gn_fwd_finalize_kernel<<<(B * groups + 127) / 128, 128, 0, st>>>(a.S1, a.S2, mean, rstd, B, C, cpg, V);
     HVC_LAUNCH_CHECK();
   }
-  const long long total = (long long)B * V * (C / 4);
-  gn_apply_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, nullptr, mean, rstd, w, b, nullptr, nullptr, reinterpret_cast<bf16*>(y),
-                                                                      nullptr, B, V, C, cpg, y_is_bf16 ? 0 : 1, activation);
+  const int rpb = gn_rows_per_block(B, V);
+  gn_apply_kernel<0><<<dim3((V + rpb - 1) / rpb, B), 256, 0, st>>>(x, nullptr, mean, rstd, w, b, nullptr, nullptr, reinterpret_cast<bf16*>(y),
+                                                                   nullptr, V, C, cpg, y_is_bf16 ? 0 : 1, activation, rpb);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
@@ -463,8 +588,8 @@ extern "C" int hvc_norm_act_bwd(const float* dy, const float* x, const float* w,
   gn_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, st>>>(T1, T2, w, dw, db, A, Bq, B, C, a.cpg, V);
   HVC_LAUNCH_CHECK();
   if (stats_frozen) HVC_CUDA(cudaMemsetAsync(A, 0, sizeof(float) * 2 * B * groups, st));   // eval-mode BatchNorm: statistics are constants
-  const long long total = (long long)B * V * (C / 4);
-  gn_apply_kernel<1><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, B, V, C, a.cpg, 0, activation);
+  gn_apply_kernel<1><<<dim3((V + a.rows_per_block - 1) / a.rows_per_block, B), 256, 0, st>>>(x, dy, mean, rstd, w, b, A, Bq, nullptr, dx, V, C,
+                                                                                             a.cpg, 0, activation, a.rows_per_block);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

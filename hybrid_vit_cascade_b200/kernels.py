@@ -700,3 +700,23 @@ def chan_dot_bwd(dout, y, w):
     _lib.check(_lib.lib().hvc_chan_dot_bwd(_ptr(dout), _ptr(y), _ptr(w), _ptr(dy), _ptr(dwb), C.c_void_p(dwb.data_ptr() + 4 * Cc),
                                            C.c_int64(M), Cc, _stream()), "hvc_chan_dot_bwd")
     return dy, dwb[:Cc], dwb[Cc:]
+
+
+def pad3d_cl(src, B, D, H, W, Cs, Cp):
+    """src (B, D, H, W, Cs) f32|bf16 dense channels-last -> zero-padded bf16 (B, D+2, H+2, W+2, Cp)."""
+    _need_cuda(src)
+    assert src.is_contiguous() and src.numel() == B * D * H * W * Cs and src.dtype in (torch.float32, torch.bfloat16)
+    dst = torch.empty(B, D + 2, H + 2, W + 2, Cp, device=src.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().hvc_pad3d_cl(_ptr(src), int(src.dtype == torch.bfloat16), _ptr(dst), B, D, H, W, Cs, Cp, _stream()), "hvc_pad3d_cl")
+    return dst
+
+
+def unpad3d_cl(src, B, D, H, W, Cc, out=None):
+    """src f32 (B, D+2, H+2, W+2, C) contiguous -> f32 (B, D, H, W, C) dense."""
+    _need_cuda(src)
+    assert src.is_contiguous() and src.dtype == torch.float32 and src.numel() == B * (D + 2) * (H + 2) * (W + 2) * Cc
+    if out is None:
+        out = torch.empty(B, D, H, W, Cc, device=src.device, dtype=torch.float32)
+    assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == B * D * H * W * Cc
+    _lib.check(_lib.lib().hvc_unpad3d_cl(_ptr(src), _ptr(out), B, D, H, W, Cc, _stream()), "hvc_unpad3d_cl")
+    return out

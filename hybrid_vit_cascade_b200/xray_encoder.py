@@ -335,8 +335,10 @@ CONV3D_IMPLICIT = True
 
 
 def _pad_cl(src_cl, B, D, H, W, Cc, Cp):
-    """(B, D, H, W, Cc) view (any float dtype) -> zero-padded bf16 (B, D+2, H+2, W+2, Cp) buffer, Cc <= Cp."""
-    out = torch.zeros(B, D + 2, H + 2, W + 2, Cp, device=src_cl.device, dtype=torch.bfloat16)
+    """(B, D, H, W, Cc) view (f32 or bf16) -> zero-padded bf16 (B, D+2, H+2, W+2, Cp) buffer, Cc <= Cp."""
+    if src_cl.is_contiguous() and Cc % 8 == 0:
+        return K.pad3d_cl(src_cl, B, D, H, W, Cc, Cp)
+    out = torch.zeros(B, D + 2, H + 2, W + 2, Cp, device=src_cl.device, dtype=torch.bfloat16)       # other layouts: strided torch copy
     out[:, 1:-1, 1:-1, 1:-1, :Cc].copy_(src_cl)
     return out
 
@@ -384,7 +386,7 @@ class Conv3dGnGelu(Function):
             # rows = padded voxels; a tap (kd, kh, kw) is a shift of (kd-1)*(H+2)*(W+2) + (kh-1)*(W+2) + (kw-1) rows
             cols = _pad_cl(xf.permute(0, 2, 3, 4, 1), B, D, H, W, Cin, Cin)
             zpad = K.gemm(cols.view(-1, Cin), w_16, bias=conv_b, epilogue=K.EPI_F32, taps=(1, Cin, (H + 2) * (W + 2), W + 2, 1))
-            z = zpad.view(B, D + 2, H + 2, W + 2, Cout)[:, 1:-1, 1:-1, 1:-1].reshape(B * V, Cout)
+            z = K.unpad3d_cl(zpad, B, D, H, W, Cout).view(B * V, Cout)
             del zpad
         elif slabs is None:
             cols = K.im2col3d(xf, B, Cin, D, H, W, 1, tuple(xf.stride()), tap_major=tm)
@@ -426,7 +428,11 @@ class Conv3dGnGelu(Function):
                         taps=(2, Cin, sd, sh, 1))[:Cout]
             if need_dx:
                 dxp = K.gemm(dzp, ops.w16_taps_t(conv_w, Cp), epilogue=K.EPI_F32, taps=(1, Cp, -sd, -sh, -1))
-                dx.permute(0, 2, 3, 4, 1).copy_(dxp.view(B, D + 2, H + 2, W + 2, Cin)[:, 1:-1, 1:-1, 1:-1])
+                dx_cl = dx.permute(0, 2, 3, 4, 1)
+                if dx_cl.is_contiguous():
+                    K.unpad3d_cl(dxp, B, D, H, W, Cin, out=dx_cl)
+                else:
+                    dx_cl.copy_(dxp.view(B, D + 2, H + 2, W + 2, Cin)[:, 1:-1, 1:-1, 1:-1])
                 del dxp
             return dx, dw.view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3).contiguous(), dconv_b, dgn_w, dgn_b, None
         w_16 = ops.w16_taps(conv_w) if tm else ops.w16(conv_w, pad_to=Kp)

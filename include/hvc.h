@@ -248,6 +248,12 @@ int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void
  * convs of the cascade's detail_enhancer (progressive_cascade/model_progressive.py:263). */
 int hvc_im2col3d_cl(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream);
 int hvc_col2im3d_cl(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream);
+/* Zero-padded channels-last volumes, the operand layout of the implicit-GEMM conv (hvc_conv_taps):
+ * pad:   src (B, D, H, W, Cs) f32|bf16 dense -> dst bf16 (B, D+2, H+2, W+2, Cp); border voxels and channels [Cs, Cp) are zero-filled.
+ * unpad: src f32 (B, D+2, H+2, W+2, C) -> dst f32 (B, D, H, W, C) dense (the interior voxels).   Cs, Cp % 8 == 0; C % 4 == 0. */
+int hvc_pad3d_cl(const void* src, int32_t src_is_bf16, void* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cs, int32_t Cp,
+                 void* stream);
+int hvc_unpad3d_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream);
 /* y [B,V,C] (bf16, or f32 when it feeds the token stream) = SiLU(GroupNorm(x f32 [B,V,C])); mean/rstd f32
  * [B,groups] saved; scratch f32 [2*B*C]. */
 int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C,
