@@ -51,6 +51,12 @@ struct GemmKArgs {
   // implicit 3x3x3 convolution over a zero-padded channels-last volume (hvc_gemm_args::taps): the operand on `taps_side` is a
   // [padded voxels, tap_cin] matrix read with a per-tap row shift instead of a materialised patch matrix
   int taps_side, tap_cin, tap_sd, tap_sh, tap_sw;
+  int n_mma;      // N of the tcgen05.mma: 128, or 64 / 32 when the whole problem is that narrow (the Cout = 32 / 64 convs of the stage
+                  // wrappers).  The B box then has n_mma rows, and an operand half that lies wholly outside the problem is not loaded:
+                  // measured on B200, a TMA box that is mostly out-of-bounds zero fill costs far more than the same box of data
+                  // (profiles/r01_implicit_conv_gemm.log)
+  int a_halves, b_halves;   // MN-major operands: 64-element halves to load per k-block (2, or 1 when M / N <= 64)
+  uint32_t stage_tx;        // bytes one stage's loads deliver
 };
 
 // row shift of tap = kd*9 + kh*3 + kw: (kd-1)*sd + (kh-1)*sh + (kw-1)*sw
@@ -258,7 +264,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           uint8_t* sA = smem + stage * kStageBytes;
           uint8_t* sB = sA + kTileBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx);
           if (A_MAJOR == kMajorK) {
             if (p.taps_side == 1) {   // k-block kb lies inside one tap (tap_cin % BK == 0): columns of that tap, rows shifted
               const int k = kb * BK, tap = k / p.tap_cin;
@@ -268,7 +274,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           } else {
             tma_load_2d(sA, &tmA, &full_bar[stage], it.m0, kb * BK);
-            tma_load_2d(sA + kTileBytes / 2, &tmA, &full_bar[stage], it.m0 + 64, kb * BK);
+            if (p.a_halves == 2) tma_load_2d(sA + kTileBytes / 2, &tmA, &full_bar[stage], it.m0 + 64, kb * BK);
           }
           if (B_MAJOR == kMajorK) {
             tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, it.n0);
@@ -278,7 +284,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64 - t1 * p.tap_cin, kb * BK + tap_shift(p, t1));
           } else {
             tma_load_2d(sB, &tmB, &full_bar[stage], it.n0, kb * BK);
-            tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64, kb * BK);
+            if (p.b_halves == 2) tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64, kb * BK);
           }
         }
         __syncwarp();
@@ -287,7 +293,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MAJOR, B_MAJOR);
+    const uint32_t idesc = make_idesc_bf16(BM, static_cast<uint32_t>(p.n_mma), A_MAJOR, B_MAJOR);
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const WorkItem it = decode_work(p, w);
@@ -331,6 +337,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = it.n0 + half * 64 + c * 32;
+        if (col0 >= p.N) break;                 // nothing of this chunk is stored (and a narrow MMA never wrote these TMEM columns)
         const bool fast = p.v256 && row < p.M && col0 + 32 <= p.N;
         uint32_t v[32];
         Side side;
@@ -397,12 +404,13 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   if (tp.side == 2) HVC_CHECK_ARG(a->b_major == 1 && tp.cin > 0 && tp.cin % 64 == 0 && a->N == 27 * tp.cin,
                                   "hvc_gemm: taps on B need an MN-major B, cin %% 64 == 0 and N == 27*cin");
 
+  const int n_mma = (a->N <= 32 && a->b_major == 0) ? 32 : (a->N <= 64 ? 64 : BN);   // an MN-major B keeps whole 64-element swizzle rows
   CUtensorMap tmA, tmB;
   int rc;
   if (a->a_major == 0) rc = make_tmap_2d(&tmA, a->A, 2, a->M, tp.side == 1 ? tp.cin : a->K, a->lda, BK, BM, true);
   else                 rc = make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, 64, BK, true);
   if (rc) return rc;
-  if (a->b_major == 0) rc = make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, BK, BN, true);
+  if (a->b_major == 0) rc = make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, BK, n_mma, true);
   else                 rc = make_tmap_2d(&tmB, a->B, 2, a->K, tp.side == 2 ? tp.cin : a->N, a->ldb, 64, BK, true);
   if (rc) return rc;
 
@@ -422,6 +430,11 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   ka.alpha = a->alpha;
   ka.drop = make_drop(a->drop);
   ka.taps_side = tp.side; ka.tap_cin = tp.cin; ka.tap_sd = tp.sd; ka.tap_sh = tp.sh; ka.tap_sw = tp.sw;
+  ka.n_mma = n_mma;
+  ka.a_halves = (a->a_major == 1 && a->M <= 64) ? 1 : 2;
+  ka.b_halves = (a->b_major == 1 && a->N <= 64) ? 1 : 2;
+  ka.stage_tx = (a->a_major == 0 ? kTileBytes : ka.a_halves * (kTileBytes / 2)) +
+                (a->b_major == 0 ? n_mma * BK * 2 : ka.b_halves * (kTileBytes / 2));
   {
     auto ok32 = [](const void* ptr, long long ld, int esz) {
       return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31u) == 0 && ((ld * esz) & 31) == 0);

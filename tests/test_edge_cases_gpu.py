@@ -59,6 +59,53 @@ def test_gemm_smallest_and_ragged_shapes(M, N, Kd):
     assert O.max_rel(outr, ref + resid) < 1e-5
 
 
+@pytest.mark.parametrize("N", [8, 32, 40, 64, 72])
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_gemm_narrow_n_all_operand_layouts(N, a_major, b_major):
+    """N <= 64 problems issue a narrower tcgen05.mma (32 or 64 columns instead of 128): every operand-layout combination, ragged N,
+    several M tiles and k-blocks."""
+    from hybrid_vit_cascade_b200 import kernels as K
+    M, Kd = 384 + 8, 200
+    g = torch.Generator(device="cuda").manual_seed(N * 7 + a_major * 2 + b_major)
+    a = torch.randn(M, Kd, device="cuda", generator=g).bfloat16()
+    b = torch.randn(N, Kd, device="cuda", generator=g).bfloat16()
+    ref = a.float() @ b.float().t()
+    out = K.gemm(a.t().contiguous() if a_major else a, b.t().contiguous() if b_major else b, a_major=a_major, b_major=b_major,
+                 epilogue=K.EPI_F32)
+    assert out.shape == (M, N) and O.max_rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("Cin,Cout", [(64, 32), (64, 64), (128, 96)])
+def test_gemm_implicit_conv_taps_match_conv3d(Cin, Cout):
+    """hvc_conv_taps: the GEMM reads a zero-padded channels-last volume with per-tap row shifts instead of a patch matrix.  Side 1 =
+    forward conv (and data gradient with negated strides + transposed filter), side 2 = weight gradient; against fp64 conv3d on the
+    bf16-rounded operands."""
+    import torch.nn.functional as F
+    from hybrid_vit_cascade_b200 import kernels as K
+    B, D, H, W = 2, 5, 6, 7
+    g = torch.Generator(device="cuda").manual_seed(Cin + Cout)
+    x = torch.randn(B, Cin, D, H, W, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (27 * Cin) ** -0.5).bfloat16()
+    dz = torch.randn(B, Cout, D, H, W, device="cuda", generator=g).bfloat16()
+    xd, wd, dzd = x.double().requires_grad_(True), w.double().requires_grad_(True), dz.double()
+    ref = F.conv3d(xd, wd, padding=1)
+    (ref * dzd).sum().backward()
+    sd, sh = (H + 2) * (W + 2), W + 2
+    xp = K.pad3d_cl(x.permute(0, 2, 3, 4, 1).contiguous(), B, D, H, W, Cin, Cin)
+    w_taps = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous()
+    zp = K.gemm(xp.view(-1, Cin), w_taps, epilogue=K.EPI_F32, taps=(1, Cin, sd, sh, 1))
+    z = K.unpad3d_cl(zp, B, D, H, W, Cout).permute(0, 4, 1, 2, 3)
+    assert O.max_rel(z, ref) < 1e-5
+    Cp = (Cout + 63) // 64 * 64
+    dzp = K.pad3d_cl(dz.permute(0, 2, 3, 4, 1).contiguous(), B, D, H, W, Cout, Cp).view(-1, Cp)
+    dw = K.gemm(dzp, xp.view(-1, Cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=3, taps=(2, Cin, sd, sh, 1))[:Cout]
+    assert O.max_rel(dw.view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3), wd.grad) < 1e-5
+    wt = torch.zeros(Cin, 27, Cp, device="cuda", dtype=torch.bfloat16)
+    wt[:, :, :Cout] = w.reshape(Cout, Cin, 27).permute(1, 2, 0)
+    dxp = K.gemm(dzp, wt.view(Cin, 27 * Cp), epilogue=K.EPI_F32, taps=(1, Cp, -sd, -sh, -1))
+    assert O.max_rel(K.unpad3d_cl(dxp, B, D, H, W, Cin).permute(0, 4, 1, 2, 3), xd.grad) < 1e-5
+
+
 def test_layernorm_odd_token_counts():
     from hybrid_vit_cascade_b200 import kernels as K
     g = torch.Generator(device="cuda").manual_seed(4)
