@@ -32,6 +32,60 @@ __global__ void __launch_bounds__(256) box1d_kernel(const float* __restrict__ x,
   out[i] = acc * (1.0f / k);
 }
 
+// The same filter with the window kept in registers (bit-identical sums: same ascending order, absent positions add 0.0f).
+// Along W (contiguous axis): one thread produces CH consecutive outputs from CH + K - 1 loads.
+template <int K, int CH>
+__global__ void __launch_bounds__(256) box1d_row_kernel(const float* __restrict__ x, float* __restrict__ out, long long chunks, int len,
+                                                        int chunks_per_row) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= chunks) return;
+  const long long row = t / chunks_per_row;
+  const int c0 = (int)(t - row * chunks_per_row) * CH;
+  const float* px = x + row * len;
+  float v[CH + K - 1];
+#pragma unroll
+  for (int j = 0; j < CH + K - 1; ++j) {
+    const int pos = c0 - K / 2 + j;
+    v[j] = (pos >= 0 && pos < len) ? __ldg(px + pos) : 0.f;
+  }
+#pragma unroll
+  for (int o = 0; o < CH; ++o) {
+    if (c0 + o >= len) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc += v[o + j];
+    out[row * len + c0 + o] = acc * (1.0f / K);
+  }
+}
+// Along H or D (element stride `inner`): one thread walks one line with a K-deep register window; neighbouring threads are
+// neighbouring `inner` positions, so every load and store is coalesced and each input is read once.
+template <int K>
+__global__ void __launch_bounds__(256) box1d_line_kernel(const float* __restrict__ x, float* __restrict__ out, long long lines, int len,
+                                                         long long inner) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t >= lines) return;
+  const long long o = t / inner, base = o * len * inner + (t - o * inner);
+  const float* px = x + base;
+  float* po = out + base;
+  constexpr int R = K / 2;
+  float w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int pos = j - R;
+    w[j] = (pos >= 0 && pos < len) ? __ldg(px + pos * inner) : 0.f;
+  }
+  for (int p = 0; p < len; ++p) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc += w[j];
+    po[p * inner] = acc * (1.0f / K);
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) w[j] = w[j + 1];
+    const int np = p + 1 + R;
+    w[K - 1] = np < len ? __ldg(px + np * inner) : 0.f;
+  }
+}
+
 __device__ __forceinline__ void ssim_terms(float mp, float mt, float epp, float ett, float ept, float& A1, float& A2, float& B1, float& B2) {
   A1 = 2.f * mp * mt + kC1;
   A2 = 2.f * (ept - mp * mt) + kC2;
@@ -101,6 +155,19 @@ static int box3d(const float* in, float* tmp, float* out, int stack, int D, int 
   // three passes: W (in -> out), H (out -> tmp), D (tmp -> out)
   const long long total = (long long)stack * D * H * W;
   const unsigned blocks = (unsigned)((total + 255) / 256);
+  if (k == 11) {   // the reference window (model_direct.py:88): register-window kernels
+    constexpr int CH = 8;
+    const int cpr = (W + CH - 1) / CH;
+    const long long chunks = (long long)stack * D * H * cpr;
+    box1d_row_kernel<11, CH><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(in, out, chunks, W, cpr);
+    HVC_LAUNCH_CHECK();
+    const long long lines_h = (long long)stack * D * W, lines_d = (long long)stack * H * W;
+    box1d_line_kernel<11><<<(unsigned)((lines_h + 255) / 256), 256, 0, st>>>(out, tmp, lines_h, H, W);
+    HVC_LAUNCH_CHECK();
+    box1d_line_kernel<11><<<(unsigned)((lines_d + 255) / 256), 256, 0, st>>>(tmp, out, lines_d, D, (long long)H * W);
+    HVC_LAUNCH_CHECK();
+    return HVC_OK;
+  }
   box1d_kernel<<<blocks, 256, 0, st>>>(in, out, total, W, 1, k);
   HVC_LAUNCH_CHECK();
   box1d_kernel<<<blocks, 256, 0, st>>>(out, tmp, total, H, W, k);
