@@ -135,10 +135,10 @@ __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[kWgCols], uint3
       }
       if (DROP) {
         const uint4 rk = lds_u4(rk_saddr + t * 4);
-        e0.x = mum32(rk.x ^ colkey, 0x2545F491u) >= thr ? e0.x : -e0.x;
-        e0.y = mum32(rk.y ^ colkey, 0x2545F491u) >= thr ? e0.y : -e0.y;
-        e1.x = mum32(rk.z ^ colkey, 0x2545F491u) >= thr ? e1.x : -e1.x;
-        e1.y = mum32(rk.w ^ colkey, 0x2545F491u) >= thr ? e1.y : -e1.y;
+        e0.x = (rk.x ^ colkey) * kDropMix >= thr ? e0.x : -e0.x;
+        e0.y = (rk.y ^ colkey) * kDropMix >= thr ? e0.y : -e0.y;
+        e1.x = (rk.z ^ colkey) * kDropMix >= thr ? e1.x : -e1.x;
+        e1.y = (rk.w ^ colkey) * kDropMix >= thr ? e1.y : -e1.y;
       }
       pv[t >> 1] = e0;
       pv[(t >> 1) + 1] = e1;
@@ -460,7 +460,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t colkey = 0, thr = 0;
     float inv_keep = 1.f;
     if (DROP) {
-      colkey = static_cast<uint32_t>(j * kBT + r) * kDropColMul;
+      colkey = drop_colterm(static_cast<uint32_t>(j * kBT + r));
       thr = p.drop.thr;
       inv_keep = p.drop.inv_keep;
     }

@@ -120,9 +120,9 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
       e.y = (c0 + c + 1 < tail) ? e.y : 0.f;
     }
     sum = fadd2(sum, e);
-    if (DROP) {
-      e.x = drop_keep(rowkey, col0 + c0 + c, thr) ? e.x : 0.f;
-      e.y = drop_keep(rowkey, col0 + c0 + c + 1, thr) ? e.y : 0.f;
+    if (DROP) {   // rowkey here is the block key of this 128-key tile (drop_blockkey); c0 + c is the column inside it
+      e.x = drop_keep_in_block(rowkey, c0 + c, thr) ? e.x : 0.f;
+      e.y = drop_keep_in_block(rowkey, c0 + c + 1, thr) ? e.y : 0.f;
     }
     pk[c >> 1] = pack_bf16(e.x, e.y);
   }
@@ -136,6 +136,7 @@ __device__ __forceinline__ float softmax_exp(uint32_t tS, int tail, float scale2
                                              uint32_t rowkey, uint32_t col0, uint32_t thr, bool trace_on, int role, int j) {
   const float2 scale2v = make_float2(scale2, scale2), neg_m = make_float2(-m, -m);
   float2 sum = make_float2(0.f, 0.f);
+  if (DROP) rowkey = drop_blockkey(rowkey, col0);   // col0 is a multiple of the 128-key tile
   uint32_t bufa[32], bufb[32];
   tmem_ld_32x32(tS, bufa);
   named_bar_sync(turn_bar, 256);

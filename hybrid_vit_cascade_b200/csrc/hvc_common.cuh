@@ -437,7 +437,7 @@ struct DropCfg {
   uint32_t k0, k1, site, thr;   // drop element iff hash < thr (thr = p * 2^32)
   float inv_keep;               // 1 / (1 - p)
 };
-__device__ __forceinline__ uint32_t mum32(uint32_t a, uint32_t b) {
+__host__ __device__ __forceinline__ uint32_t mum32(uint32_t a, uint32_t b) {
   const uint64_t w = static_cast<uint64_t>(a) * b;
   return static_cast<uint32_t>(w) ^ static_cast<uint32_t>(w >> 32);
 }
@@ -446,8 +446,19 @@ __device__ __forceinline__ uint32_t drop_rowkey(const DropCfg& c, uint32_t row) 
   h = mum32(h ^ c.site ^ c.k1, 0x85EBCA77u);
   return mum32(h + 0x6A09E667u, 0xC2B2AE3Du);
 }
-constexpr uint32_t kDropColMul = 0x9E3779B1u;
-__device__ __forceinline__ uint32_t drop_hash(uint32_t rowkey, uint32_t col) { return mum32(rowkey ^ (col * kDropColMul), 0x2545F491u); }
+// Element (row, col) of a site: keep iff ((rowkey ^ colterm(col)) * kDropMix) mod 2^32 >= thr.  The decision sits in the TOP bits of a
+// 32-bit multiplicative hash, which every bit of its argument reaches; colterm = hash(col / 128) ^ ((col % 128) * kDropColMul), so
+// inside a 128-column tile the per-element work is one xor with a constant, one 32-bit multiply, one compare and one select
+// (the first version used a 64-bit multiply-and-fold per element: 6-7 issue slots, which nearly halved the attention forward).
+constexpr uint32_t kDropColMul = 0x9E3779B1u, kDropBlkMul = 0xC2B2AE3Du, kDropMix = 0x2545F491u;
+__host__ __device__ __forceinline__ uint32_t drop_blockterm(uint32_t col) { return mum32(col >> 7, kDropBlkMul); }
+__device__ __forceinline__ uint32_t drop_colterm(uint32_t col) { return drop_blockterm(col) ^ ((col & 127u) * kDropColMul); }
+// rowkey ^ blockterm once per (row, 128-column block), then per element with the column's offset inside the block
+__device__ __forceinline__ uint32_t drop_blockkey(uint32_t rowkey, uint32_t col) { return rowkey ^ drop_blockterm(col); }
+__device__ __forceinline__ bool drop_keep_in_block(uint32_t blockkey, uint32_t col_in_block, uint32_t thr) {
+  return (blockkey ^ (col_in_block * kDropColMul)) * kDropMix >= thr;
+}
+__device__ __forceinline__ uint32_t drop_hash(uint32_t rowkey, uint32_t col) { return (rowkey ^ drop_colterm(col)) * kDropMix; }
 __device__ __forceinline__ bool drop_keep(uint32_t rowkey, uint32_t col, uint32_t thr) { return drop_hash(rowkey, col) >= thr; }
 // host-side description -> kernel config (reads the seed words on the device)
 struct DropArg {

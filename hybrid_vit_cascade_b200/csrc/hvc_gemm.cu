@@ -89,9 +89,10 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKArgs& p, int w) {
 // nn.Dropout on the 32 values of one row chunk: element (row, col) of this site, see hvc_common.cuh
 __device__ __forceinline__ void epilogue_dropout(const GemmKArgs& p, float (&v)[32], int row, int col0) {
   const DropCfg dc = drop_load(p.drop);
-  const uint32_t rk = drop_rowkey(dc, static_cast<uint32_t>(row));
+  const uint32_t bk = drop_blockkey(drop_rowkey(dc, static_cast<uint32_t>(row)), static_cast<uint32_t>(col0));   // col0 % 32 == 0
+  const uint32_t c_in = static_cast<uint32_t>(col0) & 127u;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = drop_keep(rk, static_cast<uint32_t>(col0 + j), dc.thr) ? v[j] * dc.inv_keep : 0.f;
+  for (int j = 0; j < 32; ++j) v[j] = drop_keep_in_block(bk, c_in + j, dc.thr) ? v[j] * dc.inv_keep : 0.f;
 }
 
 // ---------------------------------------------------------------- epilogue for one 32-column chunk

@@ -288,10 +288,11 @@ __global__ void __launch_bounds__(256) resid_bwd_kernel(const ResidBwdArgs a) {
         s2[i].z += d[i].z * br[i].z; s2[i].w += d[i].w * br[i].w;
       }
       if (a.drop.seed != nullptr) {   // d(pre-dropout branch) = mask / (1-p) * gate * dout
-        d[i].x = drop_keep(rk, c, a.drop.thr) ? d[i].x * a.drop.inv_keep : 0.f;
-        d[i].y = drop_keep(rk, c + 1, a.drop.thr) ? d[i].y * a.drop.inv_keep : 0.f;
-        d[i].z = drop_keep(rk, c + 2, a.drop.thr) ? d[i].z * a.drop.inv_keep : 0.f;
-        d[i].w = drop_keep(rk, c + 3, a.drop.thr) ? d[i].w * a.drop.inv_keep : 0.f;
+        const uint32_t bk = drop_blockkey(rk, c), cl = static_cast<uint32_t>(c) & 127u;     // c % 4 == 0: one 128-column block
+        d[i].x = drop_keep_in_block(bk, cl, a.drop.thr) ? d[i].x * a.drop.inv_keep : 0.f;
+        d[i].y = drop_keep_in_block(bk, cl + 1, a.drop.thr) ? d[i].y * a.drop.inv_keep : 0.f;
+        d[i].z = drop_keep_in_block(bk, cl + 2, a.drop.thr) ? d[i].z * a.drop.inv_keep : 0.f;
+        d[i].w = drop_keep_in_block(bk, cl + 3, a.drop.thr) ? d[i].w * a.drop.inv_keep : 0.f;
       }
       s1[i].x += d[i].x; s1[i].y += d[i].y; s1[i].z += d[i].z; s1[i].w += d[i].w;
       if (c < a.C) {
