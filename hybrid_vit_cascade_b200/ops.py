@@ -24,6 +24,9 @@ def _sms(dev):
     return _SM_COUNT[i]
 
 
+# stride-1 embedding convs with Cin % 64 == 0 run as implicit GEMMs (hvc_conv_taps); False = the patch-matrix path (tests compare the two)
+IMPLICIT_EMBED = True
+
 # ------------------------------------------------------------------ bf16 weight cache
 _W16 = {}
 
@@ -416,11 +419,21 @@ class VoxelEmbed(Function):
             _, Dc, Hc, Wc = dims
             weight, bias = params[pi], params[pi + 1]
             # channels-last inputs (every layer after the first, and the stage wrappers' 32-channel volume) use the tap-major patch
-            # matrix: whole 8-channel runs per access in im2col and col2im (hvc_im2col3d_cl)
+            # matrix: whole 8-channel runs per access in im2col and col2im (hvc_im2col3d_cl).  A stride-1 layer whose input has a
+            # multiple of 64 channels (the last conv of every stack in the reference's configurations) needs no patch matrix at all:
+            # implicit GEMM on the zero-padded volume (hvc_conv_taps)
             tm = cin % 8 == 0 and strides[1] == 1 and all(s % 8 == 0 for s in strides[:1] + strides[2:]) and (li > 0 or xB == B)
-            cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides, tap_major=tm)
+            implicit = IMPLICIT_EMBED and tm and stride == 1 and cin % 64 == 0 and li > 0 and cout % 8 == 0
             Do, Ho, Wo = K.conv_out(Dc, stride), K.conv_out(Hc, stride), K.conv_out(Wc, stride)
-            z = K.gemm(cols, w16_taps(weight) if tm else w16(weight, pad_to=cols.shape[1]), bias=bias, epilogue=K.EPI_F32)   # [xB*V, cout] channels-last
+            if implicit:
+                cols = K.pad3d_cl(a.view(xB, Dc, Hc, Wc, cin), xB, Dc, Hc, Wc, cin, cin)
+                zp = K.gemm(cols.view(-1, cin), w16_taps(weight), bias=bias, epilogue=K.EPI_F32, taps=(1, cin, (Hc + 2) * (Wc + 2), Wc + 2, 1))
+                z = K.unpad3d_cl(zp, xB, Dc, Hc, Wc, cout).view(-1, cout)
+                del zp
+            else:
+                cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides, tap_major=tm)
+                z = K.gemm(cols, w16_taps(weight) if tm else w16(weight, pad_to=cols.shape[1]), bias=bias, epilogue=K.EPI_F32)   # [xB*V, cout] channels-last
+            tm = 2 if implicit else int(tm)
             V = Do * Ho * Wo
             geoms.append((cin, Dc, Hc, Wc, stride, strides, V, tm))
             if groups:
@@ -482,21 +495,34 @@ class VoxelEmbed(Function):
                 pi -= 2
             dz16 = K.cast_bf16(dz.contiguous())
             grads[pi + 1] = K.colsum_bf16(dz16)
+            need_dx = li > 0 or ctx.needs_input_grad[0]
+            if tm == 2:       # implicit GEMM: padded output gradient (channels padded to whole 64-wide k-blocks), no patch matrices
+                cp = (cout + 63) // 64 * 64
+                sd_, sh_ = (Hc + 2) * (Wc + 2), Wc + 2
+                dzp = K.pad3d_cl(dz16.view(xB, Dc, Hc, Wc, cout), xB, Dc, Hc, Wc, cout, cp).view(-1, cp)
+                tiles = ((cp + 127) // 128) * ((27 * cin + 127) // 128)
+                splits = max(1, min(dzp.shape[0] // 64, (16 * _sms(dtok.device)) // tiles))
+                dwp = K.gemm(dzp, cols.view(-1, cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=splits,
+                             taps=(2, cin, sd_, sh_, 1))[:cout]
+                grads[pi] = dwp.view(cout, 3, 3, 3, cin).permute(0, 4, 1, 2, 3).contiguous()
+                dxp = K.gemm(dzp, w16_taps_t(weight, cp), epilogue=K.EPI_F32, taps=(1, cp, -sd_, -sh_, -1))
+                dz = K.unpad3d_cl(dxp, xB, Dc, Hc, Wc, cin).view(-1, cin)
+                del dxp, dzp
+                continue
             dwp = _wgrad(dz16, cols)                                    # [cout, Kp]
             grads[pi] = dwp.view(cout, 3, 3, 3, cin).permute(0, 4, 1, 2, 3).contiguous() if tm else dwp[:, :cin * 27].reshape(weight.shape)
-            need_dx = li > 0 or ctx.needs_input_grad[0]
             if need_dx:
                 dcols = _dgrad(dz16, w16_taps(weight) if tm else w16(weight, pad_to=cols.shape[1]))
                 if li > 0:
                     prev_c = plan[li - 1][1]
                     d_act = torch.empty(xB * Dc * Hc * Wc, prev_c, device=dtok.device, dtype=torch.float32)
-                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, d_act, strides, tap_major=tm)
+                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, d_act, strides, tap_major=bool(tm))
                     dz = d_act
                 else:
                     # same memory layout as the forward input (e.g. the channels-last view a stage wrapper hands over)
                     dx1 = torch.empty_strided((xB,) + tuple(xshape[1:]), ctx.in_strides, device=dtok.device, dtype=torch.float32) \
                         if xB == B else torch.empty((xB,) + tuple(xshape[1:]), device=dtok.device, dtype=torch.float32)
-                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, dx1, tuple(dx1.stride()), tap_major=tm)
+                    K.col2im3d(dcols, xB, cin, Dc, Hc, Wc, stride, dx1, tuple(dx1.stride()), tap_major=bool(tm))
                     if xB != B:
                         dx = torch.zeros(xshape, device=dtok.device, dtype=torch.float32)
                         dx[0] = dx1[0]

@@ -47,7 +47,8 @@ def test_attention_dropout_same_mask_same_numbers(d, H, nq, nk, p):
         assert O.max_rel(mine.float(), r) <= 3e-2
     # the log-sum-exp is the undropped one (softmax normalises before nn.Dropout)
     o0, lse0 = K.attn_fwd(q, k, v, B, H, nq, nk, d, d ** -0.5)
-    assert torch.equal(lse0[:, :, :nq], lse2[:, :, :nq])
+    # (not bit-equal: the dropout instantiation evaluates every exp2 on the MUFU, the plain one 6 of 16 pairs as a polynomial)
+    assert float((lse0[:, :, :nq] - lse2[:, :, :nq]).abs().max()) <= 1e-4
     assert O.max_rel(o.float(), o0.float()) > 0.05      # and the mask really was applied
 
 
