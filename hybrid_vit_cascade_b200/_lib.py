@@ -24,7 +24,7 @@ class Dropout(C.Structure):
 
 
 class ConvTaps(C.Structure):
-    _fields_ = [("side", C.c_int32), ("cin", C.c_int32), ("sd", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32)]
+    _fields_ = [("side", C.c_int32), ("cin", C.c_int32), ("n_taps", C.c_int32), ("rows", C.c_int32), ("offsets", C.c_int32 * 27)]
 
 
 class GemmArgs(C.Structure):
@@ -149,7 +149,7 @@ EXPORTS = [
     "hvc_gemm", "hvc_attn_fwd", "hvc_attn_bwd",
     "hvc_ln_fwd", "hvc_ln_bwd", "hvc_resid_bwd", "hvc_colsum_bf16", "hvc_cast_bf16", "hvc_cast_tokens",
     "hvc_adaln_fwd", "hvc_adaln_bwd",
-    "hvc_im2col3d", "hvc_col2im3d", "hvc_im2col3d_cl", "hvc_col2im3d_cl", "hvc_pad3d_cl", "hvc_unpad3d_cl", "hvc_groupnorm_silu_fwd", "hvc_groupnorm_silu_bwd",
+    "hvc_im2col3d", "hvc_col2im3d", "hvc_im2col3d_cl", "hvc_col2im3d_cl", "hvc_pad3d_cl", "hvc_unpad3d_cl", "hvc_s2d_pad_cl", "hvc_d2s_unpad_cl", "hvc_groupnorm_silu_fwd", "hvc_groupnorm_silu_bwd",
     "hvc_add_pos", "hvc_batch_sum", "hvc_head_fwd", "hvc_upsample3d_fwd", "hvc_upsample3d_bwd", "hvc_interp3d_fwd", "hvc_interp3d_bwd",
     "hvc_split3", "hvc_softmax_rows", "hvc_im2col3d_f32", "hvc_epilogue_f32",
     "hvc_im2col2d", "hvc_im2col2d_split", "hvc_col2im2d", "hvc_norm_act_fwd", "hvc_norm_act_bwd", "hvc_maxpool2d_fwd", "hvc_maxpool2d_bwd",

@@ -85,17 +85,18 @@ __global__ void __launch_bounds__(256) im2col3d_c1_kernel(const TIn* __restrict_
 // border voxels and the channels [Cs, Cp) are written as zeros (no separate memset).  One thread = one 8-channel run.
 template <typename TIn>
 __global__ void __launch_bounds__(256) pad3d_cl_kernel(const TIn* __restrict__ src, bf16* __restrict__ dst, int B, int D, int H, int W,
-                                                       int Cs, int Cp) {
+                                                       int Cs, int Cp, int hi) {
   const int c8n = Cp >> 3;
+  const int Dp = D + 1 + hi, Hp = H + 1 + hi, Wp = W + 1 + hi;       // one zero voxel on the low side, `hi` (0 | 1) on the high side
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)B * (D + 2) * (H + 2) * (W + 2) * c8n;
+  const long long total = (long long)B * Dp * Hp * Wp * c8n;
   if (idx >= total) return;
   const int c8 = (int)(idx % c8n);
   long long t = idx / c8n;
-  const int w = (int)(t % (W + 2)) - 1; t /= (W + 2);
-  const int h = (int)(t % (H + 2)) - 1; t /= (H + 2);
-  const int d = (int)(t % (D + 2)) - 1;
-  const int b = (int)(t / (D + 2));
+  const int w = (int)(t % Wp) - 1; t /= Wp;
+  const int h = (int)(t % Hp) - 1; t /= Hp;
+  const int d = (int)(t % Dp) - 1;
+  const int b = (int)(t / Dp);
   uint4 o = make_uint4(0u, 0u, 0u, 0u);
   if (w >= 0 && w < W && h >= 0 && h < H && d >= 0 && d < D && c8 * 8 < Cs) {
     const TIn* p = src + ((((long long)b * D + d) * H + h) * W + w) * Cs + c8 * 8;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) pad3d_cl_kernel(const TIn* __restrict__ s
 }
 // unpad: src f32 (B, D+2, H+2, W+2, C) -> dst f32 (B, D, H, W, C) dense, the interior voxels.  One thread = 4 channels.
 __global__ void __launch_bounds__(256) unpad3d_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int D, int H, int W,
-                                                         int C) {
+                                                         int C, int hi) {
   const int c4n = C >> 2;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long total = (long long)B * D * H * W * c4n;
@@ -121,7 +122,55 @@ __global__ void __launch_bounds__(256) unpad3d_cl_kernel(const float* __restrict
   const int h = (int)(t % H); t /= H;
   const int d = (int)(t % D);
   const int b = (int)(t / D);
-  const long long prow = (((long long)b * (D + 2) + d + 1) * (H + 2) + h + 1) * (W + 2) + w + 1;
+  const long long prow = (((long long)b * (D + 1 + hi) + d + 1) * (H + 1 + hi) + h + 1) * (W + 1 + hi) + w + 1;
+  reinterpret_cast<float4*>(dst)[idx] = __ldg(reinterpret_cast<const float4*>(src + prow * C) + c4);
+}
+// stride-2 implicit conv: split the volume by the parity of (d, h, w) into eight half-resolution volumes, each padded by one zero
+// voxel on the low side and stacked: src (B, D, H, W, C) dense (D, H, W even) -> dst bf16 (8, B, D/2+1, H/2+1, W/2+1, C); parity index
+// (d&1)*4 + (h&1)*2 + (w&1), voxel (d>>1, h>>1, w>>1) at padded coordinates +1.  One thread = one 8-channel run.
+template <typename TIn>
+__global__ void __launch_bounds__(256) s2d_pad_cl_kernel(const TIn* __restrict__ src, bf16* __restrict__ dst, int B, int D, int H, int W, int C) {
+  const int c8n = C >> 3;
+  const int Dp = D / 2 + 1, Hp = H / 2 + 1, Wp = W / 2 + 1;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = 8LL * B * Dp * Hp * Wp * c8n;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % c8n);
+  long long t = idx / c8n;
+  const int wq = (int)(t % Wp); t /= Wp;
+  const int hq = (int)(t % Hp); t /= Hp;
+  const int dq = (int)(t % Dp); t /= Dp;
+  const int b = (int)(t % B);
+  const int par = (int)(t / B);
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (wq > 0 && hq > 0 && dq > 0) {
+    const int d = 2 * (dq - 1) + (par >> 2), h = 2 * (hq - 1) + ((par >> 1) & 1), w = 2 * (wq - 1) + (par & 1);
+    const TIn* p = src + ((((long long)b * D + d) * H + h) * W + w) * C + c8 * 8;
+    if constexpr (sizeof(TIn) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), c = __ldg(reinterpret_cast<const float4*>(p) + 1);
+      o = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+    } else {
+      o = __ldg(reinterpret_cast<const uint4*>(p));
+    }
+  }
+  reinterpret_cast<uint4*>(dst)[idx] = o;
+}
+// the inverse for gradients: src f32 (8, B, D/2+1, H/2+1, W/2+1, C) -> dst f32 (B, D, H, W, C) dense.  One thread = 4 channels.
+__global__ void __launch_bounds__(256) d2s_unpad_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int D, int H, int W,
+                                                           int C) {
+  const int c4n = C >> 2;
+  const int Dp = D / 2 + 1, Hp = H / 2 + 1, Wp = W / 2 + 1;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * D * H * W * c4n;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % c4n);
+  long long t = idx / c4n;
+  const int w = (int)(t % W); t /= W;
+  const int h = (int)(t % H); t /= H;
+  const int d = (int)(t % D);
+  const int b = (int)(t / D);
+  const int par = (d & 1) * 4 + (h & 1) * 2 + (w & 1);
+  const long long prow = ((((long long)par * B + b) * Dp + (d >> 1) + 1) * Hp + (h >> 1) + 1) * Wp + (w >> 1) + 1;
   reinterpret_cast<float4*>(dst)[idx] = __ldg(reinterpret_cast<const float4*>(src + prow * C) + c4);
 }
 
@@ -509,22 +558,45 @@ extern "C" int hvc_col2im3d_cl(const void* dcols, const hvc_conv3d_geom* geom, f
 }
 
 extern "C" int hvc_pad3d_cl(const void* src, int32_t src_is_bf16, void* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cs,
-                            int32_t Cp, void* stream) {
-  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0, "hvc_pad3d_cl: bad arguments");
+                            int32_t Cp, int32_t pad_hi, void* stream) {
+  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0 && (pad_hi == 0 || pad_hi == 1), "hvc_pad3d_cl: bad arguments");
   HVC_CHECK_ARG(Cs > 0 && Cs % 8 == 0 && Cp % 8 == 0 && Cs <= Cp, "hvc_pad3d_cl: channel counts must be multiples of 8, Cs <= Cp");
-  const long long total = (long long)B * (D + 2) * (H + 2) * (W + 2) * (Cp / 8);
+  const long long total = (long long)B * (D + 1 + pad_hi) * (H + 1 + pad_hi) * (W + 1 + pad_hi) * (Cp / 8);
   const unsigned blocks = (unsigned)((total + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (src_is_bf16) pad3d_cl_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, Cs, Cp);
-  else pad3d_cl_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, Cs, Cp);
+  if (src_is_bf16) pad3d_cl_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, Cs, Cp, pad_hi);
+  else pad3d_cl_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, Cs, Cp, pad_hi);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }
 
-extern "C" int hvc_unpad3d_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream) {
-  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hvc_unpad3d_cl: bad arguments");
+extern "C" int hvc_unpad3d_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t pad_hi,
+                              void* stream) {
+  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && (pad_hi == 0 || pad_hi == 1), "hvc_unpad3d_cl: bad arguments");
   const long long total = (long long)B * D * H * W * (C / 4);
-  unpad3d_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, B, D, H, W, C);
+  unpad3d_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, B, D, H, W, C, pad_hi);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_s2d_pad_cl(const void* src, int32_t src_is_bf16, void* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C,
+                              void* stream) {
+  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "hvc_s2d_pad_cl: bad arguments");
+  HVC_CHECK_ARG(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "hvc_s2d_pad_cl: the volume sizes must be even");
+  const long long total = 8LL * B * (D / 2 + 1) * (H / 2 + 1) * (W / 2 + 1) * (C / 8);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (src_is_bf16) s2d_pad_cl_kernel<bf16><<<blocks, 256, 0, st>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, C);
+  else s2d_pad_cl_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), B, D, H, W, C);
+  HVC_LAUNCH_CHECK();
+  return HVC_OK;
+}
+
+extern "C" int hvc_d2s_unpad_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream) {
+  HVC_CHECK_ARG(src && dst && B > 0 && D > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "hvc_d2s_unpad_cl: bad arguments");
+  HVC_CHECK_ARG(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "hvc_d2s_unpad_cl: the volume sizes must be even");
+  const long long total = (long long)B * D * H * W * (C / 4);
+  d2s_unpad_cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, dst, B, D, H, W, C);
   HVC_LAUNCH_CHECK();
   return HVC_OK;
 }

@@ -50,7 +50,8 @@ struct GemmKArgs {
   int v256;       // every epilogue operand (out, out2, resid, aux) is 32-byte aligned with a 32-byte-multiple row pitch
   // implicit 3x3x3 convolution over a zero-padded channels-last volume (hvc_gemm_args::taps): the operand on `taps_side` is a
   // [padded voxels, tap_cin] matrix read with a per-tap row shift instead of a materialised patch matrix
-  int taps_side, tap_cin, tap_sd, tap_sh, tap_sw;
+  int taps_side, tap_cin, n_taps;
+  int tap_off[27];
   int n_mma;      // N of the tcgen05.mma: 128, or 64 / 32 when the whole problem is that narrow (the Cout = 32 / 64 convs of the stage
                   // wrappers).  The B box then has n_mma rows, and an operand half that lies wholly outside the problem is not loaded:
                   // measured on B200, a TMA box that is mostly out-of-bounds zero fill costs far more than the same box of data
@@ -59,11 +60,8 @@ struct GemmKArgs {
   uint32_t stage_tx;        // bytes one stage's loads deliver
 };
 
-// row shift of tap = kd*9 + kh*3 + kw: (kd-1)*sd + (kh-1)*sh + (kw-1)*sw
-__device__ __forceinline__ int tap_shift(const GemmKArgs& p, int tap) {
-  const int kd = tap / 9, kh = (tap - kd * 9) / 3, kw = tap - kd * 9 - kh * 3;
-  return (kd - 1) * p.tap_sd + (kh - 1) * p.tap_sh + (kw - 1) * p.tap_sw;
-}
+// row shift of tap t (hvc_conv_taps::offsets); a half-tile past the last tap reads tap n_taps-1 again (its columns are never stored)
+__device__ __forceinline__ int tap_shift(const GemmKArgs& p, int tap) { return p.tap_off[min(tap, p.n_taps - 1)]; }
 
 struct WorkItem {
   int m0, n0, kb0, kb1;
@@ -400,19 +398,20 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
 
   const hvc_conv_taps& tp = a->taps;
   HVC_CHECK_ARG(tp.side >= 0 && tp.side <= 2, "hvc_gemm: taps.side must be 0, 1 or 2");
-  if (tp.side == 1) HVC_CHECK_ARG(a->a_major == 0 && tp.cin > 0 && tp.cin % BK == 0 && a->K == 27 * tp.cin,
-                                  "hvc_gemm: taps on A need a K-major A, cin %% 64 == 0 and K == 27*cin");
-  if (tp.side == 2) HVC_CHECK_ARG(a->b_major == 1 && tp.cin > 0 && tp.cin % 64 == 0 && a->N == 27 * tp.cin,
-                                  "hvc_gemm: taps on B need an MN-major B, cin %% 64 == 0 and N == 27*cin");
+  if (tp.side != 0) HVC_CHECK_ARG(tp.n_taps >= 1 && tp.n_taps <= 27 && tp.rows >= 0, "hvc_gemm: taps.n_taps must be 1..27");
+  if (tp.side == 1) HVC_CHECK_ARG(a->a_major == 0 && tp.cin > 0 && tp.cin % BK == 0 && a->K == tp.n_taps * tp.cin,
+                                  "hvc_gemm: taps on A need a K-major A, cin %% 64 == 0 and K == n_taps*cin");
+  if (tp.side == 2) HVC_CHECK_ARG(a->b_major == 1 && tp.cin > 0 && tp.cin % 64 == 0 && a->N == tp.n_taps * tp.cin,
+                                  "hvc_gemm: taps on B need an MN-major B, cin %% 64 == 0 and N == n_taps*cin");
 
   const int n_mma = (a->N <= 32 && a->b_major == 0) ? 32 : (a->N <= 64 ? 64 : BN);   // an MN-major B keeps whole 64-element swizzle rows
   CUtensorMap tmA, tmB;
   int rc;
-  if (a->a_major == 0) rc = make_tmap_2d(&tmA, a->A, 2, a->M, tp.side == 1 ? tp.cin : a->K, a->lda, BK, BM, true);
+  if (a->a_major == 0) rc = make_tmap_2d(&tmA, a->A, 2, (tp.side == 1 && tp.rows) ? tp.rows : a->M, tp.side == 1 ? tp.cin : a->K, a->lda, BK, BM, true);
   else                 rc = make_tmap_2d(&tmA, a->A, 2, a->K, a->M, a->lda, 64, BK, true);
   if (rc) return rc;
   if (a->b_major == 0) rc = make_tmap_2d(&tmB, a->B, 2, a->N, a->K, a->ldb, BK, n_mma, true);
-  else                 rc = make_tmap_2d(&tmB, a->B, 2, a->K, tp.side == 2 ? tp.cin : a->N, a->ldb, 64, BK, true);
+  else                 rc = make_tmap_2d(&tmB, a->B, 2, (tp.side == 2 && tp.rows) ? tp.rows : a->K, tp.side == 2 ? tp.cin : a->N, a->ldb, 64, BK, true);
   if (rc) return rc;
 
   GemmKArgs ka;
@@ -430,7 +429,8 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
   ka.aux = reinterpret_cast<const bf16*>(a->aux); ka.ldaux = a->ldaux;
   ka.alpha = a->alpha;
   ka.drop = make_drop(a->drop);
-  ka.taps_side = tp.side; ka.tap_cin = tp.cin; ka.tap_sd = tp.sd; ka.tap_sh = tp.sh; ka.tap_sw = tp.sw;
+  ka.taps_side = tp.side; ka.tap_cin = tp.cin; ka.n_taps = tp.side ? tp.n_taps : 1;
+  for (int t = 0; t < 27; ++t) ka.tap_off[t] = tp.side ? tp.offsets[t] : 0;
   ka.n_mma = n_mma;
   ka.a_halves = (a->a_major == 1 && a->M <= 64) ? 1 : 2;
   ka.b_halves = (a->b_major == 1 && a->N <= 64) ? 1 : 2;

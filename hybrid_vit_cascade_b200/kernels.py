@@ -86,24 +86,29 @@ def _row_major_2d(t, name):
 
 def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epilogue=EPI_BF16,
          activation=ACT_NONE, bias=None, out2=None, resid=None, gate=None, gate_ld=0, rows_per_batch=0,
-         aux=None, alpha=1.0, k_splits=1, drop=None, taps=None):
+         aux=None, alpha=1.0, k_splits=1, drop=None, taps=None, m_rows=None):
     """D[M,N] = alpha * sum_k A(m,k) B(n,k) with a fused epilogue (see include/hvc.h).
 
     a: bf16, stored [M,K] (a_major=0) or [K,M] (a_major=1); b: bf16, stored [N,K] or [K,N].
-    taps = (side, cin, sd, sh, sw): implicit 3x3x3 convolution, the operand on `side` (1 = a, 2 = b) is the zero-padded channels-last
-    volume [padded voxels, cin] and stands for its 27*cin-wide patch matrix (hvc_conv_taps in include/hvc.h).
+    taps = (side, cin, offsets): implicit 3x3x3 convolution, the operand on `side` (1 = a, 2 = b) is the zero-padded channels-last
+    volume [rows, cin] and stands for its len(offsets)*cin-wide patch matrix; offsets = the row shift of every tap (hvc_conv_taps in
+    include/hvc.h; conv_tap_offsets() builds them).  m_rows: M when `a` (side 1) has more rows than the output (stacked parity volumes).
     """
     _need_cuda(a, b)
     assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
     lda, ldb = _row_major_2d(a, "a"), _row_major_2d(b, "b")
     M, K = (a.shape if a_major == 0 else (a.shape[1], a.shape[0]))
     N, Kb = (b.shape if b_major == 0 else (b.shape[1], b.shape[0]))
+    tap_rows = 0
     if taps is not None and taps[0] == 1:
         assert a_major == 0 and K == taps[1]
-        K = 27 * K
+        K = len(taps[2]) * K
+        if m_rows is not None:
+            tap_rows, M = M, m_rows
     if taps is not None and taps[0] == 2:
         assert b_major == 1 and N == taps[1]
-        N = 27 * N
+        N = len(taps[2]) * N
+        tap_rows, Kb = Kb, K
     assert K == Kb, (a.shape, b.shape, a_major, b_major)
     if out is None:
         if epilogue == EPI_BF16:
@@ -137,7 +142,9 @@ def gemm(a, b, *, a_major=0, b_major=0, out=None, out_dtype=torch.bfloat16, epil
     args.k_splits = k_splits
     _set_drop(args, drop)
     if taps is not None:
-        args.taps.side, args.taps.cin, args.taps.sd, args.taps.sh, args.taps.sw = taps
+        args.taps.side, args.taps.cin, args.taps.n_taps, args.taps.rows = taps[0], taps[1], len(taps[2]), tap_rows
+        for i, o in enumerate(taps[2]):
+            args.taps.offsets[i] = int(o)
     with _timed("gemm", 2.0 * M * N * K):
         _lib.check(_lib.lib().hvc_gemm(C.byref(args), _stream()), "hvc_gemm")
     return out
@@ -680,6 +687,23 @@ def interp3d_bwd(dout, B, grid, size, align_corners):
     return dv
 
 
+def conv_tap_offsets(H, W, sign=1):
+    """Row shifts of the 27 taps on a stride-1 padded volume (B, D+2, H+2, W+2, C): (kd-1)*(H+2)*(W+2) + (kh-1)*(W+2) + (kw-1)."""
+    sd, sh = (H + 2) * (W + 2), W + 2
+    return [sign * ((kd - 1) * sd + (kh - 1) * sh + (kw - 1)) for kd in range(3) for kh in range(3) for kw in range(3)]
+
+
+def conv_tap_offsets_s2(rows_per_volume, Hp, Wp):
+    """Stride-2 conv on the eight stacked parity volumes (s2d_pad_cl): per tap (parity volume index, shift inside it)."""
+    out = []
+    for kd in range(3):
+        for kh in range(3):
+            for kw in range(3):
+                par = (kd != 1) * 4 + (kh != 1) * 2 + (kw != 1)
+                out.append((par, -(kd == 0) * Hp * Wp - (kh == 0) * Wp - (kw == 0)))
+    return out
+
+
 def chan_dot_fwd(y, w, bias):
     """Conv3d(C -> 1, kernel 1) on channels-last y f32 [M, C]: out[m] = bias + sum_c y[m,c] w[c]."""
     _need_cuda(y, w)
@@ -702,21 +726,41 @@ def chan_dot_bwd(dout, y, w):
     return dy, dwb[:Cc], dwb[Cc:]
 
 
-def pad3d_cl(src, B, D, H, W, Cs, Cp):
-    """src (B, D, H, W, Cs) f32|bf16 dense channels-last -> zero-padded bf16 (B, D+2, H+2, W+2, Cp)."""
+def pad3d_cl(src, B, D, H, W, Cs, Cp, pad_hi=1):
+    """src (B, D, H, W, Cs) f32|bf16 dense channels-last -> zero-padded bf16 (B, D+1+pad_hi, H+1+pad_hi, W+1+pad_hi, Cp)."""
     _need_cuda(src)
     assert src.is_contiguous() and src.numel() == B * D * H * W * Cs and src.dtype in (torch.float32, torch.bfloat16)
-    dst = torch.empty(B, D + 2, H + 2, W + 2, Cp, device=src.device, dtype=torch.bfloat16)
-    _lib.check(_lib.lib().hvc_pad3d_cl(_ptr(src), int(src.dtype == torch.bfloat16), _ptr(dst), B, D, H, W, Cs, Cp, _stream()), "hvc_pad3d_cl")
+    dst = torch.empty(B, D + 1 + pad_hi, H + 1 + pad_hi, W + 1 + pad_hi, Cp, device=src.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().hvc_pad3d_cl(_ptr(src), int(src.dtype == torch.bfloat16), _ptr(dst), B, D, H, W, Cs, Cp, pad_hi, _stream()),
+               "hvc_pad3d_cl")
     return dst
 
 
-def unpad3d_cl(src, B, D, H, W, Cc, out=None):
-    """src f32 (B, D+2, H+2, W+2, C) contiguous -> f32 (B, D, H, W, C) dense."""
+def unpad3d_cl(src, B, D, H, W, Cc, out=None, pad_hi=1):
+    """src f32 (B, D+1+pad_hi, H+1+pad_hi, W+1+pad_hi, C) contiguous -> f32 (B, D, H, W, C) dense."""
     _need_cuda(src)
-    assert src.is_contiguous() and src.dtype == torch.float32 and src.numel() == B * (D + 2) * (H + 2) * (W + 2) * Cc
+    assert src.is_contiguous() and src.dtype == torch.float32
+    assert src.numel() == B * (D + 1 + pad_hi) * (H + 1 + pad_hi) * (W + 1 + pad_hi) * Cc
     if out is None:
         out = torch.empty(B, D, H, W, Cc, device=src.device, dtype=torch.float32)
     assert out.is_contiguous() and out.dtype == torch.float32 and out.numel() == B * D * H * W * Cc
-    _lib.check(_lib.lib().hvc_unpad3d_cl(_ptr(src), _ptr(out), B, D, H, W, Cc, _stream()), "hvc_unpad3d_cl")
+    _lib.check(_lib.lib().hvc_unpad3d_cl(_ptr(src), _ptr(out), B, D, H, W, Cc, pad_hi, _stream()), "hvc_unpad3d_cl")
+    return out
+
+
+def s2d_pad_cl(src, B, D, H, W, Cc):
+    """src (B, D, H, W, C) f32|bf16 dense (even sizes) -> bf16 (8, B, D/2+1, H/2+1, W/2+1, C): the eight parity volumes, low-side padded."""
+    _need_cuda(src)
+    assert src.is_contiguous() and src.numel() == B * D * H * W * Cc and src.dtype in (torch.float32, torch.bfloat16)
+    dst = torch.empty(8, B, D // 2 + 1, H // 2 + 1, W // 2 + 1, Cc, device=src.device, dtype=torch.bfloat16)
+    _lib.check(_lib.lib().hvc_s2d_pad_cl(_ptr(src), int(src.dtype == torch.bfloat16), _ptr(dst), B, D, H, W, Cc, _stream()), "hvc_s2d_pad_cl")
+    return dst
+
+
+def d2s_unpad_cl(src, B, D, H, W, Cc):
+    """src f32 (8, B, D/2+1, H/2+1, W/2+1, C) contiguous -> f32 (B, D, H, W, C) dense."""
+    _need_cuda(src)
+    assert src.is_contiguous() and src.dtype == torch.float32 and src.numel() == 8 * B * (D // 2 + 1) * (H // 2 + 1) * (W // 2 + 1) * Cc
+    out = torch.empty(B, D, H, W, Cc, device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_d2s_unpad_cl(_ptr(src), _ptr(out), B, D, H, W, Cc, _stream()), "hvc_d2s_unpad_cl")
     return out

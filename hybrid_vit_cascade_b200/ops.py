@@ -423,17 +423,27 @@ class VoxelEmbed(Function):
             # multiple of 64 channels (the last conv of every stack in the reference's configurations) needs no patch matrix at all:
             # implicit GEMM on the zero-padded volume (hvc_conv_taps)
             tm = cin % 8 == 0 and strides[1] == 1 and all(s % 8 == 0 for s in strides[:1] + strides[2:]) and (li > 0 or xB == B)
-            implicit = IMPLICIT_EMBED and tm and stride == 1 and cin % 64 == 0 and li > 0 and cout % 8 == 0
+            implicit = IMPLICIT_EMBED and tm and cin % 64 == 0 and li > 0 and cout % 8 == 0 and \
+                (stride == 1 or (Dc % 2 == 0 and Hc % 2 == 0 and Wc % 2 == 0))
             Do, Ho, Wo = K.conv_out(Dc, stride), K.conv_out(Hc, stride), K.conv_out(Wc, stride)
-            if implicit:
+            if implicit and stride == 1:
                 cols = K.pad3d_cl(a.view(xB, Dc, Hc, Wc, cin), xB, Dc, Hc, Wc, cin, cin)
-                zp = K.gemm(cols.view(-1, cin), w16_taps(weight), bias=bias, epilogue=K.EPI_F32, taps=(1, cin, (Hc + 2) * (Wc + 2), Wc + 2, 1))
+                zp = K.gemm(cols.view(-1, cin), w16_taps(weight), bias=bias, epilogue=K.EPI_F32, taps=(1, cin, K.conv_tap_offsets(Hc, Wc)))
                 z = K.unpad3d_cl(zp, xB, Dc, Hc, Wc, cout).view(-1, cout)
+                del zp
+            elif implicit:
+                # stride 2: eight parity volumes (low-side padded, stacked along the rows); the output lives on the same padded
+                # half-resolution grid, so every tap is again a row shift (include/hvc.h, hvc_conv_taps)
+                rows_p = xB * (Do + 1) * (Ho + 1) * (Wo + 1)
+                cols = K.s2d_pad_cl(a.view(xB, Dc, Hc, Wc, cin), xB, Dc, Hc, Wc, cin)
+                offs = [par * rows_p + sh for par, sh in K.conv_tap_offsets_s2(rows_p, Ho + 1, Wo + 1)]
+                zp = K.gemm(cols.view(-1, cin), w16_taps(weight), bias=bias, epilogue=K.EPI_F32, taps=(1, cin, offs), m_rows=rows_p)
+                z = K.unpad3d_cl(zp, xB, Do, Ho, Wo, cout, pad_hi=0).view(-1, cout)
                 del zp
             else:
                 cols = K.im2col3d(a, xB, cin, Dc, Hc, Wc, stride, strides, tap_major=tm)
                 z = K.gemm(cols, w16_taps(weight) if tm else w16(weight, pad_to=cols.shape[1]), bias=bias, epilogue=K.EPI_F32)   # [xB*V, cout] channels-last
-            tm = 2 if implicit else int(tm)
+            tm = (2 if stride == 1 else 3) if implicit else int(tm)
             V = Do * Ho * Wo
             geoms.append((cin, Dc, Hc, Wc, stride, strides, V, tm))
             if groups:
@@ -496,17 +506,34 @@ class VoxelEmbed(Function):
             dz16 = K.cast_bf16(dz.contiguous())
             grads[pi + 1] = K.colsum_bf16(dz16)
             need_dx = li > 0 or ctx.needs_input_grad[0]
-            if tm == 2:       # implicit GEMM: padded output gradient (channels padded to whole 64-wide k-blocks), no patch matrices
+            if tm >= 2:       # implicit GEMM: padded output gradient (channels padded to whole 64-wide k-blocks), no patch matrices
                 cp = (cout + 63) // 64 * 64
-                sd_, sh_ = (Hc + 2) * (Wc + 2), Wc + 2
-                dzp = K.pad3d_cl(dz16.view(xB, Dc, Hc, Wc, cout), xB, Dc, Hc, Wc, cout, cp).view(-1, cp)
                 tiles = ((cp + 127) // 128) * ((27 * cin + 127) // 128)
+                if tm == 2:
+                    dzp = K.pad3d_cl(dz16.view(xB, Dc, Hc, Wc, cout), xB, Dc, Hc, Wc, cout, cp).view(-1, cp)
+                    offs = K.conv_tap_offsets(Hc, Wc)
+                else:
+                    Do, Ho, Wo = Dc // 2, Hc // 2, Wc // 2
+                    dzp = K.pad3d_cl(dz16.view(xB, Do, Ho, Wo, cout), xB, Do, Ho, Wo, cout, cp, pad_hi=0).view(-1, cp)
+                    rows_p = dzp.shape[0]
+                    tt = K.conv_tap_offsets_s2(rows_p, Ho + 1, Wo + 1)
+                    offs = [par * rows_p + sh for par, sh in tt]
                 splits = max(1, min(dzp.shape[0] // 64, (16 * _sms(dtok.device)) // tiles))
                 dwp = K.gemm(dzp, cols.view(-1, cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=splits,
-                             taps=(2, cin, sd_, sh_, 1))[:cout]
+                             taps=(2, cin, offs))[:cout]
                 grads[pi] = dwp.view(cout, 3, 3, 3, cin).permute(0, 4, 1, 2, 3).contiguous()
-                dxp = K.gemm(dzp, w16_taps_t(weight, cp), epilogue=K.EPI_F32, taps=(1, cp, -sd_, -sh_, -1))
-                dz = K.unpad3d_cl(dxp, xB, Dc, Hc, Wc, cin).view(-1, cin)
+                if tm == 2:
+                    dxp = K.gemm(dzp, w16_taps_t(weight, cp), epilogue=K.EPI_F32, taps=(1, cp, K.conv_tap_offsets(Hc, Wc, -1)))
+                    dz = K.unpad3d_cl(dxp, xB, Dc, Hc, Wc, cin).view(-1, cin)
+                else:
+                    # data gradient, one GEMM per parity volume over the taps that read it: dX_par[r] = sum_t dZ[r - shift_t] W_t
+                    wt = w16_taps_t(weight, cp).view(cin, 27, cp)
+                    dxp = torch.empty(8 * rows_p, cin, device=dtok.device, dtype=torch.float32)
+                    for par in range(8):
+                        ts = [t for t, (pp, _) in enumerate(tt) if pp == par]
+                        K.gemm(dzp, wt[:, ts].reshape(cin, len(ts) * cp), epilogue=K.EPI_F32, taps=(1, cp, [-tt[t][1] for t in ts]),
+                               out=dxp[par * rows_p:(par + 1) * rows_p])
+                    dz = K.d2s_unpad_cl(dxp, xB, Dc, Hc, Wc, cin).view(-1, cin)
                 del dxp, dzp
                 continue
             dwp = _wgrad(dz16, cols)                                    # [cout, Kp]

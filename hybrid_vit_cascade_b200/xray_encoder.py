@@ -385,7 +385,7 @@ class Conv3dGnGelu(Function):
         if implicit:
             # rows = padded voxels; a tap (kd, kh, kw) is a shift of (kd-1)*(H+2)*(W+2) + (kh-1)*(W+2) + (kw-1) rows
             cols = _pad_cl(xf.permute(0, 2, 3, 4, 1), B, D, H, W, Cin, Cin)
-            zpad = K.gemm(cols.view(-1, Cin), w_16, bias=conv_b, epilogue=K.EPI_F32, taps=(1, Cin, (H + 2) * (W + 2), W + 2, 1))
+            zpad = K.gemm(cols.view(-1, Cin), w_16, bias=conv_b, epilogue=K.EPI_F32, taps=(1, Cin, K.conv_tap_offsets(H, W)))
             z = K.unpad3d_cl(zpad, B, D, H, W, Cout).view(B * V, Cout)
             del zpad
         elif slabs is None:
@@ -419,15 +419,14 @@ class Conv3dGnGelu(Function):
         if implicit:
             # padded output gradient (zero rows at the padding positions, channels padded to a whole 64-wide k-block)
             Cp = (Cout + 63) // 64 * 64
-            sd, sh = (H + 2) * (W + 2), W + 2
             dzp = _pad_cl(dz16.view(B, D, H, W, Cout), B, D, H, W, Cout, Cp).view(-1, Cp)
             del dz16
             tiles = (27 * Cin + 127) // 128
             splits = max(1, min(dzp.shape[0] // 64, (16 * ops._sms(dy.device)) // tiles))     # short fp32 accumulation chains
             dw = K.gemm(dzp, cols.view(-1, Cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=splits,
-                        taps=(2, Cin, sd, sh, 1))[:Cout]
+                        taps=(2, Cin, K.conv_tap_offsets(H, W)))[:Cout]
             if need_dx:
-                dxp = K.gemm(dzp, ops.w16_taps_t(conv_w, Cp), epilogue=K.EPI_F32, taps=(1, Cp, -sd, -sh, -1))
+                dxp = K.gemm(dzp, ops.w16_taps_t(conv_w, Cp), epilogue=K.EPI_F32, taps=(1, Cp, K.conv_tap_offsets(H, W, -1)))
                 dx_cl = dx.permute(0, 2, 3, 4, 1)
                 if dx_cl.is_contiguous():
                     K.unpad3d_cl(dxp, B, D, H, W, Cin, out=dx_cl)

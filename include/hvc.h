@@ -86,18 +86,23 @@ typedef enum hvc_activation {
   HVC_ACT_GELU_GRAD = 2   /* out = acc * gelu'(aux)  (backward of the MLP hidden activation)          */
 } hvc_activation;
 
-/* Implicit Conv3d(k3, pad 1, stride 1) through hvc_gemm: the activation is a zero-padded channels-last volume viewed as a matrix
- * [rows = B*(D+2)*(H+2)*(W+2) padded voxels, cin] (bf16); moving one voxel along w / h / d moves sw / sh / sd rows, so a filter tap
- * (kd, kh, kw) is a ROW SHIFT of (kd-1)*sd + (kh-1)*sh + (kw-1)*sw, which the TMA producer adds to the tile coordinate (rows outside the
- * matrix read as zero).  No patch matrix exists in HBM.  Column/row index of tap t = kd*9 + kh*3 + kw along the tapped dimension:
- * [t*cin, (t+1)*cin), i.e. weight.permute(0,2,3,4,1).reshape(Cout, 27*cin).
- *   side 1: A is the padded volume (a_major 0, K = 27*cin): out[r, n] = sum_t sum_c A[r + shift(t), c] B[n, t*cin + c]   (forward conv,
- *           and the data gradient with negated strides and the transposed filter); rows r at padding positions hold don't-care values.
- *   side 2: B is the padded volume (b_major 1, N = 27*cin, K = rows): out[m, t*cin + c] = sum_r A(r, m) B[r + shift(t), c]
+/* Implicit Conv3d(k3, pad 1) through hvc_gemm: the activation is a zero-padded channels-last volume viewed as a matrix
+ * [rows = padded voxels, cin] (bf16), laid out so that every filter tap is a ROW SHIFT offsets[t], which the TMA producer adds to the tile
+ * coordinate (rows outside the matrix read as zero).  No patch matrix exists in HBM.
+ *   stride 1: rows = B*(D+2)*(H+2)*(W+2) (hvc_pad3d_cl); tap t = kd*9 + kh*3 + kw shifts by (kd-1)*(H+2)*(W+2) + (kh-1)*(W+2) + (kw-1).
+ *   stride 2: the input is split by the parity of (d, h, w) into eight half-resolution volumes, each padded by one voxel on the low
+ *             side and stacked along the rows (hvc_s2d_pad_cl): output voxel o reads input 2o-1+k, i.e. parity (k != 1) at position
+ *             o - (k == 0), so tap t shifts by parity_index(t)*rows_per_volume - (kd==0)*Hp*Wp - (kh==0)*Wp - (kw==0).
+ * Column/row index of tap t along the tapped dimension: [t*cin, (t+1)*cin), i.e. weight.permute(0,2,3,4,1).reshape(Cout, 27*cin).
+ *   side 1: A is the padded volume (a_major 0, K = n_taps*cin): out[r, n] = sum_t sum_c A[r + offsets[t], c] B[n, t*cin + c]  (forward conv;
+ *           data gradient with negated shifts and the transposed filter); rows r at padding positions hold don't-care values.
+ *   side 2: B is the padded volume (b_major 1, N = n_taps*cin, K = rows of A): out[m, t*cin + c] = sum_r A(r, m) B[r + offsets[t], c]
  *           (weight gradient; A = padded output gradient with zero rows at the padding positions).
+ * rows: row count of the tapped matrix when it differs from M (side 1) / K (side 2), e.g. the eight stacked parity volumes; 0 = same.
  * cin % 64 == 0.  side 0: a plain GEMM. */
 typedef struct hvc_conv_taps {
-  int32_t side, cin, sd, sh, sw;
+  int32_t side, cin, n_taps, rows;
+  int32_t offsets[27];
 } hvc_conv_taps;
 
 typedef struct hvc_gemm_args {
@@ -248,12 +253,18 @@ int hvc_col2im3d(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void
  * convs of the cascade's detail_enhancer (progressive_cascade/model_progressive.py:263). */
 int hvc_im2col3d_cl(const void* x, int32_t x_is_bf16, const hvc_conv3d_geom* geom, void* cols, void* stream);
 int hvc_col2im3d_cl(const void* dcols, const hvc_conv3d_geom* geom, float* dx, void* stream);
-/* Zero-padded channels-last volumes, the operand layout of the implicit-GEMM conv (hvc_conv_taps):
- * pad:   src (B, D, H, W, Cs) f32|bf16 dense -> dst bf16 (B, D+2, H+2, W+2, Cp); border voxels and channels [Cs, Cp) are zero-filled.
- * unpad: src f32 (B, D+2, H+2, W+2, C) -> dst f32 (B, D, H, W, C) dense (the interior voxels).   Cs, Cp % 8 == 0; C % 4 == 0. */
+/* Zero-padded channels-last volumes, the operand layouts of the implicit-GEMM conv (hvc_conv_taps):
+ * pad:   src (B, D, H, W, Cs) f32|bf16 dense -> dst bf16 (B, D+1+pad_hi, H+1+pad_hi, W+1+pad_hi, Cp): one zero voxel on the low side of every
+ *        axis, pad_hi (0 | 1) on the high side; channels [Cs, Cp) zero-filled.   unpad: the interior of such an f32 volume -> dense.
+ * s2d_pad (stride-2 convs): the volume split by the parity of (d, h, w) into eight half-resolution volumes, each padded by one zero
+ *        voxel on the low side, stacked: dst bf16 (8, B, D/2+1, H/2+1, W/2+1, C), parity index (d&1)*4 + (h&1)*2 + (w&1).
+ * d2s_unpad: the inverse for gradients, src f32 (8, B, D/2+1, H/2+1, W/2+1, C) -> dst f32 (B, D, H, W, C).
+ * Cs, Cp, C % 8 == 0 (C % 4 for the f32 sources); D, H, W even for the parity split. */
 int hvc_pad3d_cl(const void* src, int32_t src_is_bf16, void* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t Cs, int32_t Cp,
-                 void* stream);
-int hvc_unpad3d_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream);
+                 int32_t pad_hi, void* stream);
+int hvc_unpad3d_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, int32_t pad_hi, void* stream);
+int hvc_s2d_pad_cl(const void* src, int32_t src_is_bf16, void* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream);
+int hvc_d2s_unpad_cl(const float* src, float* dst, int32_t B, int32_t D, int32_t H, int32_t W, int32_t C, void* stream);
 /* y [B,V,C] (bf16, or f32 when it feeds the token stream) = SiLU(GroupNorm(x f32 [B,V,C])); mean/rstd f32
  * [B,groups] saved; scratch f32 [2*B*C]. */
 int hvc_groupnorm_silu_fwd(const float* x, const float* w, const float* b, int32_t B, int32_t V, int32_t C,

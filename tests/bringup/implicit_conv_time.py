@@ -18,7 +18,6 @@ x = torch.randn(B, D, D, D, Cin, device="cuda", generator=g)
 dz = torch.randn(B, D, D, D, Cout, device="cuda", generator=g).bfloat16()
 w_taps = (torch.randn(Cout, 27 * Cin, device="cuda", generator=g) * 0.02).bfloat16()
 w_t = (torch.randn(Cin, 27 * Cp, device="cuda", generator=g) * 0.02).bfloat16()
-sd, sh = (D + 2) * (D + 2), D + 2
 xp = K.pad3d_cl(x, B, D, D, D, Cin, Cin).view(-1, Cin)
 dzp = K.pad3d_cl(dz, B, D, D, D, Cout, Cp).view(-1, Cp)
 rows = xp.shape[0]
@@ -40,10 +39,10 @@ def timeit(fn):
 tiles = (27 * Cin + 127) // 128
 splits = max(1, min(rows // 64, (16 * 148) // tiles))
 cases = [
-    ("forward   [rows, 32, 1728]", lambda: K.gemm(xp, w_taps, epilogue=K.EPI_F32, taps=(1, Cin, sd, sh, 1)), 2.0 * rows * Cout * 27 * Cin),
-    ("data grad [rows, 64, 1728]", lambda: K.gemm(dzp, w_t, epilogue=K.EPI_F32, taps=(1, Cp, -sd, -sh, -1)), 2.0 * rows * Cin * 27 * Cp),
+    ("forward   [rows, 32, 1728]", lambda: K.gemm(xp, w_taps, epilogue=K.EPI_F32, taps=(1, Cin, K.conv_tap_offsets(D, D))), 2.0 * rows * Cout * 27 * Cin),
+    ("data grad [rows, 64, 1728]", lambda: K.gemm(dzp, w_t, epilogue=K.EPI_F32, taps=(1, Cp, K.conv_tap_offsets(D, D, -1))), 2.0 * rows * Cin * 27 * Cp),
     ("wgt grad  [64, 1728, rows]", lambda: K.gemm(dzp, xp, a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=splits,
-                                                  taps=(2, Cin, sd, sh, 1)), 2.0 * rows * Cp * 27 * Cin),
+                                                  taps=(2, Cin, K.conv_tap_offsets(D, D))), 2.0 * rows * Cp * 27 * Cin),
     ("pad f32 -> bf16           ", lambda: K.pad3d_cl(x, B, D, D, D, Cin, Cin), 0.0),
 ]
 print(f"D={D} B={B} rows={rows} ({rows * Cin * 2 / 1e9:.2f} GB padded volume)")

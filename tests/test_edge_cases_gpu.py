@@ -90,20 +90,94 @@ def test_gemm_implicit_conv_taps_match_conv3d(Cin, Cout):
     xd, wd, dzd = x.double().requires_grad_(True), w.double().requires_grad_(True), dz.double()
     ref = F.conv3d(xd, wd, padding=1)
     (ref * dzd).sum().backward()
-    sd, sh = (H + 2) * (W + 2), W + 2
     xp = K.pad3d_cl(x.permute(0, 2, 3, 4, 1).contiguous(), B, D, H, W, Cin, Cin)
     w_taps = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous()
-    zp = K.gemm(xp.view(-1, Cin), w_taps, epilogue=K.EPI_F32, taps=(1, Cin, sd, sh, 1))
+    zp = K.gemm(xp.view(-1, Cin), w_taps, epilogue=K.EPI_F32, taps=(1, Cin, K.conv_tap_offsets(H, W)))
     z = K.unpad3d_cl(zp, B, D, H, W, Cout).permute(0, 4, 1, 2, 3)
     assert O.max_rel(z, ref) < 1e-5
     Cp = (Cout + 63) // 64 * 64
     dzp = K.pad3d_cl(dz.permute(0, 2, 3, 4, 1).contiguous(), B, D, H, W, Cout, Cp).view(-1, Cp)
-    dw = K.gemm(dzp, xp.view(-1, Cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=3, taps=(2, Cin, sd, sh, 1))[:Cout]
+    dw = K.gemm(dzp, xp.view(-1, Cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=3, taps=(2, Cin, K.conv_tap_offsets(H, W)))[:Cout]
     assert O.max_rel(dw.view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3), wd.grad) < 1e-5
     wt = torch.zeros(Cin, 27, Cp, device="cuda", dtype=torch.bfloat16)
     wt[:, :, :Cout] = w.reshape(Cout, Cin, 27).permute(1, 2, 0)
-    dxp = K.gemm(dzp, wt.view(Cin, 27 * Cp), epilogue=K.EPI_F32, taps=(1, Cp, -sd, -sh, -1))
+    dxp = K.gemm(dzp, wt.view(Cin, 27 * Cp), epilogue=K.EPI_F32, taps=(1, Cp, K.conv_tap_offsets(H, W, -1)))
     assert O.max_rel(K.unpad3d_cl(dxp, B, D, H, W, Cin).permute(0, 4, 1, 2, 3), xd.grad) < 1e-5
+
+
+@pytest.mark.parametrize("Cin,Cout", [(64, 128), (128, 72)])
+def test_gemm_implicit_conv_stride2_matches_conv3d(Cin, Cout):
+    """Stride-2 Conv3d(k3, p1) as an implicit GEMM: the input split into eight parity volumes (hvc_s2d_pad_cl), every tap a row shift
+    into one of them; forward, weight gradient (taps on B) and data gradient (one GEMM per parity volume) against fp64 conv3d."""
+    import torch.nn.functional as F
+    from hybrid_vit_cascade_b200 import kernels as K
+    B, D, H, W = 2, 6, 4, 8
+    g = torch.Generator(device="cuda").manual_seed(3 * Cin + Cout)
+    x = torch.randn(B, Cin, D, H, W, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, 3, device="cuda", generator=g) * (27 * Cin) ** -0.5).bfloat16()
+    Do, Ho, Wo = D // 2, H // 2, W // 2
+    dz = torch.randn(B, Cout, Do, Ho, Wo, device="cuda", generator=g).bfloat16()
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    ref = F.conv3d(xd, wd, stride=2, padding=1)
+    (ref * dz.double()).sum().backward()
+    xs = K.s2d_pad_cl(x.permute(0, 2, 3, 4, 1).contiguous(), B, D, H, W, Cin)
+    rows_p = B * (Do + 1) * (Ho + 1) * (Wo + 1)
+    tt = K.conv_tap_offsets_s2(rows_p, Ho + 1, Wo + 1)
+    offs = [par * rows_p + sh for par, sh in tt]
+    w_taps = w.permute(0, 2, 3, 4, 1).reshape(Cout, 27 * Cin).contiguous()
+    zp = K.gemm(xs.view(-1, Cin), w_taps, epilogue=K.EPI_F32, taps=(1, Cin, offs), m_rows=rows_p)
+    z = K.unpad3d_cl(zp, B, Do, Ho, Wo, Cout, pad_hi=0).permute(0, 4, 1, 2, 3)
+    assert O.max_rel(z, ref) < 1e-5
+    Cp = (Cout + 63) // 64 * 64
+    dzp = K.pad3d_cl(dz.permute(0, 2, 3, 4, 1).contiguous(), B, Do, Ho, Wo, Cout, Cp, pad_hi=0).view(-1, Cp)
+    dw = K.gemm(dzp, xs.view(-1, Cin), a_major=1, b_major=1, epilogue=K.EPI_F32_ATOMIC, k_splits=2, taps=(2, Cin, offs))[:Cout]
+    assert O.max_rel(dw.view(Cout, 3, 3, 3, Cin).permute(0, 4, 1, 2, 3), wd.grad) < 1e-5
+    wt = torch.zeros(Cin, 27, Cp, device="cuda", dtype=torch.bfloat16)
+    wt[:, :, :Cout] = w.reshape(Cout, Cin, 27).permute(1, 2, 0)
+    dxs = torch.empty(8 * rows_p, Cin, device="cuda", dtype=torch.float32)
+    for par in range(8):
+        ts = [t for t, (pp, _) in enumerate(tt) if pp == par]
+        K.gemm(dzp, wt[:, ts].reshape(Cin, len(ts) * Cp), epilogue=K.EPI_F32, taps=(1, Cp, [-tt[t][1] for t in ts]),
+               out=dxs[par * rows_p:(par + 1) * rows_p])
+    dx = K.d2s_unpad_cl(dxs, B, D, H, W, Cin).permute(0, 4, 1, 2, 3)
+    assert O.max_rel(dx, xd.grad) < 1e-5
+
+
+def test_voxel_embed_implicit_gemm_matches_patch_matrix_path():
+    """HybridViT3D's conv stack at the direct-regression widths (1 -> 64 s2 -> 128 s2 -> 256 s1): the layers with Cin % 64 == 0 run as
+    implicit GEMMs (stride 2 through the parity split); with ops.IMPLICIT_EMBED = False they take the patch-matrix path.  Same
+    tokens, same gradients."""
+    import hybrid_vit_cascade_b200 as hvc
+    from hybrid_vit_cascade_b200 import ops
+    torch.manual_seed(5)
+    m = hvc.HybridViT3D(volume_size=(32, 32, 32), in_channels=1, voxel_dim=256, depth=1, num_heads=4, context_dim=64, token_grid=8).cuda()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "adaln.linear" in n:
+                p.normal_(0.0, 0.02)
+    assert [(c[0], c[1], c[2]) for c in m._plan] == [(1, 64, 2), (64, 128, 2), (128, 256, 1)]
+    g = torch.Generator(device="cuda").manual_seed(6)
+    x = torch.randn(2, 1, 32, 32, 32, device="cuda", generator=g)
+    ctx = torch.randn(2, 16, 64, device="cuda", generator=g)
+    cond = torch.randn(2, 1024, device="cuda", generator=g)
+    r = torch.randn(2, 1, 32, 32, 32, device="cuda", generator=g)
+    hvc.set_dropout_policy("ignore")
+    res = []
+    try:
+        for flag in (True, False):
+            ops.IMPLICIT_EMBED = flag
+            m.zero_grad(set_to_none=True)
+            xi = x.clone().requires_grad_(True)
+            y = m(xi, ctx, cond)
+            (y * r).sum().backward()
+            res.append((y.detach(), xi.grad, {n: p.grad.clone() for n, p in m.named_parameters() if n.startswith("voxel_embed")}))
+    finally:
+        ops.IMPLICIT_EMBED = True
+        hvc.set_dropout_policy("apply")
+    (y1, gx1, gp1), (y0, gx0, gp0) = res
+    assert O.max_rel(y1, y0) <= 5e-3 and O.cosine(gx1, gx0) >= 0.9999
+    for n in gp0:
+        assert O.cosine(gp1[n], gp0[n]) >= 0.9999, (n, O.cosine(gp1[n], gp0[n]))
 
 
 def test_layernorm_odd_token_counts():
