@@ -26,6 +26,9 @@ def _sms(dev):
 
 # stride-1 embedding convs with Cin % 64 == 0 run as implicit GEMMs (hvc_conv_taps); False = the patch-matrix path (tests compare the two)
 IMPLICIT_EMBED = True
+# ... when their patch matrix would be at least this large; below it the matrix stays L2-resident and the patch path has fewer launches
+# (64^3 direct regression, one embedded sample: 14 / 28 MB, launch-bound)
+IMPLICIT_EMBED_MIN_BYTES = 64 << 20
 
 # ------------------------------------------------------------------ bf16 weight cache
 _W16 = {}
@@ -89,6 +92,27 @@ def w16_taps_t(p, cout_pad):
     src = torch.zeros(Cin, 27, cout_pad, device=p.device, dtype=torch.float32)
     src[:, :, :Cout] = p.detach().float().reshape(Cout, Cin, 27).permute(1, 2, 0)
     t = K.cast_bf16(src.view(Cin, 27 * cout_pad))
+    _cache_put(_W16, p, key, t)
+    return t
+
+
+# taps of a stride-2 conv grouped by the parity volume they read (K.conv_tap_offsets_s2): tap order, group boundaries, device index
+_S2_TAPS = [t for par in range(8) for t in range(27) if ((t // 9 != 1) * 4 + ((t // 3) % 3 != 1) * 2 + (t % 3 != 1)) == par]
+_S2_BOUNDS = [sum(1 for t in range(27) if ((t // 9 != 1) * 4 + ((t // 3) % 3 != 1) * 2 + (t % 3 != 1)) < par) for par in range(9)]
+_S2_PERM = {}
+
+
+def w16_taps_t_s2(p, cout_pad):
+    """w16_taps_t with the 27 tap blocks reordered parity volume by parity volume, so that the B operand of each of the eight
+    data-gradient GEMMs of a stride-2 implicit conv is a column slice [cin, n_taps(par)*cout_pad] of ONE cached matrix."""
+    key = ("taps_t_s2", cout_pad)
+    t = _cache_get(_W16, p, key)
+    if t is not None:
+        return t
+    dev = p.device
+    if dev not in _S2_PERM:
+        _S2_PERM[dev] = torch.tensor(_S2_TAPS, device=dev, dtype=torch.long)
+    t = w16_taps_t(p, cout_pad).view(p.shape[1], 27, cout_pad).index_select(1, _S2_PERM[dev]).view(p.shape[1], 27 * cout_pad)
     _cache_put(_W16, p, key, t)
     return t
 
@@ -423,9 +447,10 @@ class VoxelEmbed(Function):
             # multiple of 64 channels (the last conv of every stack in the reference's configurations) needs no patch matrix at all:
             # implicit GEMM on the zero-padded volume (hvc_conv_taps)
             tm = cin % 8 == 0 and strides[1] == 1 and all(s % 8 == 0 for s in strides[:1] + strides[2:]) and (li > 0 or xB == B)
-            implicit = IMPLICIT_EMBED and tm and cin % 64 == 0 and li > 0 and cout % 8 == 0 and \
-                (stride == 1 or (Dc % 2 == 0 and Hc % 2 == 0 and Wc % 2 == 0))
             Do, Ho, Wo = K.conv_out(Dc, stride), K.conv_out(Hc, stride), K.conv_out(Wc, stride)
+            implicit = IMPLICIT_EMBED and tm and cin % 64 == 0 and li > 0 and cout % 8 == 0 and \
+                (stride == 1 or (Dc % 2 == 0 and Hc % 2 == 0 and Wc % 2 == 0)) and \
+                xB * Do * Ho * Wo * 27 * cin * 2 >= IMPLICIT_EMBED_MIN_BYTES
             if implicit and stride == 1:
                 cols = K.pad3d_cl(a.view(xB, Dc, Hc, Wc, cin), xB, Dc, Hc, Wc, cin, cin)
                 zp = K.gemm(cols.view(-1, cin), w16_taps(weight), bias=bias, epilogue=K.EPI_F32, taps=(1, cin, K.conv_tap_offsets(Hc, Wc)))
@@ -527,12 +552,12 @@ class VoxelEmbed(Function):
                     dz = K.unpad3d_cl(dxp, xB, Dc, Hc, Wc, cin).view(-1, cin)
                 else:
                     # data gradient, one GEMM per parity volume over the taps that read it: dX_par[r] = sum_t dZ[r - shift_t] W_t
-                    wt = w16_taps_t(weight, cp).view(cin, 27, cp)
+                    wt = w16_taps_t_s2(weight, cp)                 # tap blocks grouped by parity volume: column slices, no copies
                     dxp = torch.empty(8 * rows_p, cin, device=dtok.device, dtype=torch.float32)
                     for par in range(8):
-                        ts = [t for t, (pp, _) in enumerate(tt) if pp == par]
-                        K.gemm(dzp, wt[:, ts].reshape(cin, len(ts) * cp), epilogue=K.EPI_F32, taps=(1, cp, [-tt[t][1] for t in ts]),
-                               out=dxp[par * rows_p:(par + 1) * rows_p])
+                        ts = _S2_TAPS[_S2_BOUNDS[par]:_S2_BOUNDS[par + 1]]
+                        K.gemm(dzp, wt[:, _S2_BOUNDS[par] * cp:_S2_BOUNDS[par + 1] * cp], epilogue=K.EPI_F32,
+                               taps=(1, cp, [-tt[t][1] for t in ts]), out=dxp[par * rows_p:(par + 1) * rows_p])
                     dz = K.d2s_unpad_cl(dxp, xB, Dc, Hc, Wc, cin).view(-1, cin)
                 del dxp, dzp
                 continue

@@ -163,6 +163,8 @@ def test_voxel_embed_implicit_gemm_matches_patch_matrix_path():
     r = torch.randn(2, 1, 32, 32, 32, device="cuda", generator=g)
     hvc.set_dropout_policy("ignore")
     res = []
+    min_bytes = ops.IMPLICIT_EMBED_MIN_BYTES
+    ops.IMPLICIT_EMBED_MIN_BYTES = 0          # (the size rule would keep this small volume on the patch path)
     try:
         for flag in (True, False):
             ops.IMPLICIT_EMBED = flag
@@ -173,6 +175,7 @@ def test_voxel_embed_implicit_gemm_matches_patch_matrix_path():
             res.append((y.detach(), xi.grad, {n: p.grad.clone() for n, p in m.named_parameters() if n.startswith("voxel_embed")}))
     finally:
         ops.IMPLICIT_EMBED = True
+        ops.IMPLICIT_EMBED_MIN_BYTES = min_bytes
         hvc.set_dropout_policy("apply")
     (y1, gx1, gp1), (y0, gx0, gp0) = res
     assert O.max_rel(y1, y0) <= 5e-3 and O.cosine(gx1, gx0) >= 0.9999
