@@ -228,7 +228,11 @@ def run_b200(args, w):
         params = list(model.parameters())
     gb = GradientBuckets(params)
     gb.broadcast_parameters(params)
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=bool(args.graph))
+    flat_opt = args.optimizer == "flat"
+    if flat_opt:    # one sum-of-squares + one fused clip+AdamW kernel per gradient bucket (hvc_optim.cu)
+        opt = hvc.FlatAdamW(gb, lr=1e-4, weight_decay=0.01, max_grad_norm=args.clip)
+    else:
+        opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True, capturable=bool(args.graph))
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     hw = w["ctx_hw"]
@@ -260,7 +264,7 @@ def run_b200(args, w):
             loss = loss_fn(out, target_)
             loss.backward()
             gb.finish()
-            if args.clip > 0:
+            if args.clip > 0 and not flat_opt:
                 torch.nn.utils.clip_grad_norm_(params, args.clip, foreach=True)
             opt.step()
             return loss
@@ -269,7 +273,7 @@ def run_b200(args, w):
             loss = loss_fn(out, target_)
             loss.backward()
             gb.finish()
-            if args.clip > 0:
+            if args.clip > 0 and not flat_opt:
                 torch.nn.utils.clip_grad_norm_(params, args.clip, foreach=True)
             opt.step()
             return loss
@@ -285,7 +289,7 @@ def run_b200(args, w):
         loss = loss_fn(out, target_)
         loss.backward()
         gb.finish()
-        if args.clip > 0:
+        if args.clip > 0 and not flat_opt:
             torch.nn.utils.clip_grad_norm_(params, args.clip, foreach=True)     # after the all-reduce, on the averaged gradients
         opt.step()
         return loss
@@ -427,7 +431,7 @@ def run_b200(args, w):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": w["desc"], "batch_per_gpu": B, "global_batch": B * world, "voxel_dim": w["voxel_dim"],
                    "heads": w["heads"], "depth": w["depth"], "tokens": oracle_cfg(w).num_tokens, "context_tokens": hw * hw,
-                   "parallelism": f"dp{world}", "dropout": 0.1 if args.dropout == "on" else 0.0, "optimizer": "AdamW(fused)", "grad_clip": args.clip,
+                   "parallelism": f"dp{world}", "dropout": 0.1 if args.dropout == "on" else 0.0, "optimizer": "FlatAdamW (hvc_optim.cu, clip fused)" if flat_opt else "AdamW(fused)", "grad_clip": args.clip,
                    "loss": "L1 + 0.5*(1-SSIM3D) (DirectRegressionLoss, hvc_loss.cu)" if args.loss == "direct" else "L1",
                    "l2_note": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush"},
         "e2e": {"value": vols / (ms_e2e / 1e3), "unit": "volumes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -471,6 +475,8 @@ def main():
     ap.add_argument("--dropout", default="on", choices=["on", "off"],
                     help="train-mode nn.Dropout(p=0.1) of the six sites per block, as the reference trainers run (masks regenerated inside "
                          "the kernels); 'on' also reports the dropout-off step as line['dropout_off']")
+    ap.add_argument("--optimizer", default="torch", choices=["torch", "flat"],
+                    help="torch: clip_grad_norm_(foreach) + AdamW(fused); flat: hvc.FlatAdamW on the gradient buckets (hvc_optim.cu)")
     ap.add_argument("--clip", type=float, default=1.0, help="gradient-norm clip (config_direct.json: 1.0; 0 = off)")
     ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")

@@ -13,7 +13,8 @@ from .hybrid_vit_backbone import HybridViT3D, HybridViTBlock3D  # noqa: F401
 from .xray_encoder import (DirectCTRegression, MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128, Stage3Refiner256, ProgressiveCascadeModel,  # noqa: F401
                            XrayConditioningModule)
 from .losses import DirectRegressionLoss, compute_ssim_loss  # noqa: F401
+from .optim import FlatAdamW  # noqa: F401
 
 __all__ = ["AdaLNModulation", "MultiHeadCrossAttention", "MultiHeadSelfAttention", "SinusoidalTimeEmbedding",
-           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "MultiScaleXrayEncoder", "DirectCTRegression", "Stage1Base64", "Stage2Refiner128", "Stage3Refiner256", "ProgressiveCascadeModel", "DirectRegressionLoss", "compute_ssim_loss", "set_dropout_policy", "set_precision",
+           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "MultiScaleXrayEncoder", "DirectCTRegression", "Stage1Base64", "Stage2Refiner128", "Stage3Refiner256", "ProgressiveCascadeModel", "DirectRegressionLoss", "compute_ssim_loss", "FlatAdamW", "set_dropout_policy", "set_precision",
            "precision"]

@@ -25,10 +25,11 @@ class GradientBuckets:
         params = list(reversed(params))                     # backward visits the last layers first
         self.buckets: List[torch.Tensor] = []
         self._members: List[List[torch.nn.Parameter]] = []
+        self._offsets: List[List[int]] = []
         self._bucket_of = {}
         cur, cur_bytes = [], 0
         for p in params:
-            nbytes = p.numel() * 4
+            nbytes = (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN * 4
             if cur and cur_bytes + nbytes > bucket_bytes:
                 self._close(cur)
                 cur, cur_bytes = [], 0
@@ -41,17 +42,21 @@ class GradientBuckets:
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self.reset()
 
+    ALIGN = 64      # elements: every member starts on a 256-byte boundary (kernels read parameters / gradients with 16-byte accesses)
+
     def _close(self, members):
-        total = sum(p.numel() for p in members)
-        flat = torch.zeros(total, device=members[0].device, dtype=torch.float32)
-        off = 0
-        idx = len(self.buckets)
+        offsets, off = [], 0
         for p in members:
-            p.grad = flat[off:off + p.numel()].view_as(p)   # autograd accumulates in place into the bucket
+            offsets.append(off)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        flat = torch.zeros(off, device=members[0].device, dtype=torch.float32)     # the padding stays zero
+        idx = len(self.buckets)
+        for p, o in zip(members, offsets):
+            p.grad = flat[o:o + p.numel()].view_as(p)   # autograd accumulates in place into the bucket
             self._bucket_of[p] = idx
-            off += p.numel()
         self.buckets.append(flat)
         self._members.append(members)
+        self._offsets.append(offsets)
 
     def broadcast_parameters(self, params, src: int = 0):
         """One-time replica sync at start-up (what the DDP constructor does)."""
@@ -79,14 +84,12 @@ class GradientBuckets:
 
     def _rebind(self, i):
         """If something replaced p.grad (e.g. zero_grad(set_to_none=True)), copy back into the bucket views."""
-        off = 0
         flat = self.buckets[i]
-        for p in self._members[i]:
+        for p, off in zip(self._members[i], self._offsets[i]):
             view = flat[off:off + p.numel()].view_as(p)
             if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
             p.grad = view
-            off += p.numel()
 
     def finish(self):
         """Wait for the outstanding all-reduces (the current stream waits; the host does not block on NCCL)."""

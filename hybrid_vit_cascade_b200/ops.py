@@ -117,8 +117,14 @@ def w16_taps_t_s2(p, cout_pad):
     return t
 
 
+_CACHES = [_W16]        # every per-parameter cache of derived operands registers here (ops_fp32._W6, xray_encoder._W3)
+
+
 def clear_weight_cache():
-    _W16.clear()
+    """Drop every cached derived operand: call after parameters were written behind autograd's version counters
+    (optim.FlatAdamW does)."""
+    for c in _CACHES:
+        c.clear()
 
 
 # ------------------------------------------------------------------ GEMM helpers (no autograd)

@@ -10,10 +10,12 @@ Attention materialises the scores per (batch, head).  Forward only (no autograd 
 import torch
 
 from . import kernels as K
+from . import ops
 from .ops import _cache_get, _cache_put
 
 A_SIDE, B_SIDE = 0, 1
 _W6 = {}
+ops._CACHES.append(_W6)
 
 
 def w6(p, pad_to=None):

@@ -1,0 +1,70 @@
+"""Optimizer step on the flat gradient buckets.
+
+The reference trainers call ``torch.nn.utils.clip_grad_norm_(model.parameters(), gradient_clip)`` and ``AdamW.step()``
+(train_direct_4gpu.py:72-80; config_direct.json: lr 1e-4, weight_decay 0.01, gradient_clip 1.0).  ``dp.GradientBuckets`` already holds
+every gradient as a view into a few flat fp32 buffers; ``FlatAdamW`` lays the parameters and both Adam moments out the same way
+(``p.data`` becomes a view, so modules, ``state_dict`` and checkpoints are unaffected) and does the whole step with one
+sum-of-squares kernel and one fused clip+AdamW kernel per bucket (``csrc/hvc_optim.cu``).  The step count lives on the device: the
+step is CUDA-graph capturable.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .kernels import _need_cuda, _ptr, _stream
+
+
+class FlatAdamW:
+    def __init__(self, buckets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=0.0):
+        self.gb = buckets
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        self.params, self.exp_avg, self.exp_avg_sq = [], [], []
+        for flat_g, members, offsets in zip(buckets.buckets, buckets._members, buckets._offsets):
+            _need_cuda(flat_g)
+            flat_p = torch.zeros_like(flat_g)          # (alignment padding between members stays zero through every update)
+            with torch.no_grad():
+                for p, off in zip(members, offsets):
+                    assert p.dtype == torch.float32, "FlatAdamW expects fp32 master parameters"
+                    view = flat_p[off:off + p.numel()].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view                      # same values, new storage: the bucket layout
+            self.params.append(flat_p)
+            self.exp_avg.append(torch.zeros_like(flat_g))
+            self.exp_avg_sq.append(torch.zeros_like(flat_g))
+        dev = buckets.buckets[0].device
+        self.state = torch.zeros(1, device=dev, dtype=torch.float32)        # step count t
+        self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)        # ||g||^2 over all buckets
+        ops.clear_weight_cache()
+
+    @torch.no_grad()
+    def step(self):
+        """Clip (global L2 norm over all bucketed gradients, as clip_grad_norm_) + AdamW.  Call after GradientBuckets.finish()."""
+        lib, st = _lib.lib(), _stream()
+        _lib.check(lib.hvc_adamw_tick(_ptr(self.state), st), "hvc_adamw_tick")
+        clip = self.max_grad_norm > 0
+        if clip:
+            self.sumsq.zero_()
+            for g in self.gb.buckets:
+                _lib.check(lib.hvc_sumsq_f32(_ptr(g), C.c_int64(g.numel()), _ptr(self.sumsq), st), "hvc_sumsq_f32")
+        f = C.c_float
+        for p, g, m, v in zip(self.params, self.gb.buckets, self.exp_avg, self.exp_avg_sq):
+            _lib.check(lib.hvc_adamw_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(p.numel()), f(self.lr), f(self.betas[0]),
+                                          f(self.betas[1]), f(self.eps), f(self.weight_decay), f(self.max_grad_norm if clip else 0.0),
+                                          _ptr(self.sumsq), _ptr(self.state), st), "hvc_adamw_flat")
+        ops.clear_weight_cache()       # the kernels write the parameters behind autograd's version counters
+
+    def grad_norm(self):
+        """Global gradient norm of the last step (device tensor; what clip_grad_norm_ returns)."""
+        return self.sumsq.sqrt()
+
+    def state_dict(self):
+        return {"step": self.state.clone(), "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq],
+                "hyper": dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, max_grad_norm=self.max_grad_norm)}
+
+    def load_state_dict(self, sd):
+        self.state.copy_(sd["step"])
+        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
+            dst.copy_(src)
+        for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
+            dst.copy_(src)

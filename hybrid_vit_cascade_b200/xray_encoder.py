@@ -20,6 +20,7 @@ from .hybrid_vit_backbone import HybridViT3D
 
 
 _W3 = {}
+ops._CACHES.append(_W3)
 
 
 def _w3(p, pad_to):

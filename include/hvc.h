@@ -387,6 +387,19 @@ int hvc_ssim_l1_fwd(const float* pred, const float* target, int32_t B, int32_t D
 int hvc_ssim_l1_bwd(const float* pred, const float* target, const float* filtered, int32_t B, int32_t D, int32_t H, int32_t W,
                     int32_t window, float c_ssim, float c_l1, const float* upstream, float* scratch, float* dpred, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer step on flat fp32 buffers: torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step() of the
+ * reference trainers (train_direct_4gpu.py:72-80) over the data-parallel gradient buckets.
+ *   hvc_sumsq_f32:  accum[0] += sum x^2 (double; zero it first, call once per bucket)
+ *   hvc_adamw_tick: state[0] += 1 (the step count t, kept on the device so the step can live in a CUDA graph)
+ *   hvc_adamw_flat: g' = g * min(1, max_norm / (sqrt(sumsq[0]) + 1e-6)) (max_norm <= 0: no clipping);
+ *                   p *= 1 - lr*wd;  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * ---------------------------------------------------------------------------------------------- */
+int hvc_sumsq_f32(const float* x, int64_t n, double* accum, void* stream);
+int hvc_adamw_tick(float* state, void* stream);
+int hvc_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float max_norm, const double* sumsq, const float* state, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

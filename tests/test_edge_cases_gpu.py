@@ -212,3 +212,46 @@ def test_errors_come_back_as_exceptions_not_crashes():
     # the library is still usable after the failures
     out = K.gemm(x, x)
     assert out.shape == (64, 64)
+
+
+def test_flat_adamw_matches_torch_clip_and_adamw():
+    """optim.FlatAdamW (one sum-of-squares + one fused clip+AdamW kernel per gradient bucket) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same gradients, several steps, clipping active and inactive; the
+    modules keep working on the re-pointed parameters (derived bf16 operands are refreshed)."""
+    import hybrid_vit_cascade_b200 as hvc
+    from hybrid_vit_cascade_b200.dp import GradientBuckets
+    torch.manual_seed(3)
+    shapes = [(257, 33), (64,), (5, 7, 3), (1,), (1024, 130)]
+    mine = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in mine]
+    gb = GradientBuckets(mine, bucket_bytes=64 << 10)           # several buckets
+    assert len(gb.buckets) >= 2
+    opt = hvc.FlatAdamW(gb, lr=1e-2, weight_decay=0.05, max_grad_norm=1.0)
+    topt = torch.optim.AdamW(ref, lr=1e-2, weight_decay=0.05)
+    for p, r in zip(mine, ref):
+        assert torch.equal(p.data, r.data)                       # re-pointing kept the values
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for step in range(6):
+        scale = 1e-3 if step % 2 else 3.0                        # below / above the clipping threshold
+        gb.reset()
+        for p, r in zip(mine, ref):
+            gr = torch.randn(p.shape, device="cuda", generator=g) * scale
+            p.grad.copy_(gr)
+            r.grad = gr.clone()
+        total = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        topt.step()
+        opt.step()
+        assert abs(float(opt.grad_norm()) - float(total)) <= 1e-5 * float(total)
+        for p, r in zip(mine, ref):
+            assert O.max_rel(p.data, r.data) <= 2e-6, (step, tuple(p.shape), O.max_rel(p.data, r.data))
+    # a module stepping through FlatAdamW: the cached bf16 weights must follow the update
+    lin = hvc.MultiHeadSelfAttention(64, num_heads=2, dropout=0.0).cuda()
+    x = torch.randn(2, 128, 64, device="cuda", generator=g)
+    gb2 = GradientBuckets(list(lin.parameters()))
+    opt2 = hvc.FlatAdamW(gb2, lr=0.05, weight_decay=0.0)
+    y0 = lin(x).detach().clone()
+    gb2.reset()
+    lin(x).square().mean().backward()
+    opt2.step()
+    y1 = lin(x).detach()
+    assert O.max_rel(y1, y0) > 1e-2                               # the forward sees the new weights
