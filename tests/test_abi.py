@@ -4,6 +4,7 @@ import os
 import re
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -110,3 +111,47 @@ def test_weight_cache_is_not_fooled_by_id_reuse():
     with torch.no_grad():
         p.add_(1)
     assert ops._cache_get(cache, p, None) is None       # an in-place update (optimizer step) invalidates the entry
+
+
+def test_implicit_conv_tap_offsets_describe_conv3d():
+    """Host logic of the implicit-GEMM Conv3d (include/hvc.h, hvc_conv_taps): the per-tap row shifts that kernels.conv_tap_offsets /
+    conv_tap_offsets_s2 hand to the GEMM's TMA producer, applied here as plain row gathers on the same padded layouts (built with
+    torch on the CPU), must reproduce F.conv3d for stride 1 and stride 2."""
+    import torch.nn.functional as F
+    from hybrid_vit_cascade_b200 import kernels as K
+    g = torch.Generator().manual_seed(0)
+    B, C, Co, D, H, W = 2, 3, 4, 4, 6, 8
+    x = torch.randn(B, C, D, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(Co, C, 3, 3, 3, generator=g, dtype=torch.float64)
+    w_taps = w.permute(0, 2, 3, 4, 1).reshape(Co, 27, C)                       # [Cout, tap, cin]
+
+    def gather(mat, rows, off):                                                # rows outside the matrix read as zero (TMA fill)
+        idx = rows + off
+        ok = (idx >= 0) & (idx < mat.shape[0])
+        out = torch.zeros(len(rows), mat.shape[1], dtype=mat.dtype)
+        out[ok] = mat[idx[ok]]
+        return out
+
+    # stride 1: (B, D+2, H+2, W+2, C) padded volume, output on the same padded grid
+    xp = F.pad(x.permute(0, 2, 3, 4, 1), (0, 0, 1, 1, 1, 1, 1, 1)).reshape(-1, C)
+    rows = torch.arange(xp.shape[0])
+    z = sum(gather(xp, rows, o) @ w_taps[:, t].T for t, o in enumerate(K.conv_tap_offsets(H, W)))
+    z = z.view(B, D + 2, H + 2, W + 2, Co)[:, 1:-1, 1:-1, 1:-1].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(z, F.conv3d(x, w, padding=1), atol=1e-12)
+    # stride 2: eight parity volumes, each padded by one voxel on the low side, stacked along the rows
+    Dh, Hh, Wh = D // 2, H // 2, W // 2
+    vols = []
+    for par in range(8):
+        v = x[:, :, (par >> 2)::2, ((par >> 1) & 1)::2, (par & 1)::2].permute(0, 2, 3, 4, 1)
+        vols.append(F.pad(v, (0, 0, 1, 0, 1, 0, 1, 0)))
+    xs = torch.stack(vols).reshape(-1, C)
+    rows_p = B * (Dh + 1) * (Hh + 1) * (Wh + 1)
+    rows = torch.arange(rows_p)
+    tt = K.conv_tap_offsets_s2(rows_p, Hh + 1, Wh + 1)
+    z = sum(gather(xs, rows, par * rows_p + sh) @ w_taps[:, t].T for t, (par, sh) in enumerate(tt))
+    z = z.view(B, Dh + 1, Hh + 1, Wh + 1, Co)[:, 1:, 1:, 1:].permute(0, 4, 1, 2, 3)
+    assert torch.allclose(z, F.conv3d(x, w, stride=2, padding=1), atol=1e-12)
+    # the parity grouping the data gradient uses (ops._S2_TAPS / _S2_BOUNDS) is the same table
+    from hybrid_vit_cascade_b200 import ops
+    for par in range(8):
+        assert ops._S2_TAPS[ops._S2_BOUNDS[par]:ops._S2_BOUNDS[par + 1]] == [t for t, (pp, _) in enumerate(tt) if pp == par]
