@@ -3,10 +3,13 @@ only tests/, __graft_entry__.smoke() and bench.py's CPU arm may import this).
 
     XrayConditioningModule.forward   models/diagnostic_losses.py:107-138
     DirectCTRegression.forward       direct_regression/model_direct.py:59-85
+    compute_ssim_loss / DirectRegressionLoss                                  direct_regression/model_direct.py:88-131
+    MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128, Stage3Refiner256, ProgressiveCascadeModel
+                                     direct_regression/progressive_cascade/model_progressive.py:57-83, 125-150, 193-215, 273-315, 371-402
 
 Functional over a state_dict, like oracle/vit_oracle.py; autograd gives the gradients.  Pinned against outputs of the real
-reference modules run in the authoring container (tests/golden/make_golden.py -> tests/golden/encoder.pt,
-tests/test_oracle_golden.py).
+reference modules run in the authoring container (tests/golden/make_golden_encoder.py -> tests/golden/encoder.pt,
+tests/golden/make_golden_loss.py -> direct_loss.pt; replayed by tests/test_oracle_golden.py).
 """
 from typing import Dict, Optional
 
