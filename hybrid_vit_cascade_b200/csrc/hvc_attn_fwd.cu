@@ -115,6 +115,10 @@ template <bool MASKED, bool DROP, int EMU>
 __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint32_t tP, int c0, int tail, float2 scale2v, float2 neg_m,
                                                   float2& sum, uint32_t rowkey, uint32_t col0, uint32_t thr) {
   uint32_t pk[16];
+  // the mask hashes do not depend on the scores, and ptxas hoisted a whole tile of them ahead of the TMEM loads, parking ~40 in local
+  // memory (160 B of spills per thread): the empty asm makes this chunk's block key formally depend on its first score, so the hashes
+  // are computed chunk by chunk (24 B of spills; forward 594 -> 620 TFLOP/s in the train-mode step, same box)
+  if (DROP) asm volatile("" : "+r"(rowkey) : "r"(v[0]));
 #pragma unroll
   for (int c = 0; c < 32; c += 2) {
     const float2 a = ffma2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), scale2v, neg_m);
