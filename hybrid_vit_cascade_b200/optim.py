@@ -48,10 +48,22 @@ class FlatAdamW:
             for g in self.gb.buckets:
                 _lib.check(lib.hvc_sumsq_f32(_ptr(g), C.c_int64(g.numel()), _ptr(self.sumsq), st), "hvc_sumsq_f32")
         f = C.c_float
-        for p, g, m, v in zip(self.params, self.gb.buckets, self.exp_avg, self.exp_avg_sq):
-            _lib.check(lib.hvc_adamw_flat(_ptr(p), _ptr(g), _ptr(m), _ptr(v), C.c_int64(p.numel()), f(self.lr), f(self.betas[0]),
+
+        def tick(pt, gt, mt, vt):
+            _lib.check(lib.hvc_adamw_flat(_ptr(pt), _ptr(gt), _ptr(mt), _ptr(vt), C.c_int64(pt.numel()), f(self.lr), f(self.betas[0]),
                                           f(self.betas[1]), f(self.eps), f(self.weight_decay), f(self.max_grad_norm if clip else 0.0),
                                           _ptr(self.sumsq), _ptr(self.state), st), "hvc_adamw_flat")
+
+        for i, (p, g, m, v) in enumerate(zip(self.params, self.gb.buckets, self.exp_avg, self.exp_avg_sq)):
+            members, offsets, got = self.gb._members[i], self.gb._offsets[i], self.gb.touched(i)
+            if len(got) == len(members):
+                tick(p, g, m, v)                       # the usual case: one launch per bucket
+                continue
+            # a trainable parameter that took no part in this step (its slot holds zeros, not a gradient): torch.optim.AdamW skips
+            # parameters whose grad is None -- no weight decay, no moment decay -- so only the members that got a gradient are updated
+            for k in sorted(got):
+                lo, n = offsets[k], members[k].numel()
+                tick(p[lo:lo + n], g[lo:lo + n], m[lo:lo + n], v[lo:lo + n])
         ops.clear_weight_cache()       # the kernels write the parameters behind autograd's version counters
 
     def grad_norm(self):
