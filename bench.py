@@ -148,15 +148,17 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_baseline(w, seconds_budget=20.0, rows=2048, steps=None, warmup=1):
-    """Oracle port on the host cores, bounded sample (oracle/cpu_baseline.py)."""
+def cpu_baseline(w, seconds_budget=20.0, rows=2048, steps=None, warmup=1, train=True):
+    """Oracle port on the host cores, bounded sample (oracle/cpu_baseline.py).  The sample executes `measured_fraction` of one
+    volume's work and the per-volume time is EXTRAPOLATED from it (flagged as such in every line that carries it)."""
     from oracle.cpu_baseline import CpuBaseline
-    cb = CpuBaseline(oracle_cfg(w), w["ctx_hw"] ** 2, rows=rows)
+    cb = CpuBaseline(oracle_cfg(w), w["ctx_hw"] ** 2, rows=rows, train=train)
     for _ in range(warmup):
         cb.step()
-    est, t0 = [], time.perf_counter()
+    est, meas, t0 = [], [], time.perf_counter()
     while True:
         est.append(cb.step())
+        meas.append(cb.last_measured_s)
         if steps is not None:
             if len(est) >= steps:
                 break
@@ -164,24 +166,128 @@ def cpu_baseline(w, seconds_budget=20.0, rows=2048, steps=None, warmup=1):
             break
     sec_per_vol = min(est) if steps is None else sum(est) / len(est)
     return {"value": 1.0 / sec_per_vol, "unit": "volumes/s", "cores": cb.threads, "kind": "port", "sample": cb.describe(),
-            "sec_per_volume": sec_per_vol, "samples": len(est)}
+            "extrapolated": True, "measured_fraction": cb.measured_fraction(), "measured_ms_per_sample_step": 1e3 * sum(meas) / len(meas),
+            "dropout": 0.1 if train else 0.0, "sec_per_volume": sec_per_vol, "samples": len(est)}
+
+
+def a0_full(best_of=2):
+    """BASELINE.json configs[0] / SURVEY 8(d) 'config A0', measured IN FULL on the host cores: DirectCTRegression 64^3, B=1,
+    forward + loss + backward, train() and dropout-off.  One warm-up step, then best of `best_of` per mode."""
+    from oracle.cpu_baseline import A0Full
+    a = A0Full()
+    a.step(False)
+    out = {"cores": a.threads, "kind": "port", "extrapolated": False, "steps_per_mode": best_of}
+    for name, train in (("train", True), ("dropout_off", False)):
+        t = min(a.step(train) for _ in range(best_of))
+        out[name] = {"value": 1.0 / t, "unit": "volumes/s", "ms_per_step": t * 1e3, "sample": a.describe(train)}
+    return out
 
 
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(w, rows=args.cpu_rows, steps=args.steps, warmup=max(1, min(args.warmup, 2)))
+    t_wall = time.perf_counter()
+    cb = cpu_baseline(w, rows=args.cpu_rows, steps=args.steps, warmup=max(1, min(args.warmup, 2)), train=True)
+    cb_off = cpu_baseline(w, rows=args.cpu_rows, steps=2, warmup=1, train=False)      # the same sample with the nn.Dropout sites off
+    full = a0_full() if not args.skip_a0 else None
     line = {
         "impl": "reference", "metric": "train volumes/sec (3D ViT backbone fwd+bwd)", "value": cb["value"], "unit": "volumes/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["sec_per_volume"] * 1e3,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        # what one timed step of THIS run took (the bounded sample), not the per-volume estimate: value = 1 / (ms_per_step / measured_fraction + embed/head)
+        "ms_per_step": cb["measured_ms_per_sample_step"], "extrapolated": True, "measured_fraction": cb["measured_fraction"],
+        "estimated_ms_per_volume": cb["sec_per_volume"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "batch_per_gpu": 1, "dropout": 0.0, "note": "CPU arm: one step = one bounded sample of one volume"},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": {"workload": w["desc"], "batch_per_gpu": 1, "dropout": 0.1,
+                   "note": "CPU arm, train mode like the GPU arm: one step = one bounded sample of one volume (one block, a slab of query rows); "
+                           "value is EXTRAPOLATED from it (the full 128^3 step needs 15.8 TFLOP and a 17 GB score tensor per block on the host); "
+                           "a0_full is the reference's own CPU-runnable configuration measured in full"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "measured_fraction")},
         "e2e": {"value": cb["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["dropout_off"] = {k: cb_off[k] for k in ("value", "unit", "extrapolated", "measured_fraction", "measured_ms_per_sample_step", "sample")}
+    if full:
+        line["a0_full"] = full
+    line["wall_s"] = time.perf_counter() - t_wall
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU-eager arm
+def _run_self(extra, timeout=900):
+    """Run this script again (fresh process, fresh CUDA context) and parse its one JSON line."""
+    r = subprocess.run([sys.executable, os.path.abspath(__file__)] + extra, capture_output=True, text=True, timeout=timeout)
+    for ln in reversed(r.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)
+    raise RuntimeError(f"bench.py {' '.join(extra)} printed no JSON line (rc {r.returncode}): {r.stderr[-400:]}")
+
+
+def run_eager(args):
+    """SURVEY 0.1 / BASELINE.md 3: 'the bar is PyTorch eager on the same B200'.  The oracle port (the reference's ATen calls) under
+    torch.autocast(bf16) on cuda:0, timed beside the hand-written kernels:
+      * the full 64^3 direct-regression training step at batch 8 (configs[1]) -- eager vs this package (a bench.py --workload direct64 run);
+      * one block at the headline configuration's 32768 tokens, batch 1, forward+backward -- all of it that the reference's
+        materialised softmax lets a 180 GB GPU hold."""
+    import hybrid_vit_cascade_b200 as hvc
+    from oracle import eager_baseline as EB
+    from oracle import vit_oracle as O
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    out = {"impl": "eager", "what": "oracle port of the reference modules on the same B200, torch.autocast(bf16), cuBLAS/ATen eager kernels",
+           "torch": torch.__version__}
+    # ---- one block at 32768 tokens, B = 1, train mode and dropout off
+    blk = {}
+    for mode, train in (("train", True), ("dropout_off", False)):
+        try:
+            eb = EB.Block32768(dev, heads=4, train=train)
+            ms_eager = eb.ms_per_step(steps=3, warmup=1)
+            sd = {k[len("blocks.0."):]: v.detach() for k, v in eb.sd.items()}
+            x, ctx, cond, r = eb.x.detach(), eb.ctx, eb.cond, eb.r
+            del eb
+            torch.cuda.empty_cache()
+        except torch.OutOfMemoryError as e:     # pragma: no cover
+            blk[mode] = {"eager": "out of memory", "detail": str(e)[:120]}
+            continue
+        m = hvc.HybridViTBlock3D(256, num_heads=4, context_dim=512, cond_dim=1024).to(dev).train()
+        m.load_state_dict(sd, strict=True)
+        hvc.set_dropout_policy("apply" if train else "ignore")
+        xg = x.clone().requires_grad_(True)
+
+        def hstep():
+            m.zero_grad(set_to_none=True)
+            xg.grad = None
+            (m(xg, ctx, cond) * r).sum().backward()
+
+        from oracle.eager_baseline import _time
+        ms_hvc = _time(hstep, 5, 2)
+        hvc.set_dropout_policy("apply")
+        blk[mode] = {"eager_ms": ms_eager, "hvc_ms": ms_hvc, "speedup": ms_eager / ms_hvc}
+        del m
+        torch.cuda.empty_cache()
+    out["block_32768_tokens_b1_fwd_bwd"] = dict(blk, shape="HybridViTBlock3D C=256, 4 heads (d=64), 32768 tokens, 4096 context tokens, batch 1")
+    # ---- full 64^3 training step at batch 8
+    d64 = {}
+    for mode, train in (("train", True), ("dropout_off", False)):
+        st = EB.Direct64Step(dev, batch=8, train=train)
+        d64[mode] = {"eager_ms": st.ms_per_step(steps=args.steps, warmup=max(2, args.warmup))}
+        del st
+        torch.cuda.empty_cache()
+    try:
+        h = _run_self(["--workload", "direct64", "--skip-cpu-baseline", "--skip-eager", "--steps", str(max(args.steps, 10)), "--warmup", "5"])
+        d64["train"]["hvc_ms"] = h["ms_per_step"]
+        d64["dropout_off"]["hvc_ms"] = h["dropout_off"]["ms_per_step"]
+        for k in ("train", "dropout_off"):
+            d64[k]["speedup"] = d64[k]["eager_ms"] / d64[k]["hvc_ms"]
+            d64[k]["eager_volumes_per_s"] = 8e3 / d64[k]["eager_ms"]
+            d64[k]["hvc_volumes_per_s"] = 8e3 / d64[k]["hvc_ms"]
+    except Exception as e:      # pragma: no cover
+        d64["hvc_error"] = str(e)[:300]
+    out["direct64_b8_training_step"] = dict(d64, shape="direct_regression 64^3 backbone, B=8, 4096 tokens: forward + DirectRegressionLoss + backward + clip + AdamW")
+    out.update({"metric": "train volumes/sec (3D ViT backbone fwd+bwd)", "value": 8e3 / d64["train"]["eager_ms"], "unit": "volumes/s", "n_gpus": 1,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": d64["train"]["eager_ms"], "higher_is_better": True, "dtype": "bf16",
+                "data": "synthetic", "config": {"workload": WORKLOADS["direct64"]["desc"], "batch_per_gpu": 8, "dropout": 0.1}})
+    print(json.dumps(out), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -453,8 +559,17 @@ def run_b200(args, w):
         line["cuda_graph"] = graph_info
         line["config"]["step_launch"] = "one CUDA graph per step (value, e2e); roofline / kernels / clocks from the eager run before it"
     if world == 1 and not args.skip_cpu_baseline:
-        cb = cpu_baseline(w, rows=args.cpu_rows)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb = cpu_baseline(w, rows=args.cpu_rows, train=args.dropout == "on")
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated", "measured_fraction", "dropout")}
+    if world == 1 and not args.skip_eager:
+        # the reference's own algorithm as PyTorch eager on this same GPU (a fresh process; this one's tensors are released first)
+        try:
+            del model, opt, gb
+            torch.cuda.empty_cache()
+            eg = _run_self(["--impl", "eager", "--steps", "5", "--warmup", "2"])
+            line["eager_b200"] = {k: eg[k] for k in ("what", "block_32768_tokens_b1_fwd_bwd", "direct64_b8_training_step", "torch") if k in eg}
+        except Exception as e:      # pragma: no cover
+            line["eager_b200"] = {"error": str(e)[:300]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -465,7 +580,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager"],
+                    help="b200: this package; reference: the reference's algorithm on the host cores (oracle port); eager: the same algorithm "
+                         "as PyTorch eager on the GPU under autocast(bf16)")
     ap.add_argument("--workload", default="direct128", choices=sorted(WORKLOADS),
                     help="direct128 = BASELINE.json's metric configuration (default); the others are the remaining configs")
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
@@ -478,12 +595,17 @@ def main():
     ap.add_argument("--optimizer", default="torch", choices=["torch", "flat"],
                     help="torch: clip_grad_norm_(foreach) + AdamW(fused); flat: hvc.FlatAdamW on the gradient buckets (hvc_optim.cu)")
     ap.add_argument("--clip", type=float, default=1.0, help="gradient-norm clip (config_direct.json: 1.0; 0 = off)")
-    ap.add_argument("--cpu-rows", type=int, default=2048, help="query rows in the CPU baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=1024, help="query rows in the CPU baseline sample")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true", help="do not time the GPU-eager arm beside the kernels (eager_b200 key)")
+    ap.add_argument("--skip-a0", action="store_true", help="--impl reference: skip the fully measured config-A0 steps")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
+    elif args.impl == "eager":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_eager(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py --impl b200 needs a CUDA device (sm_100); there is no CPU fallback")

@@ -165,7 +165,8 @@ def check(rc, what=""):
 
 
 def require_device(dev_index):
-    """Verify once per device that we are on sm_100 with a usable driver."""
+    """Verify once per device that we are on sm_100 with a usable driver.  hvc_check_device() inspects the CURRENT device, so
+    `dev_index` must be the current device's ordinal (kernels._need_cuda passes torch.cuda.current_device())."""
     if not _device_ok.get(dev_index):
         check(lib().hvc_check_device(), "hvc_check_device")
         _device_ok[dev_index] = True

@@ -659,11 +659,7 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   ka.dk = reinterpret_cast<bf16*>(a->dk); ka.lddk = a->lddk;
   ka.dv = reinterpret_cast<bf16*>(a->dv); ka.lddv = a->lddv;
   ka.scale = a->scale; ka.scale2 = a->scale * 1.4426950408889634f;
-  static bool configured = false;
-  if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<HD, DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  HVC_SMEM_OPT_IN((attn_bwd_kernel<HD, DROP>), L::kTotal);
   dim3 grid((a->nk + kBT - 1) / kBT, a->batch * a->heads);
   attn_bwd_kernel<HD, DROP><<<grid, kBwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, tmDO, tmDQ, ka);
   HVC_LAUNCH_CHECK();

@@ -406,11 +406,7 @@ static int launch_attn_fwd(const hvc_attn_args* a, cudaStream_t st) {
   ka.nq_pad = (a->nq + 127) / 128 * 128;
   ka.scale2 = a->scale * 1.4426950408889634f;
   ka.drop = make_drop(a->drop);
-  static bool configured = false;
-  if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DROP, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  HVC_SMEM_OPT_IN((attn_fwd_kernel<HD, DROP, EMU>), L::kTotal);
   dim3 grid((a->nq + 2 * kQTile - 1) / (2 * kQTile), a->batch * a->heads);
   attn_fwd_kernel<HD, DROP, EMU><<<grid, kFwdThreads, L::kTotal, st>>>(tmQ, tmK, tmV, ka);
   HVC_LAUNCH_CHECK();

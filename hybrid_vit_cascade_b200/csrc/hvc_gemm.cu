@@ -362,11 +362,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int A_MAJOR, int B_MAJOR, int EPI>
 static int launch_gemm_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKArgs& ka, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    HVC_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<A_MAJOR, B_MAJOR, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    configured = true;
-  }
+  HVC_SMEM_OPT_IN((gemm_bf16_kernel<A_MAJOR, B_MAJOR, EPI>), kGemmSmem);
   gemm_bf16_kernel<A_MAJOR, B_MAJOR, EPI><<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, ka);
   HVC_LAUNCH_CHECK();
   return HVC_OK;

@@ -68,6 +68,16 @@ int device_sm_count() {
   return sms[dev];
 }
 
+int smem_opt_in(const void* func, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  HVC_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (dev < 64 && (done.load(std::memory_order_acquire) & bit)) return HVC_OK;
+  HVC_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev < 64) done.fetch_or(bit, std::memory_order_release);
+  return HVC_OK;
+}
+
 }  // namespace hvc
 
 extern "C" {

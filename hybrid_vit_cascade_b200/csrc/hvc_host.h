@@ -1,6 +1,7 @@
 // hvc_host.h -- host-side helpers shared by the translation units of libhvc_sm100a.so
 // (error reporting across the C ABI, TMA tensor-map encoding, launch accounting).
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdarg.h>
@@ -48,5 +49,16 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t ro
                  uint32_t box_cols, uint32_t box_rows, int swizzle);
 
 int device_sm_count();
+
+// ---- opt-in to > 48 KB of dynamic shared memory.  cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of the
+// function: a process that touches a second GPU must set it there too.  `done` is one bit per device ordinal (a function-local
+// static std::atomic<uint64_t> at each call site); a racing second thread at worst sets the attribute twice, which is harmless.
+int smem_opt_in(const void* func, int bytes, std::atomic<uint64_t>& done);
+#define HVC_SMEM_OPT_IN(kernel, bytes)                                                  \
+  do {                                                                                  \
+    static std::atomic<uint64_t> _done{0};                                              \
+    int _r = hvc::smem_opt_in(reinterpret_cast<const void*>(kernel), (bytes), _done);   \
+    if (_r != HVC_OK) return _r;                                                        \
+  } while (0)
 
 }  // namespace hvc

@@ -70,11 +70,24 @@ def _ptr(t):
 
 
 def _need_cuda(*ts):
+    """Every tensor on one CUDA device, and that device is the CURRENT one: the kernels are launched on the current device's
+    stream (_stream()) and per-device state (shared-memory opt-in, SM count) is keyed by cudaGetDevice().  A tensor of another
+    GPU is an error, not a silent launch on the wrong device -- wrap the call in ``torch.cuda.device(t.device)``."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.HvcError("hybrid_vit_cascade_b200 kernels need CUDA tensors (there is no CPU fallback)")
-    dev = next(t for t in ts if t is not None).device
-    _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.HvcError(f"hybrid_vit_cascade_b200: operands on different devices ({dev} and {t.device})")
+    cur = torch.cuda.current_device()
+    if dev.index is not None and dev.index != cur:
+        raise _lib.HvcError(f"hybrid_vit_cascade_b200: operands live on cuda:{dev.index} but the current device is cuda:{cur}; "
+                            f"run the module under torch.cuda.device({dev.index}) (or torch.cuda.set_device)")
+    _lib.require_device(cur)
 
 
 def _row_major_2d(t, name):

@@ -171,9 +171,8 @@ class XrayConditioningModule(nn.Module):
         """xrays: (B, num_views, C, H, W); t: (B, time_embed_dim) -> (xray_context (B, cond_dim), time_xray_cond (B, cond_dim),
         xray_features_2d (B, embed_dim, H/8, W/8))"""
         B, V = xrays.shape[0], xrays.shape[1]
-        if V == 1 or self.num_views <= 1:
+        if V == 1:                             # diagnostic_losses.py:120-128: the INPUT's view count decides, not self.num_views
             x = xrays[:, 0]
-            V = 1
         else:
             x = xrays.reshape(B * V, *xrays.shape[2:])
         x = x.float().contiguous()

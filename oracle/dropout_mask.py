@@ -88,3 +88,20 @@ class DropoutOracle:
         rows = torch.arange(T, device=self.device)
         cols = torch.arange(C, device=self.device)
         return keep_mask(self.seed, site, rows, cols, self.p).to(torch.float32) * inv_keep(self.p)
+
+
+class TorchDropout:
+    """nn.Dropout(p) in train mode exactly as the reference modules apply it (torch's own generator; vit_components.py:27-29,
+    49, 55, 76-78, 110, 117; hybrid_vit_backbone.py:78, 80).  Used by the TIMED baselines (bench.py --impl reference / --impl eager),
+    where the cost of the reference's dropout matters and the masks need not match the kernels'."""
+
+    def __init__(self, p=0.1):
+        self.p = float(p)
+
+    def attn(self, site, B, H, N, M):
+        import torch.nn.functional as F
+        return lambda a: F.dropout(a, self.p, True)
+
+    def apply_tokens(self, t):
+        import torch.nn.functional as F
+        return F.dropout(t, self.p, True)

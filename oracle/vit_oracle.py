@@ -171,19 +171,28 @@ def attention_core(q: Tensor, k: Tensor, v: Tensor, scale: float,
     """
     # pmask: attn_drop (vit_components.py:49, :110) as an explicit (B,h,N,M) keep-mask already scaled by 1/(1-p);
     # None = dropout off.  The stored attention map is taken BEFORE dropout (:106-108).
+    # A callable pmask is torch's own nn.Dropout applied to the probabilities (oracle.dropout_mask.TorchDropout: the timed baselines,
+    # where the masks need not match the kernels').
     if attn_chunk is None:
         attn = (q @ k.transpose(-2, -1)) * scale
         attn = attn.softmax(dim=-1)
-        out = (attn if pmask is None else attn * pmask) @ v
+        out = (attn if pmask is None else pmask(attn) if callable(pmask) else attn * pmask) @ v
         return (out, attn) if return_probs else (out, None)
     outs = []
     for s in range(0, q.shape[2], attn_chunk):
         a = (q[:, :, s:s + attn_chunk] @ k.transpose(-2, -1)) * scale
         a = a.softmax(dim=-1)
         if pmask is not None:
-            a = a * pmask[:, :, s:s + attn_chunk]
+            a = pmask(a) if callable(pmask) else a * pmask[:, :, s:s + attn_chunk]
         outs.append(a @ v)
     return torch.cat(outs, dim=2), None
+
+
+def _drop_tokens(drop, site: int, t: Tensor) -> Tensor:
+    """proj_drop / MLP dropout on a (B, N, C) tensor: explicit kernel-matching mask, or torch's nn.Dropout (TorchDropout)."""
+    if hasattr(drop, "apply_tokens"):
+        return drop.apply_tokens(t)
+    return t * drop.tokens(site, t.shape[0] * t.shape[1], t.shape[2]).view(t.shape)
 
 
 # --------------------------------------------------------------------------
@@ -204,7 +213,7 @@ def self_attention(x: Tensor, sd: StateDict, pfx: str, num_heads: int,
     o = o.transpose(1, 2).reshape(B, N, C)                           # :51
     o = F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])  # :54
     if drop is not None:
-        o = o * drop.tokens(site + 1, B * N, C).view(B, N, C)        # :55
+        o = _drop_tokens(drop, site + 1, o)                          # :55
     return o
 
 
@@ -226,7 +235,7 @@ def cross_attention(x: Tensor, context: Tensor, sd: StateDict, pfx: str, num_hea
     o = o.transpose(1, 2).reshape(B, N, C)
     o = F.linear(o, sd[pfx + "proj.weight"], sd[pfx + "proj.bias"])                         # :116
     if drop is not None:
-        o = o * drop.tokens(site + 1, B * N, C).view(B, N, C)                               # :117
+        o = _drop_tokens(drop, site + 1, o)                                                 # :117
     return (o, probs.detach()) if return_probs else o                                       # :107-108
 
 
@@ -249,7 +258,6 @@ def block(x: Tensor, context: Tensor, cond: Tensor, sd: StateDict, pfx: str, num
     """drop/site_base: train-mode dropout as explicit masks (oracle.dropout_mask.DropoutOracle); sites site_base + 0..5 =
     self-attn probabilities, self-attn proj, cross-attn probabilities, cross-attn proj, MLP activation, MLP output."""
     C = x.shape[-1]
-    Bx, Nx = x.shape[0], x.shape[1]
     if use_prev_stage:                                                # :106-114
         if prev_stage_embed is None:
             prev_stage_embed = torch.zeros(x.shape[0], 256, device=x.device, dtype=x.dtype)
@@ -273,10 +281,10 @@ def block(x: Tensor, context: Tensor, cond: Tensor, sd: StateDict, pfx: str, num
     h = F.linear(h, sd[pfx + "mlp.0.weight"], sd[pfx + "mlp.0.bias"]) # :75-81
     h = F.gelu(h)                                                     # nn.GELU() = exact erf
     if drop is not None:
-        h = h * drop.tokens(site_base + 4, Bx * Nx, h.shape[-1]).view(h.shape)      # mlp.2
+        h = _drop_tokens(drop, site_base + 4, h)                      # mlp.2
     h = F.linear(h, sd[pfx + "mlp.3.weight"], sd[pfx + "mlp.3.bias"])
     if drop is not None:
-        h = h * drop.tokens(site_base + 5, Bx * Nx, C).view(h.shape)                # mlp.4
+        h = _drop_tokens(drop, site_base + 5, h)                      # mlp.4
     x = x + gate_mlp * h                                              # :139
     return (x, attn_map) if return_attention else x
 
