@@ -171,11 +171,14 @@ class GradientBuckets:
         self._works = []
 
     def touched(self, i):
-        """Indices (into the bucket's member list) of the parameters that received a gradient in this step."""
+        """Indices (into the bucket's member list) of the parameters that received a gradient in this step.  If no hook fired at
+        all since reset() the gradients were written into the buckets by hand (no backward ran): every member counts."""
+        if not any(self._touched):
+            return set(range(len(self._members[i])))
         return self._touched[i]
 
     def all_touched(self):
-        return all(len(t) == len(m) for t, m in zip(self._touched, self._members))
+        return all(len(self.touched(i)) == len(m) for i, m in enumerate(self._members))
 
     def remove(self):
         for h in self._hooks:

@@ -255,3 +255,37 @@ def test_flat_adamw_matches_torch_clip_and_adamw():
     opt2.step()
     y1 = lin(x).detach()
     assert O.max_rel(y1, y0) > 1e-2                               # the forward sees the new weights
+
+
+def test_flat_adamw_skips_unused_parameters_like_torch_adamw():
+    """A trainable parameter that takes no part in a step (ProgressiveCascadeModel(xrays, max_stage=1) leaves stages 2-3 unused,
+    train_progressive_4gpu.py:238) has grad None under torch: AdamW neither decays it nor touches its moments.  Its bucket slot holds
+    zeros here; FlatAdamW must skip it the same way (GradientBuckets.touched)."""
+    import hybrid_vit_cascade_b200 as hvc
+    from hybrid_vit_cascade_b200.dp import GradientBuckets
+    torch.manual_seed(5)
+    used = torch.nn.Linear(40, 24).cuda()
+    unused = torch.nn.Linear(24, 8).cuda()
+    ref_used, ref_unused = torch.nn.Linear(40, 24).cuda(), torch.nn.Linear(24, 8).cuda()
+    ref_used.load_state_dict(used.state_dict())
+    ref_unused.load_state_dict(unused.state_dict())
+    mine = list(used.parameters()) + list(unused.parameters())
+    ref = list(ref_used.parameters()) + list(ref_unused.parameters())
+    gb = GradientBuckets(mine)                                     # ONE bucket holds used and unused members
+    assert len(gb.buckets) == 1
+    opt = hvc.FlatAdamW(gb, lr=1e-2, weight_decay=0.1)
+    topt = torch.optim.AdamW(ref, lr=1e-2, weight_decay=0.1)
+    x = torch.randn(16, 40, device="cuda")
+    w_unused0 = unused.weight.detach().clone()
+    for step in range(3):
+        gb.reset()
+        topt.zero_grad(set_to_none=True)
+        used(x).square().mean().backward()
+        ref_used(x).square().mean().backward()
+        gb.finish()
+        assert gb.touched(0) == {2, 3} and not gb.all_touched()   # reverse registration order: the unused pair comes first
+        opt.step()
+        topt.step()
+    for p, r in zip(mine, ref):
+        assert O.max_rel(p.data, r.data) <= 1e-5              # three lr = 1e-2 steps on |w| ~ 0.1 weights (fast-math rsqrt in the kernel)
+    assert torch.equal(unused.weight.detach(), w_unused0)         # no weight decay on a parameter that got no gradient
