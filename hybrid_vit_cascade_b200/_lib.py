@@ -155,6 +155,8 @@ EXPORTS = [
     "hvc_im2col2d", "hvc_im2col2d_split", "hvc_col2im2d", "hvc_norm_act_fwd", "hvc_norm_act_bwd", "hvc_maxpool2d_fwd", "hvc_maxpool2d_bwd",
     "hvc_view_mean_fwd", "hvc_view_mean_bwd", "hvc_silu", "hvc_ssim_l1_fwd", "hvc_ssim_l1_bwd", "hvc_chan_dot_fwd", "hvc_chan_dot_bwd",
     "hvc_sumsq_f32", "hvc_adamw_tick", "hvc_adamw_flat",
+    "hvc_tv_fwd", "hvc_tv_finalize", "hvc_tv_bwd", "hvc_freq_l1_fwd", "hvc_freq_l1_bwd", "hvc_proj_mean_fwd", "hvc_proj_mean_bwd",
+    "hvc_l1_fwd", "hvc_l1_bwd",
 ]
 
 

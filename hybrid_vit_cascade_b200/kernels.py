@@ -777,3 +777,90 @@ def d2s_unpad_cl(src, B, D, H, W, Cc):
     out = torch.empty(B, D, H, W, Cc, device=src.device, dtype=torch.float32)
     _lib.check(_lib.lib().hvc_d2s_unpad_cl(_ptr(src), _ptr(out), B, D, H, W, Cc, _stream()), "hvc_d2s_unpad_cl")
     return out
+
+
+# ------------------------------------------------------------------ stage 2-3 loss terms (hvc_loss_multiscale.cu)
+
+def _vol_dims(x):
+    """(B, D, H, W) of a contiguous f32 volume tensor (B, 1, D, H, W) / (B, D, H, W): leading dims fold into the batch."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() >= 3
+    D, H, W = x.shape[-3:]
+    return x.numel() // (D * H * W), D, H, W
+
+
+def tv_sums(x, eps):
+    """f64[3] = sum sqrt(diff^2 + eps) along D, H, W (TotalVariationLoss, loss_multiscale.py:162-170)."""
+    _need_cuda(x)
+    sums = torch.empty(3, device=x.device, dtype=torch.float64)
+    _lib.check(_lib.lib().hvc_tv_fwd(_ptr(x), *_vol_dims(x), C.c_float(eps), _ptr(sums), _stream()), "hvc_tv_fwd")
+    return sums
+
+
+def tv_finalize(sums_pred, sums_target, dims):
+    """-> (loss f32[1], coef f32[1] = d loss / d tv_pred)."""
+    _need_cuda(sums_pred)
+    loss = torch.empty(1, device=sums_pred.device, dtype=torch.float32)
+    coef = torch.empty(1, device=sums_pred.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_tv_finalize(_ptr(sums_pred), _ptr(sums_target), *dims, _ptr(loss), _ptr(coef), _stream()), "hvc_tv_finalize")
+    return loss, coef
+
+
+def tv_bwd(x, eps, coef, upstream=None):
+    _need_cuda(x, coef)
+    dx = torch.empty_like(x)
+    _lib.check(_lib.lib().hvc_tv_bwd(_ptr(x), *_vol_dims(x), C.c_float(eps), _ptr(coef), _ptr(upstream), _ptr(dx), _stream()), "hvc_tv_bwd")
+    return dx
+
+
+def freq_l1_sums(spec_pred, spec_target):
+    """spectra complex64 [..., D, H, W] contiguous -> f64[2] = (low, high) sums of | |Fp| - |Ft| | (FrequencyLoss, :206-234)."""
+    _need_cuda(spec_pred, spec_target)
+    assert spec_pred.dtype == torch.complex64 and spec_target.dtype == torch.complex64 and spec_pred.is_contiguous() and spec_target.is_contiguous()
+    D, H, W = spec_pred.shape[-3:]
+    B = spec_pred.numel() // (D * H * W)
+    sums = torch.empty(2, device=spec_pred.device, dtype=torch.float64)
+    _lib.check(_lib.lib().hvc_freq_l1_fwd(_ptr(spec_pred), _ptr(spec_target), B, D, H, W, _ptr(sums), _stream()), "hvc_freq_l1_fwd")
+    return sums
+
+
+def freq_l1_bwd(spec_pred, spec_target, c_low, c_high, upstream=None):
+    _need_cuda(spec_pred, spec_target)
+    D, H, W = spec_pred.shape[-3:]
+    B = spec_pred.numel() // (D * H * W)
+    g = torch.empty_like(spec_pred)
+    _lib.check(_lib.lib().hvc_freq_l1_bwd(_ptr(spec_pred), _ptr(spec_target), B, D, H, W, C.c_float(c_low), C.c_float(c_high), _ptr(upstream),
+                                          _ptr(g), _stream()), "hvc_freq_l1_bwd")
+    return g
+
+
+def proj_mean_fwd(vol):
+    """vol f32 (B, 1, D, H, W) -> ap (B, H, W) = mean over D, lat (B, D, H) = mean over W (DRRReprojectionLoss.generate_drr, :249-265)."""
+    _need_cuda(vol)
+    B, D, H, W = _vol_dims(vol)
+    ap = torch.empty(B, H, W, device=vol.device, dtype=torch.float32)
+    lat = torch.empty(B, D, H, device=vol.device, dtype=torch.float32)
+    _lib.check(_lib.lib().hvc_proj_mean_fwd(_ptr(vol), B, D, H, W, _ptr(ap), _ptr(lat), _stream()), "hvc_proj_mean_fwd")
+    return ap, lat
+
+
+def proj_mean_bwd(dap, dlat, shape):
+    _need_cuda(dap, dlat)
+    dvol = torch.empty(shape, device=dap.device, dtype=torch.float32)
+    B, D, H, W = _vol_dims(dvol)
+    _lib.check(_lib.lib().hvc_proj_mean_bwd(_ptr(dap), _ptr(dlat), B, D, H, W, _ptr(dvol), _stream()), "hvc_proj_mean_bwd")
+    return dvol
+
+
+def l1_sum(a, b):
+    _need_cuda(a, b)
+    assert a.dtype == b.dtype == torch.float32 and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    s = torch.empty(1, device=a.device, dtype=torch.float64)
+    _lib.check(_lib.lib().hvc_l1_fwd(_ptr(a), _ptr(b), C.c_int64(a.numel()), _ptr(s), _stream()), "hvc_l1_fwd")
+    return s
+
+
+def l1_bwd(a, b, c, upstream=None):
+    _need_cuda(a, b)
+    da = torch.empty_like(a)
+    _lib.check(_lib.lib().hvc_l1_bwd(_ptr(a), _ptr(b), C.c_int64(a.numel()), C.c_float(c), _ptr(upstream), _ptr(da), _stream()), "hvc_l1_bwd")
+    return da

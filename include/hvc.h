@@ -388,6 +388,31 @@ int hvc_ssim_l1_bwd(const float* pred, const float* target, const float* filtere
                     int32_t window, float c_ssim, float c_l1, const float* upstream, float* scratch, float* dpred, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Stage 2-3 loss terms of the progressive cascade (direct_regression/progressive_cascade/loss_multiscale.py).
+ * Volumes are f32 [B, D, H, W] contiguous; sums are f64 device accumulators (zeroed by the call); `upstream` = one f32 in device memory
+ * (gradient of the scalar loss; NULL = 1), so no value crosses to the host.
+ *   TotalVariationLoss (:140-188): hvc_tv_fwd -> sums[3] = sum sqrt(diff^2 + eps) along D, H, W; hvc_tv_finalize -> loss[0] = clamp(tv, 0, 100)
+ *     (sums_target == NULL) or |tv_pred - tv_target|, coef[0] = d loss / d tv_pred; hvc_tv_bwd -> dx.
+ *   FrequencyLoss (:191-236): spectra = interleaved complex64 [B, D, H, W] from the library FFT (torch.fft.fftn); hvc_freq_l1_fwd ->
+ *     sums[2] = sum | |Fp| - |Ft| | over the low / high-frequency sets (mask built on the unshifted spectrum exactly as :214-229);
+ *     hvc_freq_l1_bwd -> dspec (complex64) = upstream * (c_low | c_high) * sign(|Fp| - |Ft|) * Fp / |Fp|.
+ *   DRRReprojectionLoss (:239-293): hvc_proj_mean_fwd -> ap [B, H, W] = mean over D, lat [B, D, H] = mean over W; hvc_proj_mean_bwd is
+ *     the adjoint; the bilinear resize is hvc_interp3d_* with unit depth; hvc_l1_fwd / hvc_l1_bwd = F.l1_loss sums and gradient.
+ * ---------------------------------------------------------------------------------------------- */
+int hvc_tv_fwd(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, float eps, double* sums, void* stream);
+int hvc_tv_finalize(const double* sums_pred, const double* sums_target, int32_t B, int32_t D, int32_t H, int32_t W, float* loss, float* coef,
+                    void* stream);
+int hvc_tv_bwd(const float* x, int32_t B, int32_t D, int32_t H, int32_t W, float eps, const float* coef, const float* upstream, float* dx,
+               void* stream);
+int hvc_freq_l1_fwd(const float* spec_pred, const float* spec_target, int32_t B, int32_t D, int32_t H, int32_t W, double* sums, void* stream);
+int hvc_freq_l1_bwd(const float* spec_pred, const float* spec_target, int32_t B, int32_t D, int32_t H, int32_t W, float c_low, float c_high,
+                    const float* upstream, float* dspec, void* stream);
+int hvc_proj_mean_fwd(const float* vol, int32_t B, int32_t D, int32_t H, int32_t W, float* ap, float* lat, void* stream);
+int hvc_proj_mean_bwd(const float* dap, const float* dlat, int32_t B, int32_t D, int32_t H, int32_t W, float* dvol, void* stream);
+int hvc_l1_fwd(const float* a, const float* b, int64_t n, double* sum, void* stream);
+int hvc_l1_bwd(const float* a, const float* b, int64_t n, float c, const float* upstream, float* da, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer step on flat fp32 buffers: torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step() of the
  * reference trainers (train_direct_4gpu.py:72-80) over the data-parallel gradient buckets.
  *   hvc_sumsq_f32:  accum[0] += sum x^2 (double; zero it first, call once per bucket)
