@@ -48,7 +48,7 @@ def flat_to_torch_state(opt, params: Iterable[torch.nn.Parameter]) -> dict:
     for bi, (members, offsets) in enumerate(zip(opt.gb._members, opt.gb._offsets)):
         for p, off in zip(members, offsets):
             where[id(p)] = (bi, off)
-    step = opt.state.detach().clone().reshape(())
+    step = opt.t.detach().clone().reshape(())
     state = {}
     for i, p in enumerate(params):
         if id(p) not in where:
@@ -61,8 +61,10 @@ def flat_to_torch_state(opt, params: Iterable[torch.nn.Parameter]) -> dict:
                     "exp_avg": opt.exp_avg[bi][off:off + n].view_as(p).clone(),
                     "exp_avg_sq": opt.exp_avg_sq[bi][off:off + n].view_as(p).clone()}
     group = {"lr": opt.lr, "betas": tuple(opt.betas), "eps": opt.eps, "weight_decay": opt.weight_decay, "amsgrad": False, "maximize": False,
-             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": True,
-             "params": list(range(len(params)))}
+             "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": True}
+    if "initial_lr" in opt.param_groups[0]:              # written by an attached LR scheduler, as in the reference's files
+        group["initial_lr"] = opt.param_groups[0]["initial_lr"]
+    group["params"] = list(range(len(params)))
     return {"state": state, "param_groups": [group]}
 
 
@@ -89,9 +91,11 @@ def torch_to_flat_state(opt, torch_state: dict, params: Iterable[torch.nn.Parame
                 steps.add(float(st["step"]))
         if len(steps) > 1:
             raise ValueError(f"FlatAdamW keeps one step count; the checkpoint holds several ({sorted(steps)})")
-        opt.state.fill_(steps.pop() if steps else 0.0)
+        opt.t.fill_(steps.pop() if steps else 0.0)
     g = torch_state["param_groups"][0]
     opt.lr, opt.betas, opt.eps, opt.weight_decay = g["lr"], tuple(g["betas"]), g["eps"], g["weight_decay"]
+    if "initial_lr" in g:
+        opt.param_groups[0]["initial_lr"] = g["initial_lr"]
 
 
 def _is_flat(opt) -> bool:
@@ -106,8 +110,8 @@ def save_checkpoint(path, model, optimizer=None, scheduler=None, epoch=0, config
     m = unwrap(model)
     ckpt = {"epoch": epoch, "model_state_dict": m.state_dict()}
     if optimizer is not None:
-        ckpt["optimizer_state_dict"] = (flat_to_torch_state(optimizer, optimizer_params if optimizer_params is not None else m.parameters())
-                                        if _is_flat(optimizer) else optimizer.state_dict())
+        ckpt["optimizer_state_dict"] = (flat_to_torch_state(optimizer, optimizer_params) if _is_flat(optimizer) and optimizer_params is not None
+                                        else optimizer.state_dict())
     if scheduler is not None:
         ckpt["scheduler_state_dict"] = scheduler.state_dict()
     ckpt.update(metrics)
@@ -125,10 +129,10 @@ def load_checkpoint(path_or_dict, model, optimizer=None, scheduler=None, strict=
     result = m.load_state_dict(strip_module_prefix(ckpt["model_state_dict"]), strict=strict)
     _after_weight_load()
     if optimizer is not None and "optimizer_state_dict" in ckpt:
-        if _is_flat(optimizer):
-            torch_to_flat_state(optimizer, ckpt["optimizer_state_dict"], optimizer_params if optimizer_params is not None else m.parameters())
+        if _is_flat(optimizer) and optimizer_params is not None:
+            torch_to_flat_state(optimizer, ckpt["optimizer_state_dict"], optimizer_params)
         else:
-            optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+            optimizer.load_state_dict(ckpt["optimizer_state_dict"])      # FlatAdamW speaks the torch.optim.AdamW layout itself
     if scheduler is not None and "scheduler_state_dict" in ckpt:
         scheduler.load_state_dict(ckpt["scheduler_state_dict"])
     start_epoch = ckpt.get("epoch", 0) + 1

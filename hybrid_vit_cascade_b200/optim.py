@@ -15,10 +15,19 @@ from . import _lib, ops
 from .kernels import _need_cuda, _ptr, _stream
 
 
-class FlatAdamW:
-    def __init__(self, buckets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=0.0):
+class FlatAdamW(torch.optim.Optimizer):
+    """A ``torch.optim.Optimizer`` (so ``CosineAnnealingLR`` and friends drive its learning rate, train_direct_4gpu.py:165-168) whose
+    ``state_dict()`` / ``load_state_dict()`` speak the ``torch.optim.AdamW`` layout: a checkpoint written through it resumes in the
+    reference trainer and vice versa (checkpoint.flat_to_torch_state / torch_to_flat_state).  `params`: the parameter list a torch
+    optimizer would have been built from, in order (default: the bucketed parameters in registration order; pass
+    ``model.parameters()`` when some are frozen so that the state indices match the reference's)."""
+
+    def __init__(self, buckets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_grad_norm=0.0, params=None):
         self.gb = buckets
-        self.lr, self.betas, self.eps, self.weight_decay, self.max_grad_norm = lr, betas, eps, weight_decay, max_grad_norm
+        order = list(params) if params is not None else list(reversed([p for m in buckets._members for p in m]))
+        super().__init__(order, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._order = order
+        self.max_grad_norm = max_grad_norm
         self.params, self.exp_avg, self.exp_avg_sq = [], [], []
         for flat_g, members, offsets in zip(buckets.buckets, buckets._members, buckets._offsets):
             _need_cuda(flat_g)
@@ -33,15 +42,26 @@ class FlatAdamW:
             self.exp_avg.append(torch.zeros_like(flat_g))
             self.exp_avg_sq.append(torch.zeros_like(flat_g))
         dev = buckets.buckets[0].device
-        self.state = torch.zeros(1, device=dev, dtype=torch.float32)        # step count t
+        self.t = torch.zeros(1, device=dev, dtype=torch.float32)            # step count t (on the device: graph-capturable)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)        # ||g||^2 over all buckets
         ops.clear_weight_cache()
 
+    # hyper-parameters live in param_groups[0] (where torch's LR schedulers write them)
+    lr = property(lambda self: self.param_groups[0]["lr"], lambda self, v: self.param_groups[0].__setitem__("lr", v))
+    betas = property(lambda self: self.param_groups[0]["betas"], lambda self, v: self.param_groups[0].__setitem__("betas", v))
+    eps = property(lambda self: self.param_groups[0]["eps"], lambda self, v: self.param_groups[0].__setitem__("eps", v))
+    weight_decay = property(lambda self: self.param_groups[0]["weight_decay"], lambda self, v: self.param_groups[0].__setitem__("weight_decay", v))
+
+    def zero_grad(self, set_to_none=False):
+        """The gradients ARE the buckets: zero them in place and re-arm the all-reduce counters (never detach p.grad)."""
+        self.gb.reset()
+
     @torch.no_grad()
-    def step(self):
+    def step(self, closure=None):
         """Clip (global L2 norm over all bucketed gradients, as clip_grad_norm_) + AdamW.  Call after GradientBuckets.finish()."""
+        assert closure is None, "FlatAdamW does not re-evaluate the model"
         lib, st = _lib.lib(), _stream()
-        _lib.check(lib.hvc_adamw_tick(_ptr(self.state), st), "hvc_adamw_tick")
+        _lib.check(lib.hvc_adamw_tick(_ptr(self.t), st), "hvc_adamw_tick")
         clip = self.max_grad_norm > 0
         if clip:
             self.sumsq.zero_()
@@ -52,7 +72,7 @@ class FlatAdamW:
         def tick(pt, gt, mt, vt):
             _lib.check(lib.hvc_adamw_flat(_ptr(pt), _ptr(gt), _ptr(mt), _ptr(vt), C.c_int64(pt.numel()), f(self.lr), f(self.betas[0]),
                                           f(self.betas[1]), f(self.eps), f(self.weight_decay), f(self.max_grad_norm if clip else 0.0),
-                                          _ptr(self.sumsq), _ptr(self.state), st), "hvc_adamw_flat")
+                                          _ptr(self.sumsq), _ptr(self.t), st), "hvc_adamw_flat")
 
         for i, (p, g, m, v) in enumerate(zip(self.params, self.gb.buckets, self.exp_avg, self.exp_avg_sq)):
             members, offsets, got = self.gb._members[i], self.gb._offsets[i], self.gb.touched(i)
@@ -71,12 +91,10 @@ class FlatAdamW:
         return self.sumsq.sqrt()
 
     def state_dict(self):
-        return {"step": self.state.clone(), "exp_avg": [t.clone() for t in self.exp_avg], "exp_avg_sq": [t.clone() for t in self.exp_avg_sq],
-                "hyper": dict(lr=self.lr, betas=self.betas, eps=self.eps, weight_decay=self.weight_decay, max_grad_norm=self.max_grad_norm)}
+        """The ``torch.optim.AdamW`` layout (per-parameter step / exp_avg / exp_avg_sq, indexed by position in the parameter list)."""
+        from .checkpoint import flat_to_torch_state
+        return flat_to_torch_state(self, self._order)
 
     def load_state_dict(self, sd):
-        self.state.copy_(sd["step"])
-        for dst, src in zip(self.exp_avg, sd["exp_avg"]):
-            dst.copy_(src)
-        for dst, src in zip(self.exp_avg_sq, sd["exp_avg_sq"]):
-            dst.copy_(src)
+        from .checkpoint import torch_to_flat_state
+        torch_to_flat_state(self, sd, self._order)

@@ -95,7 +95,15 @@ def test_stage_losses_at_cascade_resolution_properties():
     assert float((b - a - 0.25).abs().max()) < 1e-5
     loss = drr(p, xr)
     loss.backward()
-    assert torch.isfinite(p.grad).all() and abs(float(p.grad.abs().sum()) - 1.0) < 1e-3      # sum |dL/dvol| = (1/2)(1 + 1): every pixel has unit-sum weights
+    assert torch.isfinite(p.grad).all()
+    # directional derivative: the loss is piecewise linear in the volume, so a central difference along a random direction matches <grad, d>
+    # up to the few pixels whose residual changes sign inside the step
+    d = torch.randn(t.shape, device="cuda", generator=g)
+    eps = 1e-2
+    with torch.no_grad():
+        fd = (float(drr(t + eps * d, xr)) - float(drr(t - eps * d, xr))) / (2 * eps)
+    an = float((p.grad * d).sum())
+    assert abs(fd - an) <= 0.05 * max(abs(an), 1e-6) + 1e-6, (fd, an)
 
 
 def test_checkpoint_roundtrip_reference_format_both_optimizers(tmp_path):

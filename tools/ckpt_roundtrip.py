@@ -92,10 +92,12 @@ class OracleTrainer:
         return float(loss)
 
     def checkpoint(self, epoch=3):
-        """The dict of train_direct_4gpu.py:277-287."""
+        """The dict of train_direct_4gpu.py:277-287.  torch.save serialises the optimizer's tensors at this moment; an in-memory dict must
+        copy them, state_dict() hands out references that the next step() mutates."""
+        import copy
         return {"epoch": epoch, "model_state_dict": {k: v.detach().clone() for k, v in self.sd.items()},
-                "optimizer_state_dict": self.opt.state_dict(), "scheduler_state_dict": self.sched.state_dict(), "val_psnr": 21.5,
-                "best_psnr": 21.5, "config": CONFIG}
+                "optimizer_state_dict": copy.deepcopy(self.opt.state_dict()), "scheduler_state_dict": copy.deepcopy(self.sched.state_dict()),
+                "val_psnr": 21.5, "best_psnr": 21.5, "config": CONFIG}
 
 
 def check_layout(ckpt):
@@ -129,11 +131,11 @@ class HvcRun:
         self.params = list(self.model.parameters())
         self.gb = GradientBuckets(self.params)
         if backend == "flat":
-            self.opt = hvc.FlatAdamW(self.gb, lr=tc["learning_rate"], weight_decay=tc["weight_decay"], max_grad_norm=tc["gradient_clip"])
-            self.sched = None
+            self.opt = hvc.FlatAdamW(self.gb, lr=tc["learning_rate"], weight_decay=tc["weight_decay"], max_grad_norm=tc["gradient_clip"],
+                                     params=self.params)
         else:
             self.opt = torch.optim.AdamW(self.params, lr=tc["learning_rate"], weight_decay=tc["weight_decay"])
-            self.sched = torch.optim.lr_scheduler.CosineAnnealingLR(self.opt, T_max=tc["num_epochs"])
+        self.sched = torch.optim.lr_scheduler.CosineAnnealingLR(self.opt, T_max=tc["num_epochs"])      # either backend is a torch Optimizer
         self.start_epoch, self.best, _ = CK.load_checkpoint(ckpt, self.model, self.opt, self.sched, strict=True, map_location=dev)
         self.clip = tc["gradient_clip"]
         self.xrays, self.target = xrays.to(dev), target.to(dev)
