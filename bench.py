@@ -366,6 +366,8 @@ def run_b200(args, w):
     def step(feat_, cond_, target_):
         gb.reset()
         if full:
+            if world > 1:
+                gb.broadcast_buffers(model)          # DDP(broadcast_buffers=True), train_direct_4gpu.py:146: BatchNorm running stats follow rank 0
             out = model(feat_)
             loss = loss_fn(out, target_)
             loss.backward()
@@ -424,12 +426,12 @@ def run_b200(args, w):
     prof = {}
     K.set_profiler(prof)
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()                       # every rank samples its own GPU (per_rank evidence); rank 0's goes into "clocks"
     l0 = _lib.launch_count()
     ms_total = timed(lambda: step(feat, cond, target), args.steps)
     launches = _lib.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else {}
+    local_clocks = sampler.stop()
+    clocks = local_clocks if rank == 0 else {}
     K.set_profiler(None)
     torch.cuda.synchronize()
     kern = {}
@@ -446,8 +448,8 @@ def run_b200(args, w):
     # host-side launch gaps that dominate the small 64^3 configuration (225 kernel launches in ~11 ms)
     graph_info = None
     if args.graph:
-        if world > 1:
-            raise SystemExit("--graph is a single-GPU measurement (the NCCL bucket hooks are not captured)")
+        # N > 1: the bucket all-reduces are issued from the gradient hooks while the backward is being captured; NCCL collectives are
+        # capturable, so they become nodes of the same graph (on the communicator's stream, joined back by finish()'s stream wait)
         s_feat, s_cond, s_target = feat.clone(), cond.clone(), target.clone()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -457,7 +459,7 @@ def run_b200(args, w):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         cg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cg):
+        with torch.cuda.graph(cg, capture_error_mode="thread_local" if world > 1 else "global"):
             s_loss = step(s_feat, s_cond, s_target)
 
         def step(f, c, t, _eager=step):                      # noqa: F811  (replaces the eager step from here on)
@@ -504,9 +506,34 @@ def run_b200(args, w):
         bo = [z for z in bo if z[1] == bo[0][1]] if bo else []
         off = {"ms_per_step": ms_off / args.steps, "attn_bwd_tflops": (sum(f for _, f in bo) / (sum(t for t, _ in bo) * 1e9)) if bo else None}
 
+    # per-rank evidence for the scaling numbers: every rank's own device time in the hot kernels and its SM clock under load.  The step
+    # time is the MAX over ranks and the ranks meet in every all-reduce, so the slowest GPU of the box (power-capped clocks differ by a
+    # few per cent between the GPUs of one box) sets the pace of all of them.
+    per_rank = None
+    if world > 1:
+        mine = torch.tensor([sum(v["ms_total"] for v in kern.values()) / args.steps, kern.get("attn_bwd", {}).get("ms_total", 0.0) / args.steps,
+                             float(local_clocks.get("sm_mhz") or 0.0)], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"hot_kernel_ms_per_step": [round(float(t[0]), 3) for t in allr], "attn_bwd_ms_per_step": [round(float(t[1]), 3) for t in allr],
+                    "sm_mhz_median": [float(t[2]) for t in allr],
+                    "note": "device time of this rank's own gemm + attention launches (CUDA events on its stream) and its SM clock; "
+                            "ms_per_step is the max over ranks"}
+    def teardown():
+        if world == 1:
+            return
+        if args.graph:
+            # tearing down a communicator whose collectives live in an instantiated CUDA graph blocks in this torch/NCCL build (measured:
+            # the run printed its line and then hung in destroy_process_group); leave together and let the process exit release it
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown()
         return
     peaks = {}
     try:
@@ -555,6 +582,8 @@ def run_b200(args, w):
                                "roofline_achieved": off["attn_bwd_tflops"],
                                "roofline_frac": off["attn_bwd_tflops"] / peak_tf if off["attn_bwd_tflops"] else None,
                                "note": "same step, nn.Dropout sites skipped (the mode the parity tests and the CPU arm run in)"}
+    if per_rank:
+        line["per_rank"] = per_rank
     if graph_info:
         line["cuda_graph"] = graph_info
         line["config"]["step_launch"] = "one CUDA graph per step (value, e2e); roofline / kernels / clocks from the eager run before it"
@@ -571,8 +600,7 @@ def run_b200(args, w):
         except Exception as e:      # pragma: no cover
             line["eager_b200"] = {"error": str(e)[:300]}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():
@@ -588,7 +616,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--loss", default="direct", choices=["l1", "direct"],
                     help="direct (default) = DirectRegressionLoss L1 + 0.5 (1 - SSIM3D) on the package's loss kernels (config_direct.json); l1 = plain L1")
-    ap.add_argument("--graph", action="store_true", help="capture the training step in a CUDA graph and time its replay (N=1)")
+    ap.add_argument("--graph", action="store_true", help="capture the training step (incl. the bucket all-reduces at N > 1) in a CUDA graph and time its replay")
     ap.add_argument("--dropout", default="on", choices=["on", "off"],
                     help="train-mode nn.Dropout(p=0.1) of the six sites per block, as the reference trainers run (masks regenerated inside "
                          "the kernels); 'on' also reports the dropout-off step as line['dropout_off']")

@@ -31,15 +31,25 @@
 //        straight from registers needs no staging but hits the L2 atomic rate (600 vs 794 TFLOP/s at d=64, B=8).
 //      * dQ tiles are staged for the TMA reduce in the dS^T sub-tile that the same warpgroup wrote two tiles earlier
 //        and dK/dQ have released, which is what lets three Q/dO stages and two dS^T buffers fit in shared memory.
+//      * round 2: dQ(i) is drained by its OWN warpgroup (TMEM -> registers -> swizzled staging tile -> TMA reduce-add).  In round 1 each
+//        elementwise warpgroup drained its half of dQ(i-1) after phase B(i): ~380 clk waiting for the dQ product plus ~470 clk of drain sat
+//        on the serial path of every tile (profiles/r01_attn_bwd_timeline_d64_v5.log).  Upper bound measured by dropping the drain
+//        altogether: 793 -> 933 TFLOP/s at d = 64 (646 -> 786 with dropout), profiles/r02_attn_bwd_nodrain_bound.log.  The block grows to
+//        512 threads; setmaxnreg moves registers from the drain / TMA / MMA warps to the elementwise warpgroups (168 each).
 //      TMEM is used to the last column (S^T 128 | P^T 64 | dP^T 128 | dV d | dK d | dQ d).
 //   attn_dq_convert_kernel   dq_accum (f32, per head) * scale -> dq (bf16, packed token-major)
+#define HVC_WAIT_INLINE 1      // no device function calls in this translation unit: see mbar_wait_slow
 #include "hvc_common.cuh"
 #include "hvc_host.h"
 
 namespace hvc {
 
 constexpr int kBwdWGs = 2;                        // elementwise warpgroups
-constexpr int kBwdThreads = kBwdWGs * 128 + 64;   // + TMA warp (8) + MMA warp (9)
+// warps 0-7: elementwise warpgroups; 8-11: dQ drain warpgroup; 12: TMA; 13: MMA; 14-15: idle (setmaxnreg works on whole warpgroups)
+constexpr int kBwdThreads = 512;
+// Register budget: the block launches with 65536 / 512 = 128 registers per thread; the drain warpgroup and the TMA / MMA warpgroup give
+// registers back (setmaxnreg.dec), the elementwise warpgroups take them (setmaxnreg.inc): 128*64 + 128*104 + 256*168 = 64512.
+constexpr int kRegsAux = 64, kRegsDrain = 104, kRegsEw = 168;
 constexpr int kBT = 128;                          // tile edge (queries and keys)
 constexpr int kQStages = 3;
 constexpr int kWgCols = kBT / kBwdWGs;            // query columns per warpgroup (64)
@@ -62,6 +72,7 @@ struct AttnBwdKArgs {
   bf16* dk; long long lddk;
   bf16* dv; long long lddv;
   float scale, scale2;
+  float* dq_accum;           // [B, H, nq_pad, HD] f32 (HVC_BWD_DQ_RED variant only)
   const uint32_t* rowkeys;   // [B, H, nq_pad] dropout row keys (DROP instantiations; written by the pre-pass)
   DropArg drop;
 };
@@ -75,15 +86,17 @@ struct BwdSmem {
   static constexpr int kQ = 2 * kTile;
   static constexpr int kDS = kQ + kQStages * kQStage;        // 2 x [128 keys x 128 queries] bf16 (two 64-query sub-tiles each);
   static constexpr int kDSBuf = kBT * kBT * 2;               //   also: K/V landing zone at start, dQ staging when released
-  static constexpr int kBar = kDS + 2 * kDSBuf;
+  static constexpr int kDQStage = kDS + 2 * kDSBuf;            // dQ staging of the drain warpgroup: 128 queries x HD/2 columns f32
+  static constexpr int kDQStageBytes = kBT * (HD / 2) * 4;
+  static constexpr int kBar = kDQStage + kDQStageBytes;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
 // mbarriers; the ones marked [2] exist once per column half (warpgroup)
 enum { BB_KV = 0, BB_KT = 1, BB_QF = 2, BB_QE = 5, BB_ST = 8 /*[2]*/, BB_STFREE = 10 /*[2]*/, BB_PT = 12 /*[2]*/, BB_DPT = 14 /*[2]*/,
-       BB_DS = 16 /*[2]*/, BB_DQF = 18, BB_DQFREE = 19, BB_N = 20 };
-// named barriers: 1 + x = warpgroup x (drain / staging), 3 + x = warpgroup x's turn on the exp unit
-enum { NB_WG = 1, NB_TURN = 3 };
+       BB_DS = 16 /*[2]*/, BB_DQF = 18, BB_DQFREE = 19, BB_DONE = 20, BB_N = 21 };
+// named barriers: 1 = the drain warpgroup, 3 + x = elementwise warpgroup x's turn on the exp unit
+enum { NB_DRAIN = 1, NB_TURN = 3 };
 
 // In-kernel timeline: SM-clock stamps of CTA (0,0) at the protocol points of iterations [kTraceI0, kTraceI0+8) for the two
 // warpgroups (roles 0-1) and the MMA warp (role 2), written when tracing is switched on (hvc_debug_bwd_trace_enable;
@@ -135,10 +148,10 @@ __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[kWgCols], uint3
       }
       if (DROP) {
         const uint4 rk = lds_u4(rk_saddr + t * 4);
-        e0.x = (rk.x ^ colkey) * kDropMix >= thr ? e0.x : -e0.x;
-        e0.y = (rk.y ^ colkey) * kDropMix >= thr ? e0.y : -e0.y;
-        e1.x = (rk.z ^ colkey) * kDropMix >= thr ? e1.x : -e1.x;
-        e1.y = (rk.w ^ colkey) * kDropMix >= thr ? e1.y : -e1.y;
+        e0.x = drop_negate_if_dropped(e0.x, rk.x * colkey, thr);      // colkey = this thread's column multiplier: one multiply per element
+        e0.y = drop_negate_if_dropped(e0.y, rk.y * colkey, thr);
+        e1.x = drop_negate_if_dropped(e1.x, rk.z * colkey, thr);
+        e1.y = drop_negate_if_dropped(e1.y, rk.w * colkey, thr);
       }
       pv[t >> 1] = e0;
       pv[(t >> 1) + 1] = e1;
@@ -220,14 +233,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + BB_N);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);   // warp-uniform for the compiler (role dispatch, setmaxnreg)
   const int lane = threadIdx.x & 31;
   const int bh = blockIdx.y;
   const int b = bh / p.heads, h = bh - b * p.heads;
   const int j = blockIdx.x;           // key tile
   const int nQ = p.n_q_tiles;
   const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && *reinterpret_cast<volatile int*>(&g_bwd_trace_on) != 0;
-  constexpr int kTmaWarp = kBwdWGs * 4, kMmaWarp = kBwdWGs * 4 + 1;
+  constexpr int kDrainWarp0 = kBwdWGs * 4, kTmaWarp = kDrainWarp0 + 4, kMmaWarp = kTmaWarp + 1;
   constexpr uint32_t kEw = kBwdWGs * 4;     // elementwise warps: one mbarrier arrival per warp on the joint barriers
 
   if (threadIdx.x == 0) {
@@ -243,7 +256,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&bar[BB_DS + x], 4);
     }
     mbar_init(&bar[BB_DQF], 1);
-    mbar_init(&bar[BB_DQFREE], kEw);
+    mbar_init(&bar[BB_DQFREE], 4);          // one arrival per drain warp
+    mbar_init(&bar[BB_DONE], 1);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, 512);
@@ -255,8 +269,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr uint32_t kSubKT = HD * 128;     // one 64-key sub-tile of K^T / V^T: HD rows of 128 bytes
   constexpr uint32_t kHalfRows = 64 * HD * 2;   // byte offset of row 64 inside a Q / dO tile (a whole number of swizzle atoms)
 
+  // setmaxnreg sits INSIDE each role's branch: after a control-flow merge ptxas must assume the smallest budget of the merging paths
   if (warp == kTmaWarp) {
     // ===================== TMA producer =====================
+    reg_dealloc<kRegsAux>();
     if (elect_one()) {
       mbar_arrive_expect_tx(&bar[BB_KV], 2 * L::kTile);     // K, V land in the (still unused) dS^T buffers
       tma_load_2d(smem + L::kDS, &tmK, &bar[BB_KV], h * HD, b * p.nk + j * kBT, kEvictFirst);
@@ -276,6 +292,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (whole warp runs the loop; only the elected lane issues) =====================
+    reg_dealloc<kRegsAux>();
     // Warpgroup 1 runs about half a tile behind warpgroup 0 (they alternate on the exp unit), and the issue order below
     // follows the order in which their results become available:
     //   dS_1(i-1) | P_0(i) | STFREE_0+1(i) | dS_0(i) | P_1(i)
@@ -397,8 +414,60 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_dv(1, st, false);
     }
     finish_tile(nQ - 1);
-  } else {
+    commit(BB_DONE);        // every product issued: dV and dK are complete when this fires
+  } else if (warp >= kDrainWarp0 && warp < kTmaWarp) {
+    // ===================== dQ drain warpgroup: thread == query row of the tile =====================
+    reg_dealloc<kRegsDrain>();
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool lead = threadIdx.x == kDrainWarp0 * 32;
+    const uint32_t stage = smem_u32(smem + L::kDQStage);
+    for (int i = 0; i < nQ; ++i) {
+      mbar_wait(&bar[BB_DQF], i & 1, 31);
+      tc_fence_after();
+      uint32_t v[HD];
+      if constexpr (HD == 64) {
+        uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+        uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+        tmem_ld_32x32(tmem_base + lane_base + kColDQ, v0);
+        tmem_ld_32x32(tmem_base + lane_base + kColDQ + 32, v1);
+      } else {
+        tmem_ld_32x32(tmem_base + lane_base + kColDQ, v);
+      }
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive_warp(&bar[BB_DQFREE]);              // the next dQ product may overwrite the accumulator
+#ifdef HVC_BWD_DQ_RED
+      {   // variant: L2 reductions straight from registers (no staging tile, no TMA)
+        float* dst = p.dq_accum + ((long long)bh * p.nq_pad + i * kBT + r) * HD;
+#pragma unroll
+        for (int k = 0; k < HD / 4; ++k)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * k), "f"(__uint_as_float(v[4 * k])), "f"(__uint_as_float(v[4 * k + 1])),
+                       "f"(__uint_as_float(v[4 * k + 2])), "f"(__uint_as_float(v[4 * k + 3])) : "memory");
+      }
+#else
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (lead) bulk_wait_read<0>();                // the previous reduce has finished reading the staging tile
+        named_bar_sync(NB_DRAIN, 128);
+#pragma unroll
+        for (int k = 0; k < kDCols / 4; ++k)
+          sts_u4(stage + swz_offset<kDCols * 4>(r, k), v[half * kDCols + 4 * k], v[half * kDCols + 4 * k + 1], v[half * kDCols + 4 * k + 2],
+                 v[half * kDCols + 4 * k + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(NB_DRAIN, 128);
+        if (lead) {
+          tma_reduce_add_2d(&tmDQ, smem + L::kDQStage, half * kDCols, bh * p.nq_pad + i * kBT);
+          bulk_commit();
+        }
+      }
+#endif
+    }
+    if (lead) bulk_wait<0>();
+  } else if (warp < kDrainWarp0) {
     // ===================== elementwise warpgroups: thread == key row, warpgroup x == query columns [64x, 64x+64) =====================
+    reg_alloc<kRegsEw>();
     const int wg = warp >> 2;
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
@@ -435,35 +504,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive_warp(&bar[BB_KT]);
     }
 
-    // dQ(i) drain: TMEM -> registers -> swizzled staging tile -> TMA reduce-add.  The staging tile is sub-tile `wg` of the
-    // dS^T buffer (i & 1), which dK/dQ(i) have released and which this same warpgroup rewrites in phase B(i+2).
-    auto drain_dq = [&](int i) {
-      mbar_wait(&bar[BB_DQF], i & 1, 31);
-      tc_fence_after();
-      if (wg_lead) HVC_TR(wg, i + 1, 8);
-      uint32_t v[kDCols];
-      if constexpr (HD == 64) tmem_ld_32x32(tmem_base + lane_base + kColDQ + wg * kDCols, v);   // lane = query row of tile i,
-      else                    tmem_ld_32x16(tmem_base + lane_base + kColDQ + wg * kDCols, v);   // this warpgroup's half of the d columns
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_warp(&bar[BB_DQFREE]);
-      const uint32_t stage_off = L::kDS + (i & 1) * L::kDSBuf + wg * 16384;
-      const uint32_t stage = smem_u32(smem + stage_off);
-#pragma unroll
-      for (int k = 0; k < kDCols / 4; ++k) sts_u4(stage + swz_offset<kDCols * 4>(r, k), v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-      fence_proxy_async_smem();
-      named_bar_sync(NB_WG + wg, 128);
-      if (wg_lead) {
-        tma_reduce_add_2d(&tmDQ, smem + stage_off, wg * kDCols, bh * p.nq_pad + i * kBT);
-        bulk_commit();
-      }
-    };
-
     const float2 nss = make_float2(scale2, scale2);
     uint32_t colkey = 0, thr = 0;
     float inv_keep = 1.f;
     if (DROP) {
-      colkey = drop_colterm(static_cast<uint32_t>(j * kBT + r));
+      colkey = drop_colmul(static_cast<uint32_t>(j * kBT + r));
       thr = p.drop.thr;
       inv_keep = p.drop.inv_keep;
     }
@@ -517,9 +562,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t(&d1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&dv[32]);
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * kWgCols, d0);
         tmem_ld_32x32(tmem_base + lane_base + kColDPt + wg * kWgCols + 32, d1);
-        // the sub-tile held this warpgroup's dQ(i-2) staging tile: its reduce must have finished reading it
-        if (wg_lead) bulk_wait_read<0>();
-        named_bar_sync(NB_WG + wg, 128);
+        // sub-tile `wg` of dS^T buffer (i & 1) was last read by dK_wg(i-2) and dQ(i-2); the commit behind BB_ST(i) -- waited for in phase A
+        // -- was issued after both, and the tensor pipe completes in order, so the sub-tile is free
         tmem_ld_wait();
         if (wg_lead) HVC_TR(wg, i, 5);
         const uint32_t sub_saddr = sDS0 + (i & 1) * L::kDSBuf + wg * 16384;
@@ -534,12 +578,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_arrive_warp(&bar[BB_DS + wg]);
       if (wg_lead) HVC_TR(wg, i, 7);
 
-      // ---------------- drain dQ(i-1) while the tensor pipe works on the next products
-      if (i > 0) drain_dq(i - 1);
       if (wg_lead) HVC_TR(wg, i, 9);
     }
-    drain_dq(nQ - 1);   // the commit behind BB_DQF covers every earlier MMA: dV and dK are complete too
-    if (wg_lead) bulk_wait<0>();
+    mbar_wait(&bar[BB_DONE], 0, 35);      // every product has completed: dV and dK are final
+    tc_fence_after();
 
     // ---- epilogue: dV, dK (x softmax scale) -> bf16 -> global; warpgroup x writes d columns [x*HD/2, (x+1)*HD/2)
     const int key = j * kBT + r;
@@ -563,6 +605,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
+  } else {
+    reg_dealloc<kRegsAux>();      // the two idle warps of the TMA / MMA warpgroup (setmaxnreg is a warpgroup-wide instruction)
   }
 
   tc_fence_before();
@@ -654,7 +698,7 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   AttnBwdKArgs ka;
   ka.batch = a->batch; ka.heads = a->heads; ka.nq = a->nq; ka.nk = a->nk; ka.nq_pad = nq_pad;
   ka.n_q_tiles = nq_pad / kBT;
-  ka.nlse2 = a->delta + plane; ka.delta = a->delta;
+  ka.nlse2 = a->delta + plane; ka.delta = a->delta; ka.dq_accum = a->dq_accum;
   ka.rowkeys = reinterpret_cast<const uint32_t*>(a->delta + 2 * plane); ka.drop = drop;
   ka.dk = reinterpret_cast<bf16*>(a->dk); ka.lddk = a->lddk;
   ka.dv = reinterpret_cast<bf16*>(a->dv); ka.lddv = a->lddv;

@@ -130,11 +130,11 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
       e.y = (c0 + c + 1 < tail) ? e.y : 0.f;
     }
     sum = fadd2(sum, e);
-    if (DROP) {   // rowkey here is the block key of this 128-key tile (drop_blockkey); c0 + c is the column inside it
-      e.x = drop_keep_in_block(rowkey, c0 + c, thr) ? e.x : 0.f;
-      e.y = drop_keep_in_block(rowkey, c0 + c + 1, thr) ? e.y : 0.f;
+    if (DROP) {   // rowkey here is the block key of this 128-key tile (drop_blockkey); c0 + c is the column inside it (a constant multiplier)
+      e.x = drop_negate_if_dropped(e.x, drop_hash_in_block(rowkey, c0 + c), thr);
+      e.y = drop_negate_if_dropped(e.y, drop_hash_in_block(rowkey, c0 + c + 1), thr);
     }
-    pk[c >> 1] = pack_bf16(e.x, e.y);
+    pk[c >> 1] = DROP ? pack_bf16_relu(e.x, e.y) : pack_bf16(e.x, e.y);      // relu: the negated (dropped) entries become 0
   }
   tmem_st_32x16(tP + (c0 >> 1), pk);   // P (bf16 pairs) over S columns that were already consumed
 }

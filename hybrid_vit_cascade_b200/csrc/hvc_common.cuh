@@ -82,6 +82,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #ifndef HVC_WAIT_LIMIT_NS
 #define HVC_WAIT_LIMIT_NS 4000000000ull
 #endif
+// HVC_WAIT_INLINE (kernels that re-partition registers with setmaxnreg): the slow path is inlined and reports through a device word
+// instead of printf.  A real call -- to a __noinline__ function or to vprintf -- makes ptxas allocate the WHOLE kernel inside the smallest
+// setmaxnreg budget of any call site (measured: attn_bwd_kernel stayed below R61 with budgets 64 / 104 / 168 until the calls were gone).
+static __device__ unsigned int g_hvc_wait_timeout_tag = 0;      // 0 = no timeout; else (tag << 16 | thread) of the first waiter that gave up
+#ifdef HVC_WAIT_INLINE
+static __device__ __forceinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > HVC_WAIT_LIMIT_NS) {
+      atomicCAS(&g_hvc_wait_timeout_tag, 0u, (static_cast<unsigned>(tag) << 16) | threadIdx.x);
+      __trap();
+    }
+  }
+}
+#else
 static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
@@ -93,6 +109,7 @@ static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parit
     }
   }
 }
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, tag);
@@ -431,8 +448,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 // kernels.  keep(row, col) is a pure function of (seed words, site, row, col), so forward and backward kernels with
 // different thread layouts regenerate the same mask and nothing of mask size is stored.  The seed is two 32-bit
 // words drawn by the caller from torch's CUDA generator (replayed by torch.utils.checkpoint) and read from device
-// memory, so no host synchronisation is needed.  Mixer: 32x32->64 multiply folded by xor ("mum"); three rounds for
-// the per-row key, one per element.  oracle/dropout_mask.py restates it for the parity tests.
+// memory, so no host synchronisation is needed.  oracle/dropout_mask.py restates it for the parity tests.
+//
+//   keep(row, col)  <=>  (rowkey(row) * colmul(col)) mod 2^32 >= thr          (thr = p * 2^32; decision in the TOP bits of the product)
+//   rowkey(row)  = three rounds of a 32x32->64 multiply folded by xor ("mum") over (row, seed, site), forced odd
+//   colmul(col)  = blockmul(col / 128) * inblockmul(col % 128) mod 2^32, both odd outputs of a 32-bit finaliser
+//
+// Round 2: the per-element work is ONE 32-bit multiply and one compare.  A thread that owns a row folds blockmul into its key once per
+// 128-column tile and multiplies by the compile-time constants inblockmul(c) (attention forward, GEMM epilogues); a thread that owns a
+// column multiplies the row keys by its own colmul (attention backward).  Round 1 hashed (rowkey ^ colterm) * M: an extra xor per
+// element on the ALU pipe, which the mask work saturates (profiles/r02_maskbench_dropout_sequences.log: 6.06 -> 4.13 clk per element
+// and SM sub-partition with the keep decision applied as a predicated negate on the FMA pipe instead of a select).  Two columns of one
+// row are related by a fixed odd ratio B2/B1; for the 128 constants below (and their products with the block multipliers) the joint
+// keep statistics of all pairs are indistinguishable from independent draws (tests/test_dropout_mask_cpu.py: every pair within 5 sigma
+// over 2^20 rows, per-row counts binomial).
 struct DropCfg {
   uint32_t k0, k1, site, thr;   // drop element iff hash < thr (thr = p * 2^32)
   float inv_keep;               // 1 / (1 - p)
@@ -444,22 +473,32 @@ __host__ __device__ __forceinline__ uint32_t mum32(uint32_t a, uint32_t b) {
 __device__ __forceinline__ uint32_t drop_rowkey(const DropCfg& c, uint32_t row) {
   uint32_t h = mum32(row ^ c.k0, 0x9E3779B1u);
   h = mum32(h ^ c.site ^ c.k1, 0x85EBCA77u);
-  return mum32(h + 0x6A09E667u, 0xC2B2AE3Du);
+  return mum32(h + 0x6A09E667u, 0xC2B2AE3Du) | 1u;      // odd: multiplication by it is a bijection of the 32-bit words
 }
-// Element (row, col) of a site: keep iff ((rowkey ^ colterm(col)) * kDropMix) mod 2^32 >= thr.  The decision sits in the TOP bits of a
-// 32-bit multiplicative hash, which every bit of its argument reaches; colterm = hash(col / 128) ^ ((col % 128) * kDropColMul), so
-// inside a 128-column tile the per-element work is one xor with a constant, one 32-bit multiply, one compare and one select
-// (the first version used a 64-bit multiply-and-fold per element: 6-7 issue slots, which nearly halved the attention forward).
-constexpr uint32_t kDropColMul = 0x9E3779B1u, kDropBlkMul = 0xC2B2AE3Du, kDropMix = 0x2545F491u;
-__host__ __device__ __forceinline__ uint32_t drop_blockterm(uint32_t col) { return mum32(col >> 7, kDropBlkMul); }
-__device__ __forceinline__ uint32_t drop_colterm(uint32_t col) { return drop_blockterm(col) ^ ((col & 127u) * kDropColMul); }
-// rowkey ^ blockterm once per (row, 128-column block), then per element with the column's offset inside the block
-__device__ __forceinline__ uint32_t drop_blockkey(uint32_t rowkey, uint32_t col) { return rowkey ^ drop_blockterm(col); }
+__host__ __device__ constexpr uint32_t drop_mix32(uint32_t c) {
+  uint32_t x = (c + 1u) * 0x9E3779B1u;
+  x ^= x >> 15; x *= 0x85EBCA77u;
+  x ^= x >> 13; x *= 0xC2B2AE3Du;
+  x ^= x >> 16;
+  return x;
+}
+__host__ __device__ constexpr uint32_t drop_inblock_mul(uint32_t col_in_block) { return drop_mix32(col_in_block) | 1u; }
+__host__ __device__ constexpr uint32_t drop_block_mul(uint32_t block) { return drop_mix32(block ^ 0x5BD1E995u) | 1u; }
+__host__ __device__ constexpr uint32_t drop_colmul(uint32_t col) { return drop_block_mul(col >> 7) * drop_inblock_mul(col & 127u); }
+// rowkey * blockmul once per (row, 128-column block), then per element one multiply by the column's in-block constant
+__device__ __forceinline__ uint32_t drop_blockkey(uint32_t rowkey, uint32_t col) { return rowkey * drop_block_mul(col >> 7); }
+__device__ __forceinline__ uint32_t drop_hash_in_block(uint32_t blockkey, uint32_t col_in_block) { return blockkey * drop_inblock_mul(col_in_block); }
 __device__ __forceinline__ bool drop_keep_in_block(uint32_t blockkey, uint32_t col_in_block, uint32_t thr) {
-  return (blockkey ^ (col_in_block * kDropColMul)) * kDropMix >= thr;
+  return drop_hash_in_block(blockkey, col_in_block) >= thr;
 }
-__device__ __forceinline__ uint32_t drop_hash(uint32_t rowkey, uint32_t col) { return (rowkey ^ drop_colterm(col)) * kDropMix; }
+__device__ __forceinline__ uint32_t drop_hash(uint32_t rowkey, uint32_t col) { return rowkey * drop_colmul(col); }
 __device__ __forceinline__ bool drop_keep(uint32_t rowkey, uint32_t col, uint32_t thr) { return drop_hash(rowkey, col) >= thr; }
+// The attention kernels carry the decision in the SIGN of the (non-negative) probability: dropped -> negated.  One compare (ALU pipe) and
+// a predicated negate (FMA pipe); the bf16 pack with relu then zeroes the dropped entries for free.
+__device__ __forceinline__ float drop_negate_if_dropped(float e, uint32_t hash, uint32_t thr) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lo.u32 p, %1, %2;\n\t@p neg.f32 %0, %0;\n\t}" : "+f"(e) : "r"(hash), "r"(thr));
+  return e;
+}
 // host-side description -> kernel config (reads the seed words on the device)
 struct DropArg {
   const uint32_t* seed; uint32_t site; uint32_t thr; float inv_keep;   // seed == nullptr: disabled

@@ -84,13 +84,22 @@ __device__ __forceinline__ WorkItem decode_work(const GemmKArgs& p, int w) {
   return it;
 }
 
-// nn.Dropout on the 32 values of one row chunk: element (row, col) of this site, see hvc_common.cuh
+// nn.Dropout on the 32 values of one row chunk: element (row, col) of this site, see hvc_common.cuh.  The chunk starts at a multiple of
+// 32 inside its 128-column block; one instantiation per start makes the 32 in-block multipliers compile-time constants.
+template <int C0>
+__device__ __forceinline__ void epilogue_dropout_chunk(float (&v)[32], uint32_t bk, uint32_t thr, float inv_keep) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = drop_keep_in_block(bk, C0 + j, thr) ? v[j] * inv_keep : 0.f;
+}
 __device__ __forceinline__ void epilogue_dropout(const GemmKArgs& p, float (&v)[32], int row, int col0) {
   const DropCfg dc = drop_load(p.drop);
   const uint32_t bk = drop_blockkey(drop_rowkey(dc, static_cast<uint32_t>(row)), static_cast<uint32_t>(col0));   // col0 % 32 == 0
-  const uint32_t c_in = static_cast<uint32_t>(col0) & 127u;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = drop_keep_in_block(bk, c_in + j, dc.thr) ? v[j] * dc.inv_keep : 0.f;
+  switch ((static_cast<uint32_t>(col0) & 127u) >> 5) {
+    case 0: epilogue_dropout_chunk<0>(v, bk, dc.thr, dc.inv_keep); break;
+    case 1: epilogue_dropout_chunk<32>(v, bk, dc.thr, dc.inv_keep); break;
+    case 2: epilogue_dropout_chunk<64>(v, bk, dc.thr, dc.inv_keep); break;
+    default: epilogue_dropout_chunk<96>(v, bk, dc.thr, dc.inv_keep); break;
+  }
 }
 
 // ---------------------------------------------------------------- epilogue for one 32-column chunk

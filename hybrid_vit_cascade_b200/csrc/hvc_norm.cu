@@ -273,6 +273,12 @@ __global__ void __launch_bounds__(256) resid_bwd_kernel(const ResidBwdArgs a) {
     s1[i] = s2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     gv[i] = a.gate ? ld4(a.gate + (long long)b * a.gate_ld, 4 * (lane + 32 * i), a.C) : make_float4(1.f, 1.f, 1.f, 1.f);
   }
+  uint4 cm[VPL];      // dropout: the column multipliers of this thread's four columns per vector (the same for every row)
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint32_t c = 4u * (lane + 32 * i);
+    cm[i] = make_uint4(drop_colmul(c), drop_colmul(c + 1), drop_colmul(c + 2), drop_colmul(c + 3));
+  }
   for (int r = r0 + warp; r < r1; r += 8) {
     const long long row = (long long)b * a.rows_per_batch + r;
     float4 d[VPL], br[VPL];
@@ -287,12 +293,11 @@ __global__ void __launch_bounds__(256) resid_bwd_kernel(const ResidBwdArgs a) {
         s2[i].x += d[i].x * br[i].x; s2[i].y += d[i].y * br[i].y;
         s2[i].z += d[i].z * br[i].z; s2[i].w += d[i].w * br[i].w;
       }
-      if (a.drop.seed != nullptr) {   // d(pre-dropout branch) = mask / (1-p) * gate * dout
-        const uint32_t bk = drop_blockkey(rk, c), cl = static_cast<uint32_t>(c) & 127u;     // c % 4 == 0: one 128-column block
-        d[i].x = drop_keep_in_block(bk, cl, a.drop.thr) ? d[i].x * a.drop.inv_keep : 0.f;
-        d[i].y = drop_keep_in_block(bk, cl + 1, a.drop.thr) ? d[i].y * a.drop.inv_keep : 0.f;
-        d[i].z = drop_keep_in_block(bk, cl + 2, a.drop.thr) ? d[i].z * a.drop.inv_keep : 0.f;
-        d[i].w = drop_keep_in_block(bk, cl + 3, a.drop.thr) ? d[i].w * a.drop.inv_keep : 0.f;
+      if (a.drop.seed != nullptr) {   // d(pre-dropout branch) = mask / (1-p) * gate * dout; cm = this thread's column multipliers
+        d[i].x = rk * cm[i].x >= a.drop.thr ? d[i].x * a.drop.inv_keep : 0.f;
+        d[i].y = rk * cm[i].y >= a.drop.thr ? d[i].y * a.drop.inv_keep : 0.f;
+        d[i].z = rk * cm[i].z >= a.drop.thr ? d[i].z * a.drop.inv_keep : 0.f;
+        d[i].w = rk * cm[i].w >= a.drop.thr ? d[i].w * a.drop.inv_keep : 0.f;
       }
       s1[i].x += d[i].x; s1[i].y += d[i].y; s1[i].z += d[i].z; s1[i].w += d[i].w;
       if (c < a.C) {

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE (oracle): restatement of the counter-based dropout masks the sm_100a kernels generate
-(hybrid_vit_cascade_b200/csrc/hvc_common.cuh: mum32 / drop_rowkey / drop_colterm / drop_hash), so that train-mode parity can be
+(hybrid_vit_cascade_b200/csrc/hvc_common.cuh: mum32 / drop_rowkey / drop_colmul / drop_hash), so that train-mode parity can be
 checked exactly: with the same mask, the CUDA path must match the reference arithmetic
 
     attn = dropout(softmax(q k^T * scale))          vit_components.py:47-49, :104-110
@@ -14,9 +14,6 @@ Only tests/ may import this module.
 import torch
 
 _M32 = 0xFFFFFFFF
-COL_MUL = 0x9E3779B1      # kDropColMul
-BLK_MUL = 0xC2B2AE3D      # kDropBlkMul
-MIX = 0x2545F491          # kDropMix
 
 
 def _mum32(a, b):
@@ -33,22 +30,30 @@ def _mum32(a, b):
 
 
 def _mul32(a, b):
-    """low 32 bits of a * b; a: int64 tensor holding uint32 values, b: python int (uint32)"""
+    """low 32 bits of a * b; a, b: int64 tensors (or python ints) holding uint32 values"""
     a = a & _M32
     return ((a * (b & 0xFFFF)) + (((a * (b >> 16)) & 0xFFFF) << 16)) & _M32
 
 
-def colterm(cols):
-    """drop_colterm: hash of the 128-column block xor a multiple of the column's offset inside it"""
+def _mix32(c):
+    """drop_mix32: 32-bit finaliser of (c + 1) * 0x9E3779B1"""
+    x = _mul32((c + 1) & _M32, 0x9E3779B1)
+    x = _mul32(x ^ (x >> 15), 0x85EBCA77)
+    x = _mul32(x ^ (x >> 13), 0xC2B2AE3D)
+    return x ^ (x >> 16)
+
+
+def colmul(cols):
+    """drop_colmul: blockmul(col / 128) * inblockmul(col % 128) mod 2^32, both factors odd"""
     cols = cols.to(torch.int64)
-    return _mum32(cols >> 7, BLK_MUL) ^ _mul32(cols & 127, COL_MUL)
+    return _mul32(_mix32((cols >> 7) ^ 0x5BD1E995) | 1, _mix32(cols & 127) | 1)
 
 
 def rowkey(k0, k1, site, rows):
-    """rows: int64 tensor of row ids -> uint32 keys (as int64)."""
+    """rows: int64 tensor of row ids -> odd uint32 keys (as int64)."""
     h = _mum32((rows & _M32) ^ k0, 0x9E3779B1)
     h = _mum32(h ^ site ^ k1, 0x85EBCA77)
-    return _mum32((h + 0x6A09E667) & _M32, 0xC2B2AE3D)
+    return _mum32((h + 0x6A09E667) & _M32, 0xC2B2AE3D) | 1
 
 
 def keep_mask(seed_words, site, rows, cols, p):
@@ -57,7 +62,7 @@ def keep_mask(seed_words, site, rows, cols, p):
     k0, k1 = (int(w) & _M32 for w in seed_words)
     thr = min(int(p * 4294967296.0), _M32)
     rk = rowkey(k0, k1, int(site) & _M32, rows.to(torch.int64))
-    h = _mul32(rk[:, None] ^ colterm(cols)[None, :], MIX)       # drop_hash: the decision sits in the top bits of a 32-bit multiply
+    h = _mul32(rk[:, None], colmul(cols)[None, :])             # drop_hash: the decision sits in the top bits of one 32-bit multiply
     return h >= thr
 
 

@@ -173,3 +173,39 @@ def test_dropout_replay_eval_and_checkpoint():
             acc += m(x, ctx, cond)
     single = O.max_rel(y1, e1)
     assert O.max_rel(acc / n, e1) < 0.45 * single
+
+
+def test_mask_statistics_at_the_bench_shape_from_the_kernels():
+    """correlation checks on GPU-GENERATED masks over the index ranges of the benchmark (32 (batch, head) slices x
+    32768 queries = 2^20 rows; 32768 key columns): the GEMM epilogue writes 0 where it drops, so a constant product exposes the mask.
+    Keep rate, lag correlations along both axes, across row blocks of 32768 (the same query in the next (batch, head) slice), across
+    sites and across seeds."""
+    from hybrid_vit_cascade_b200 import kernels as K
+    p, Kd = 0.1, 64
+
+    def mask(T, N, seed, site):
+        a = torch.ones(T, Kd, device="cuda", dtype=torch.bfloat16)
+        b = torch.full((N, Kd), 1.0 / Kd, device="cuda", dtype=torch.bfloat16)
+        y = K.gemm(a, b, epilogue=K.EPI_F32, drop=K.Drop(seed, site, p))
+        return (y != 0)
+
+    s1, s2 = _seed(), _seed((0x1234568, -0x3456789))            # seeds one bit apart
+    # (a) the whole column range of one key axis: 4096 rows x 32768 columns
+    m = mask(4096, 32768, s1, 0).float() - (1 - p)
+    noise = 5 * p * (1 - p) / m.numel() ** 0.5
+    assert abs(float(m.mean())) < 4 * (p * (1 - p) / m.numel()) ** 0.5
+    for lag in (1, 2, 3, 64, 127, 128, 129, 4096, 16384):
+        assert abs(float((m[:, :-lag] * m[:, lag:]).mean())) < noise, ("col lag", lag)
+    for lag in (1, 2, 128, 2048):
+        assert abs(float((m[:-lag] * m[lag:]).mean())) < noise, ("row lag", lag)
+    for other in (mask(4096, 32768, s1, 8), mask(4096, 32768, s1, 1), mask(4096, 32768, s2, 0)):      # next block's site, next site, next seed
+        assert abs(float((m * (other.float() - (1 - p))).mean())) < noise
+    del m, other
+    # (b) the whole row range: 2^20 rows (b, h, q) x 256 columns; rows 32768 apart are the same query of the next (batch, head) slice
+    r = mask(1 << 20, 256, s1, 0).float() - (1 - p)
+    noise = 5 * p * (1 - p) / r.numel() ** 0.5
+    assert abs(float(r.mean())) < 4 * (p * (1 - p) / r.numel()) ** 0.5
+    for lag in (1, 32768, 65536, 4 * 32768):
+        assert abs(float((r[:-lag] * r[lag:]).mean())) < noise * 1.1, ("row-block lag", lag)
+    spread = float(r.mean(1).std())                               # per-row keep rates scatter like a binomial over 256 columns
+    assert 0.9 < spread / (p * (1 - p) / 256) ** 0.5 < 1.1
