@@ -49,6 +49,7 @@ constexpr int kBwdWGs = 2;                        // elementwise warpgroups
 constexpr int kBwdThreads = 512;
 // Register budget: the block launches with 65536 / 512 = 128 registers per thread; the drain warpgroup and the TMA / MMA warpgroup give
 // registers back (setmaxnreg.dec), the elementwise warpgroups take them (setmaxnreg.inc): 128*64 + 128*104 + 256*168 = 64512.
+constexpr int kDQChunk = 16, kDQBufs = 3;          // dQ leaves in 16-column chunks through a ring of three staging buffers
 constexpr int kRegsAux = 64, kRegsDrain = 104, kRegsEw = 168;
 constexpr int kBT = 128;                          // tile edge (queries and keys)
 constexpr int kQStages = 3;
@@ -86,9 +87,9 @@ struct BwdSmem {
   static constexpr int kQ = 2 * kTile;
   static constexpr int kDS = kQ + kQStages * kQStage;        // 2 x [128 keys x 128 queries] bf16 (two 64-query sub-tiles each);
   static constexpr int kDSBuf = kBT * kBT * 2;               //   also: K/V landing zone at start, dQ staging when released
-  static constexpr int kDQStage = kDS + 2 * kDSBuf;            // dQ staging of the drain warpgroup: 128 queries x HD/2 columns f32
-  static constexpr int kDQStageBytes = kBT * (HD / 2) * 4;
-  static constexpr int kBar = kDQStage + kDQStageBytes;
+  static constexpr int kDQStage = kDS + 2 * kDSBuf;            // dQ staging ring of the drain warpgroup: kDQBufs x [128 queries x 16 columns] f32
+  static constexpr int kDQBufBytes = kBT * kDQChunk * 4;       // 8 KB
+  static constexpr int kBar = kDQStage + kDQBufs * kDQBufBytes;
   static constexpr int kTotal = kBar + 256 + 1024;
 };
 
@@ -438,7 +439,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive_warp(&bar[BB_DQFREE]);              // the next dQ product may overwrite the accumulator
-#ifdef HVC_BWD_DQ_RED
+#if defined(HVC_BWD_EXP_DRAIN_LDONLY)
+      asm volatile("" ::"r"(v[0]), "r"(v[HD - 1]));      // timing experiment: TMEM load only
+#elif defined(HVC_BWD_DQ_RED)
       {   // variant: L2 reductions straight from registers (no staging tile, no TMA)
         float* dst = p.dq_accum + ((long long)bh * p.nq_pad + i * kBT + r) * HD;
 #pragma unroll
@@ -447,20 +450,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                        "f"(__uint_as_float(v[4 * k + 2])), "f"(__uint_as_float(v[4 * k + 3])) : "memory");
       }
 #else
+      // 16-column chunks through a ring of three 8 KB staging buffers: reduce(c) is issued once every thread's rows of chunk c are in
+      // shared memory; the buffer that chunk c + 1 will use was read by reduce(c - 2), which the leader waits for BEFORE the barrier, so
+      // one barrier per chunk covers both conditions and the TMA engine always has up to two reduces in flight
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (lead) bulk_wait_read<0>();                // the previous reduce has finished reading the staging tile
-        named_bar_sync(NB_DRAIN, 128);
+      for (int c = 0; c < HD / kDQChunk; ++c) {
+        const uint32_t buf = static_cast<uint32_t>((i * (HD / kDQChunk) + c) % kDQBufs) * L::kDQBufBytes;
 #pragma unroll
-        for (int k = 0; k < kDCols / 4; ++k)
-          sts_u4(stage + swz_offset<kDCols * 4>(r, k), v[half * kDCols + 4 * k], v[half * kDCols + 4 * k + 1], v[half * kDCols + 4 * k + 2],
-                 v[half * kDCols + 4 * k + 3]);
+        for (int k = 0; k < kDQChunk / 4; ++k)
+          sts_u4(stage + buf + swz_offset<kDQChunk * 4>(r, k), v[c * kDQChunk + 4 * k], v[c * kDQChunk + 4 * k + 1], v[c * kDQChunk + 4 * k + 2],
+                 v[c * kDQChunk + 4 * k + 3]);
         fence_proxy_async_smem();
+        if (lead) bulk_wait_read<1>();
         named_bar_sync(NB_DRAIN, 128);
+#ifndef HVC_BWD_EXP_DRAIN_NOREDUCE
         if (lead) {
-          tma_reduce_add_2d(&tmDQ, smem + L::kDQStage, half * kDCols, bh * p.nq_pad + i * kBT);
+          tma_reduce_add_2d(&tmDQ, smem + L::kDQStage + buf, c * kDQChunk, bh * p.nq_pad + i * kBT);
           bulk_commit();
         }
+#endif
       }
 #endif
     }
@@ -690,7 +698,7 @@ static int launch_attn_bwd(const hvc_attn_args* a, cudaStream_t st) {
   }
   CUtensorMap tmQ, tmK, tmV, tmDO, tmDQ;
   int rc;
-  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, HD / kBwdWGs, kBT, swz))) return rc;
+  if ((rc = make_tmap_2d(&tmDQ, a->dq_accum, 4, (uint64_t)a->batch * a->heads * nq_pad, HD, HD, kDQChunk, kBT, 2))) return rc;   // 64-byte rows: SWIZZLE_64B
   if ((rc = make_tmap_2d(&tmQ, a->q, 2, (uint64_t)a->batch * a->nq, width, a->ldq, HD, kBT, swz))) return rc;
   if ((rc = make_tmap_2d(&tmDO, a->d_o, 2, (uint64_t)a->batch * a->nq, width, a->lddo, HD, kBT, swz))) return rc;
   if ((rc = make_tmap_2d(&tmK, a->k, 2, (uint64_t)a->batch * a->nk, width, a->ldk, HD, kBT, swz))) return rc;
