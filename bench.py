@@ -69,10 +69,11 @@ WORKLOADS = {
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE self-attention backward launch per sample at 32768
-# tokens, from the `ncu --set full` capture profiles/r01_ncu_full_hot_kernels_b1.csv (one sample, C = 256): head_dim -> bytes.
+# tokens, from the `ncu --set full` captures profiles/r02_ncu_full_attn_d64_b1.csv (d = 64: 104.1 MB read + 24.1 MB written) and
+# profiles/r01_ncu_full_hot_kernels_b1.csv (d = 32) (one sample, C = 256): head_dim -> bytes.
 # A launch over B samples moves B times that (each (batch, head) slice is touched by its own CTAs only).  The algorithmic
 # bytes are Q, K, V, dO, O reads + dK, dV writes + the fp32 dQ reduction = 8 * N * C * 2 + N * C * 4 = 151 MB per sample.
-NCU_ATTN_BWD_DRAM_BYTES_PER_SAMPLE_32K = {64: 129.0e6, 32: 141.4e6}
+NCU_ATTN_BWD_DRAM_BYTES_PER_SAMPLE_32K = {64: 128.2e6, 32: 141.4e6}
 
 
 def log(*a):
@@ -554,7 +555,7 @@ def run_b200(args, w):
                 "bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": (NCU_ATTN_BWD_DRAM_BYTES_PER_SAMPLE_32K.get(w["voxel_dim"] // w["heads"], 0.0) * B
                             if oracle_cfg(w).num_tokens == 32768 and w["voxel_dim"] == 256 else None),
-                "traffic_note": "bytes per launch = ncu DRAM read+write of a one-sample launch x batch (profiles/r01_ncu_full_hot_kernels_b1.csv)",
+                "traffic_note": "bytes per launch = ncu DRAM read+write of a one-sample launch x batch (profiles/r02_ncu_full_attn_d64_b1.csv; d=32: r01_ncu_full_hot_kernels_b1.csv)",
                 "peak_source": peak_src, "launches": len(big), "ms_per_launch": sum(t for t, _ in big) / len(big),
                 "frac_of_nominal_2250": ach / 2250.0}
     line = {
