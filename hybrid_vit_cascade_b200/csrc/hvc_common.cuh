@@ -66,6 +66,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait parks the warp in hardware until the phase completes or a system time limit expires.  Tried and rejected (round 2): the optional
+// suspend-time hint (1 ms) to thin out the retry loops of the mostly-waiting TMA / MMA / drain warps (0.45 TRYWAIT + 0.9 BRA per score in
+// attn_bwd_kernel, profiles/r02_ncu_full_attn_d64_b1.csv) -- wake-ups became slower instead: attention backward 797 -> 743, forward
+// 797 -> 766 TFLOP/s at d = 64.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
