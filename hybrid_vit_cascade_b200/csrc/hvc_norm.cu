@@ -6,6 +6,8 @@
 //   * AdaLN modulation linear on the tiny (B, cond) input           (vit_components.py:144)
 // All are one-pass over their [T, C] operands with 128-bit accesses; roofline = HBM bandwidth.
 // Row layout: one warp per token row, lane l owns columns {4*(l + 32*i) .. +3}, i < VPL.
+#include <stdlib.h>
+
 #include "hvc_common.cuh"
 #include "hvc_host.h"
 
@@ -145,10 +147,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
     }
   }
   const float invC = 1.0f / a.C;
+  // Every operand of a row (x, dz, the residual-stream gradient dx_in, mean, rstd) is requested before any of it is used: round 1 fetched
+  // dx_in after the two warp reductions, which put a second exposed memory latency on every row (4.1 TB/s = 0.62 of the copy bandwidth).
   for (int r = r0 + warp; r < r1; r += 8) {
     const long long row = (long long)b * a.rows_per_batch + r;
-    float4 xv[VPL], dz[VPL];
+    float4 xv[VPL], dz[VPL], ev[VPL];
     load_row_f32<VPL>(a.x + row * a.ldx, a.C, lane, xv);
+    if (a.dx_in) load_row_f32<VPL>(a.dx_in + row * a.lddxi, a.C, lane, ev);
     if (a.dz_bf16) {
       load_row_bf16<VPL>(a.dz_bf16 + row * a.lddz, a.C, lane, dz);
     } else if (a.dz_f32) {
@@ -187,10 +192,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnBwdArgs a) {
       g.y = rstd * (dz[i].y - t1 - xv[i].y * t2);
       g.z = rstd * (dz[i].z - t1 - xv[i].z * t2);
       g.w = rstd * (dz[i].w - t1 - xv[i].w * t2);
-      if (a.dx_in) {
-        const float4 e = __ldg(reinterpret_cast<const float4*>(a.dx_in + row * a.lddxi + c));
-        g.x += e.x; g.y += e.y; g.z += e.z; g.w += e.w;
-      }
+      if (a.dx_in) { g.x += ev[i].x; g.y += ev[i].y; g.z += ev[i].z; g.w += ev[i].w; }
       *reinterpret_cast<float4*>(a.dx + row * a.lddx + c) = g;
     }
   }
@@ -448,6 +450,12 @@ __global__ void __launch_bounds__(128) adaln_dgrad_kernel(const float* __restric
   }
 }
 
+// rows per block of the backward kernels before the grid-size rule below shrinks it (HVC_NORM_RPB: tuning only)
+static int hvc_rows_per_block() {
+  static int v = 0;
+  if (v == 0) { const char* e = getenv("HVC_NORM_RPB"); v = e ? atoi(e) : 64; if (v < 8) v = 8; }
+  return v;
+}
 static int pick_vpl(int C) { return C <= 128 ? 1 : C <= 256 ? 2 : C <= 512 ? 4 : C <= 1024 ? 8 : 0; }
 
 }  // namespace hvc
@@ -494,7 +502,7 @@ extern "C" int hvc_ln_bwd(const hvc_ln_bwd_args* a, void* stream) {
   k.dx_in = a->dx_in; k.lddxi = a->lddx_in; k.dx = a->dx; k.lddx = a->lddx; k.S1 = a->S1; k.S2 = a->S2;
   k.rows_per_batch = a->rows_per_batch; k.C = a->C;
   // ~4 blocks per SM worth of work, but at least 8 rows (one per warp) per block
-  int rpb = 64;
+  int rpb = hvc_rows_per_block();
   while (rpb > 8 && (long long)a->batch * ((a->rows_per_batch + rpb - 1) / rpb) < 4LL * device_sm_count()) rpb >>= 1;
   k.rows_per_block = rpb;
   dim3 grid((a->rows_per_batch + rpb - 1) / rpb, a->batch);
@@ -523,7 +531,7 @@ extern "C" int hvc_resid_bwd(const hvc_resid_bwd_args* a, void* stream) {
   k.D1 = a->D1; k.D2 = a->dgate; k.rows_per_batch = a->rows_per_batch; k.C = a->C;
   k.drop = make_drop(a->drop);
   HVC_CHECK_ARG(k.drop.seed == nullptr || a->drop.p < 1.f, "hvc_resid_bwd: dropout p must be < 1");
-  int rpb = 64;
+  int rpb = hvc_rows_per_block();
   while (rpb > 8 && (long long)a->batch * ((a->rows_per_batch + rpb - 1) / rpb) < 4LL * device_sm_count()) rpb >>= 1;
   k.rows_per_block = rpb;
   dim3 grid((a->rows_per_batch + rpb - 1) / rpb, a->batch);
