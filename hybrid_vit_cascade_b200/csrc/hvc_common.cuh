@@ -409,6 +409,42 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi
   erf_exp_fast(x * 0.70710678118654752f, e, ex);
   return fmaf(0.3989422804014327f * x, ex, fmaf(0.5f, e, 0.5f));
 }
+// The same GELU / GELU' on a PAIR of values with packed fp32 arithmetic (FFMA2 / FMUL2: one issue slot per two elements) and without the
+// sign handling of erf: with h(x) = 1/2 pl(t) exp(-x^2/2), t = 1 / (1 + 0.3275911 |x| / sqrt 2)  (Abramowitz & Stegun 7.1.26),
+//     Phi(x) = x >= 0 ? 1 - h : h,        GELU(x) = relu(x) - |x| h,        GELU'(x) = Phi(x) + x exp(-x^2/2) / sqrt(2 pi).
+// ~10 issue slots per element instead of ~19: the GEMMs with a GELU epilogue were bound by the epilogue warps' instruction issue
+// (profiles/r02_gemm_time_by_shape.log: 429 / 468 us against 160-240 us for the same shapes without the activation).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void gelu_h_exp2(float2 x, float2& h, float2& e) {
+  const float2 x2 = __fmul2_rn(x, x);
+  const float2 arg = __fmul2_rn(x2, make_float2(-0.72134752044448170f, -0.72134752044448170f));       // -x^2/2 * log2(e)
+  e = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
+  const float2 t = make_float2(rcp_approx(fmaf(0.23164189f, fabsf(x.x), 1.0f)), rcp_approx(fmaf(0.23164189f, fabsf(x.y), 1.0f)));
+  // 1/2 * (((((a5 t + a4) t + a3) t + a2) t + a1) t): the 1/2 is folded into the coefficients
+  float2 pl = __ffma2_rn(t, make_float2(0.5307027145f, 0.5307027145f), make_float2(-0.7265760135f, -0.7265760135f));
+  pl = __ffma2_rn(pl, t, make_float2(0.7107068705f, 0.7107068705f));
+  pl = __ffma2_rn(pl, t, make_float2(-0.142248368f, -0.142248368f));
+  pl = __ffma2_rn(pl, t, make_float2(0.127414796f, 0.127414796f));
+  h = __fmul2_rn(__fmul2_rn(pl, t), e);
+}
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  float2 h, e;
+  gelu_h_exp2(x, h, e);
+  return make_float2(fmaf(-fabsf(x.x), h.x, fmaxf(x.x, 0.f)), fmaf(-fabsf(x.y), h.y, fmaxf(x.y, 0.f)));
+}
+__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
+  float2 h, e;
+  gelu_h_exp2(x, h, e);
+  // Phi = h + [x >= 0] (1 - 2 h);   + x e / sqrt(2 pi)
+  const float2 one_m2h = __ffma2_rn(h, make_float2(-2.f, -2.f), make_float2(1.f, 1.f));
+  const float2 xe = __fmul2_rn(__fmul2_rn(x, e), make_float2(0.3989422804014327f, 0.3989422804014327f));
+  const float kx = x.x >= 0.f ? 1.f : 0.f, ky = x.y >= 0.f ? 1.f : 0.f;
+  return __fadd2_rn(__ffma2_rn(make_float2(kx, ky), one_m2h, h), xe);
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));

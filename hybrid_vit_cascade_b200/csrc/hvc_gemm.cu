@@ -175,14 +175,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKArgs& p, const uint32_
     if (p.out2 != nullptr) store_bf16_row(reinterpret_cast<bf16*>(p.out2) + (long long)row * p.ldo2 + col0, v, ncols, fast);
     if (p.activation == HVC_ACT_GELU) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float2 g = gelu_fast2(make_float2(v[j], v[j + 1]));
+        v[j] = g.x; v[j + 1] = g.y;
+      }
     } else if (p.activation == HVC_ACT_GELU_GRAD) {
       if (fast) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float2 a = unpack_bf16(s.a[j]);
-          v[2 * j] *= gelu_grad_fast(a.x);
-          v[2 * j + 1] *= gelu_grad_fast(a.y);
+          const float2 g = gelu_grad_fast2(unpack_bf16(s.a[j]));
+          v[2 * j] *= g.x;
+          v[2 * j + 1] *= g.y;
         }
       } else {
         const bf16* ax = p.aux + (long long)row * p.ldaux + col0;
