@@ -20,6 +20,8 @@
 //
 // Roofline: tensor pipe for K >= ~512; at the backbone's C=256 projections the kernel sits on the
 // HBM/tensor ridge (A read + D write vs 2*M*N*K flops), so the fused epilogues are what matters.
+#include <stdlib.h>
+
 #include "hvc_common.cuh"
 #include "hvc_host.h"
 
@@ -58,6 +60,13 @@ struct GemmKArgs {
                   // (profiles/r01_implicit_conv_gemm.log)
   int a_halves, b_halves;   // MN-major operands: 64-element halves to load per k-block (2, or 1 when M / N <= 64)
   uint32_t stage_tx;        // bytes one stage's loads deliver
+  // Resident weight panel (round 2): with K <= 256 the whole B panel of an N tile (<= 4 k-blocks x 16 KB) fits in the B halves of the ring's
+  // first stages.  CTA c keeps N tile c % n_blocks for its whole life, loads that panel once and streams only A through the ring; the
+  // n_blocks CTAs of a group walk the same M tiles in step, so an A tile is fetched from HBM once and shared through L2.  (A contiguous
+  // n-major range per CTA was tried first: the CTAs of different N tiles drift apart and A is re-read from HBM -- qkv 147 -> 197 us.)  The K = 256 projections ran at the L2 -> SM throughput cap of the chip (every 128x128 tile fetched 64 KB of A and
+  // the same 64 KB weight panel again: 5800 of ~6300 B/clk, profiles/r02_gemm_time_by_shape.log); this halves that traffic.
+  int b_resident, tiles_per_cta;
+  uint32_t stage_tx_a, panel_tx;
 };
 
 // row shift of tap t (hvc_conv_taps::offsets); a half-tile past the last tap reads tap n_taps-1 again (its columns are never stored)
@@ -67,6 +76,11 @@ struct WorkItem {
   int m0, n0, kb0, kb1;
 };
 __device__ __forceinline__ WorkItem decode_work(const GemmKArgs& p, int w) {
+  if (p.b_resident) {     // this CTA keeps ONE N tile (blockIdx % n_blocks) and walks the M tiles w = group, group + groups, ...
+    WorkItem it;
+    it.m0 = w * BM; it.n0 = (static_cast<int>(blockIdx.x) % p.n_blocks) * BN; it.kb0 = 0; it.kb1 = p.k_blocks;
+    return it;
+  }
 #ifdef HVC_GEMM_SPLIT_FASTEST
   const int tile = w / p.k_splits, split = w - tile * p.k_splits;
 #else
@@ -240,11 +254,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAccStages);
+  uint64_t* panel_full = tempty_bar + kAccStages;      // resident weight panel: loaded / released (b_resident)
+  uint64_t* panel_empty = panel_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(panel_empty + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_work = p.m_blocks * p.n_blocks * p.k_splits;
+  // work items of this CTA: strided over the grid, or (resident panel) one contiguous range
+  const int w_first = p.b_resident ? static_cast<int>(blockIdx.x) / p.n_blocks : blockIdx.x;
+  const int w_step = p.b_resident ? p.tiles_per_cta /* = groups */ : gridDim.x;
+  const int w_end = p.b_resident ? p.m_blocks : num_work;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -257,6 +277,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);
     }
+    mbar_init(panel_full, 1);
+    mbar_init(panel_empty, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kAccStages * BN);
@@ -267,15 +289,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    uint32_t stage = 0, phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    uint32_t stage = 0, phase = 0, panel_gen = 0;
+    int panel_n0 = -1;
+    auto load_b = [&](uint8_t* sB, uint64_t* bar, int kb, int n0) {
+      if (B_MAJOR == kMajorK) {
+        tma_load_2d(sB, &tmB, bar, kb * BK, n0);
+      } else if (p.taps_side == 2) {   // each 64-column half lies inside one tap (tap_cin % 64 == 0): K rows shifted per tap
+        const int t0 = n0 / p.tap_cin, t1 = (n0 + 64) / p.tap_cin;
+        tma_load_2d(sB, &tmB, bar, n0 - t0 * p.tap_cin, kb * BK + tap_shift(p, t0));
+        tma_load_2d(sB + kTileBytes / 2, &tmB, bar, n0 + 64 - t1 * p.tap_cin, kb * BK + tap_shift(p, t1));
+      } else {
+        tma_load_2d(sB, &tmB, bar, n0, kb * BK);
+        if (p.b_halves == 2) tma_load_2d(sB + kTileBytes / 2, &tmB, bar, n0 + 64, kb * BK);
+      }
+    };
+    for (int w = w_first; w < w_end; w += w_step) {
       const WorkItem it = decode_work(p, w);
+      if (p.b_resident && it.n0 != panel_n0) {
+        // new N tile: once the MMAs of the previous one have read the old panel, load k-block kb's B tile into stage kb's B half
+        mbar_wait(panel_empty, (panel_gen & 1) ^ 1, 5);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(panel_full, p.panel_tx);
+          for (int kb = 0; kb < p.k_blocks; ++kb) load_b(smem + kb * kStageBytes + kTileBytes, panel_full, kb, it.n0);
+        }
+        __syncwarp();
+        panel_n0 = it.n0;
+        ++panel_gen;
+      }
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
         if (elect_one()) {
           uint8_t* sA = smem + stage * kStageBytes;
           uint8_t* sB = sA + kTileBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], p.stage_tx);
+          mbar_arrive_expect_tx(&full_bar[stage], p.b_resident ? p.stage_tx_a : p.stage_tx);
           if (A_MAJOR == kMajorK) {
             if (p.taps_side == 1) {   // k-block kb lies inside one tap (tap_cin % BK == 0): columns of that tap, rows shifted
               const int k = kb * BK, tap = k / p.tap_cin;
@@ -287,16 +333,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sA, &tmA, &full_bar[stage], it.m0, kb * BK);
             if (p.a_halves == 2) tma_load_2d(sA + kTileBytes / 2, &tmA, &full_bar[stage], it.m0 + 64, kb * BK);
           }
-          if (B_MAJOR == kMajorK) {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, it.n0);
-          } else if (p.taps_side == 2) {   // each 64-column half lies inside one tap (tap_cin % 64 == 0): K rows shifted per tap
-            const int t0 = it.n0 / p.tap_cin, t1 = (it.n0 + 64) / p.tap_cin;
-            tma_load_2d(sB, &tmB, &full_bar[stage], it.n0 - t0 * p.tap_cin, kb * BK + tap_shift(p, t0));
-            tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64 - t1 * p.tap_cin, kb * BK + tap_shift(p, t1));
-          } else {
-            tma_load_2d(sB, &tmB, &full_bar[stage], it.n0, kb * BK);
-            if (p.b_halves == 2) tma_load_2d(sB + kTileBytes / 2, &tmB, &full_bar[stage], it.n0 + 64, kb * BK);
-          }
+          if (!p.b_resident) load_b(sB, &full_bar[stage], kb, it.n0);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -305,10 +342,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = make_idesc_bf16(BM, static_cast<uint32_t>(p.n_mma), A_MAJOR, B_MAJOR);
-    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, panel_gen = 0;
+    int panel_n0 = -1;
+    for (int w = w_first; w < w_end; w += w_step) {
       const WorkItem it = decode_work(p, w);
       if (it.kb0 >= it.kb1) continue;
+      if (p.b_resident && it.n0 != panel_n0) {
+        mbar_wait(panel_full, panel_gen & 1, 6);
+        panel_n0 = it.n0;
+        ++panel_gen;
+      }
+      // last tile that reads this panel: the next work item of this CTA belongs to another N tile (or there is none)
+      const bool panel_last = p.b_resident && w + w_step >= w_end;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
       tc_fence_after();
       for (int kb = it.kb0; kb < it.kb1; ++kb) {
@@ -316,7 +361,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a0 = smem_u32(smem + stage * kStageBytes);
-          const uint32_t b0 = a0 + kTileBytes;
+          const uint32_t b0 = p.b_resident ? smem_u32(smem + kb * kStageBytes) + kTileBytes : a0 + kTileBytes;
 #pragma unroll
           for (int k16 = 0; k16 < BK / 16; ++k16) {
             const uint64_t ad = (A_MAJOR == kMajorK) ? make_sdesc_sw128(a0 + k16 * 32, 16, 1024)
@@ -326,7 +371,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             umma_ss(tmem_base + acc * BN, ad, bd, idesc, (kb > it.kb0 || k16 > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);
-          if (kb == it.kb1 - 1) tc_commit(&tfull_bar[acc]);
+          if (kb == it.kb1 - 1) {
+            tc_commit(&tfull_bar[acc]);
+            if (panel_last) tc_commit(panel_empty);
+          }
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -338,7 +386,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // which 64 of the tile's 128 columns
     uint32_t acc = 0, acc_phase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = w_first; w < w_end; w += w_step) {
       const WorkItem it = decode_work(p, w);
       if (it.kb0 >= it.kb1) continue;
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
@@ -455,7 +503,19 @@ extern "C" int hvc_gemm(const hvc_gemm_args* a, void* stream) {
 
   const long long num_work = (long long)ka.m_blocks * ka.n_blocks * ka.k_splits;
   const int sms = device_sm_count();
-  const int grid = (int)(num_work < sms ? num_work : sms);
+  int grid = (int)(num_work < sms ? num_work : sms);
+  // resident weight panel: whole-K panels that fit the ring's B slots, no split-K / taps, at most one group's worth of N tiles per SM
+  // count and enough M tiles per CTA to amortise the panel load; the grid is a whole number of groups of n_blocks CTAs
+  ka.b_resident = (getenv("HVC_GEMM_NO_RESIDENT") == nullptr && ka.k_blocks <= kStages - 1 && ka.k_splits == 1 && tp.side == 0 &&
+                   ka.n_blocks <= sms / 4 && num_work >= 8LL * sms) ? 1 : 0;
+  ka.tiles_per_cta = 1;
+  if (ka.b_resident) {
+    const int groups = sms / ka.n_blocks;
+    ka.tiles_per_cta = groups;              // the step between the M tiles of one CTA
+    grid = groups * ka.n_blocks;
+  }
+  ka.stage_tx_a = a->a_major == 0 ? kTileBytes : ka.a_halves * (kTileBytes / 2);
+  ka.panel_tx = (uint32_t)ka.k_blocks * (ka.stage_tx - ka.stage_tx_a);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (a->a_major == 0 && a->b_major == 0) return launch_gemm<kMajorK, kMajorK>(tmA, tmB, ka, grid, st);
   if (a->a_major == 0 && a->b_major == 1) return launch_gemm<kMajorK, kMajorMN>(tmA, tmB, ka, grid, st);
