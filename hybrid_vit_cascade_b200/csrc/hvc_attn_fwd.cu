@@ -37,9 +37,10 @@ constexpr int kEmu64 = 6, kEmu32 = 6;   // element pairs (of 16) whose exp2 runs
 #ifndef HVC_FWD_EMU_DROP
 #define HVC_FWD_EMU_DROP 0
 #endif
-// the dropout instantiations keep every exp2 on the MUFU: their mask hash (one 32-bit multiply per element) already fills the FMA
-// pipe -- measured in the 128^3 training step with dropout 0.1: 6 -> 531, 3 -> 555, 0 -> 594 TFLOP/s
-constexpr int kEmuDrop = HVC_FWD_EMU_DROP;
+// the dropout instantiations keep every exp2 on the MUFU at d = 64: their mask work already fills the FMA pipe -- round 1 (xor hash), in the
+// 128^3 training step: 6 -> 531, 3 -> 555, 0 -> 594 TFLOP/s; round 2 (multiplicative hash), kernel level: 2 -> 653, 4 -> 646, 6 -> 587, 0 -> 670.
+// At d = 32 (half the tensor work per exp) two pairs of 16 help a little: 335 -> 344 TFLOP/s (profiles/r02_attn_bwd_nodrain_bound.log).
+constexpr int kEmuDrop = HVC_FWD_EMU_DROP, kEmuDrop32 = HVC_FWD_EMU_DROP ? HVC_FWD_EMU_DROP : 2;
 
 struct AttnFwdKArgs {
   int batch, heads, nq, nk, n_kv_tiles;
@@ -471,7 +472,7 @@ extern "C" int hvc_attn_fwd(const hvc_attn_args* a, void* stream) {
   const bool drop = a->drop.seed != nullptr && a->drop.p > 0.f;
   HVC_CHECK_ARG(!drop || a->drop.p < 1.f, "hvc_attn_fwd: dropout p must be < 1");
   const int rc = a->head_dim == 64 ? (drop ? launch_attn_fwd<64, true, kEmuDrop>(a, st) : launch_attn_fwd<64, false, kEmu64>(a, st))
-                         : (drop ? launch_attn_fwd<32, true, kEmuDrop>(a, st) : launch_attn_fwd<32, false, kEmu32>(a, st));
+                         : (drop ? launch_attn_fwd<32, true, kEmuDrop32>(a, st) : launch_attn_fwd<32, false, kEmu32>(a, st));
   if (rc != HVC_OK || a->probs == nullptr) return rc;
   return attn_store_probs(a, st);
 }
