@@ -380,3 +380,27 @@ def test_attention_lazy_rescale_path(d):
     K.attn_bwd(qb, kb, vb, o, lse2, r, 1, 1, N, M, d, d ** -0.5, dq, dk, dv)
     for a, b in ((dq, qf.grad), (dk, kf.grad), (dv, vf.grad)):
         assert O.cosine(a, b) >= COS_TOL
+
+
+def test_backbone_vs_oracle_under_autocast_bf16():
+    """the bf16 path against the reference algorithm run the way the reference trainers run it on a GPU --
+    under torch.autocast (train_direct_4gpu.py:65; bf16 here) -- as well as against fp32: both within 2e-2, and the kernels are
+    closer to the fp32 result than the autocast reference is (fp32 residual stream, statistics and softmax)."""
+    import hybrid_vit_cascade_b200 as hvc
+    volume = (64, 64, 64)
+    kw = dict(volume_size=volume, in_channels=1, voxel_dim=256, depth=2, num_heads=4, context_dim=512, cond_dim=1024)
+    cfg = O.BackboneConfig(**kw)
+    sd = {k: v.cuda() for k, v in O.init_state_dict(cfg, seed=9).items()}
+    m = hvc.HybridViT3D(**kw).cuda().eval()
+    m.load_state_dict(sd, strict=True)
+    g = torch.Generator(device="cuda").manual_seed(29)
+    x = torch.randn(2, 1, *volume, device="cuda", generator=g) * 0.5
+    ctx = torch.randn(2, 512, 512, device="cuda", generator=g)
+    cond = torch.randn(2, 1024, device="cuda", generator=g)
+    with torch.no_grad():
+        y = m(x, ctx, cond)
+        y32 = O.backbone(x, ctx, cond, sd, cfg, attn_chunk=1024)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y16 = O.backbone(x, ctx, cond, sd, cfg, attn_chunk=1024).float()
+    assert O.max_rel(y, y32) <= FWD_TOL and O.max_rel(y, y16) <= FWD_TOL
+    assert O.max_rel(y, y32) <= O.max_rel(y16, y32) + 1e-3
