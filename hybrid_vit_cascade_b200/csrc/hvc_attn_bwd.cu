@@ -36,6 +36,11 @@
 //        on the serial path of every tile (profiles/r01_attn_bwd_timeline_d64_v5.log).  Upper bound measured by dropping the drain
 //        altogether: 793 -> 933 TFLOP/s at d = 64 (646 -> 786 with dropout), profiles/r02_attn_bwd_nodrain_bound.log.  The block grows to
 //        512 threads; setmaxnreg moves registers from the drain / TMA / MMA warps to the elementwise warpgroups (168 each).
+//      * round 2: the kernel is bound by the tensor pipe's in-order execution when dropout is off (dropping the dV products: +12 %, the dQ
+//        products: +21 %, replacing the exp by a multiply: 0 %; profiles/r02_attn_bwd_limiter_experiments.log), and a tcgen05.mma step costs
+//        (A + B operand bytes) / 128 B/clk.  dP^T is therefore ONE N = 128 product per tile (8 KB per step) instead of two N = 64 ones
+//        (2 x 6 KB), issued in the tail of the previous tile, and S^T(i+1) is issued before dV_0(i) so the pipe never waits for a
+//        warpgroup: 790 -> 847 TFLOP/s at d = 64, 451 -> 486 at d = 32 (dropout off; with dropout the elementwise path is the bound: +1 %).
 //      TMEM is used to the last column (S^T 128 | P^T 64 | dP^T 128 | dV d | dK d | dQ d).
 //   attn_dq_convert_kernel   dq_accum (f32, per head) * scale -> dq (bf16, packed token-major)
 #define HVC_WAIT_INLINE 1      // no device function calls in this translation unit: see mbar_wait_slow
@@ -137,10 +142,14 @@ __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[kWgCols], uint3
       const float2 a = ffma2(make_float2(__uint_as_float(sv[t]), __uint_as_float(sv[t + 1])), nss, make_float2(l4.x, l4.y));
       const float2 c = ffma2(make_float2(__uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3])), nss, make_float2(l4.z, l4.w));
       float2 e0, e1;
+#ifdef HVC_BWD_EXP_NO_MUFU      // timing experiment only (wrong results): the exp replaced by one FMUL2
+      e0 = fmul2(a, a); e1 = fmul2(c, c);
+#else
       if (((t >> 1) * kBwdEmu) % 16 < kBwdEmu) e0 = ex2_poly2(a);
       else e0 = make_float2(ex2_approx(a.x), ex2_approx(a.y));
       if ((((t >> 1) + 1) * kBwdEmu) % 16 < kBwdEmu) e1 = ex2_poly2(c);
       else e1 = make_float2(ex2_approx(c.x), ex2_approx(c.y));
+#endif
       if (!FULL) {
         e0.x = (key_ok && t + 0 < q_valid) ? e0.x : 0.f;
         e0.y = (key_ok && t + 1 < q_valid) ? e0.y : 0.f;
@@ -327,7 +336,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     auto issue_dv = [&](int x, int st, bool first) {   // dV += P^T_x dO_x   (A = P^T_x in TMEM, 8 columns per K=16 step; B = dO MN-major)
       const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
+#ifdef HVC_BWD_EXP_SKIP_DV
+      if (false) {
+#else
       if (leader) {
+#endif
 #pragma unroll
         for (int k16 = 0; k16 < kWgCols / 16; ++k16)
           umma_ts(tmem_base + kColDV, tmem_base + kColPt + x * (kWgCols / 2) + k16 * 8,
@@ -349,7 +362,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
     auto issue_dq = [&](int buf) {   // dQ = dS K   (A = both dS^T sub-tiles read MN-major: M = queries; B = K^T K-major: rows = d, two 64-key sub-tiles)
+#ifdef HVC_BWD_EXP_SKIP_DQ
+      if (false) {
+#else
       if (leader) {
+#endif
 #pragma unroll
         for (int k16 = 0; k16 < kBT / 16; ++k16)
           umma_ss(tmem_base + kColDQ, make_sdesc_sw128(sDS0 + buf * L::kDSBuf + k16 * 2048, 16384, 1024),
@@ -357,6 +374,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       commit(BB_DQF);
     };
+#ifndef HVC_BWD_DPT_SPLIT      // (the round-1 schedule with one dP^T product per column half is kept behind HVC_BWD_DPT_SPLIT for A/B runs)
+    // dP^T(i) for both column halves in ONE N = 128 product (8 KB of operands per K = 16 step instead of 2 x 6 KB): issued in the tail of
+    // tile i-1, after dK_0(i-1) and dK_1(i-1) have read the dS^T that shares its columns
+    auto issue_dpt_full = [&](int st) {
+      const uint32_t sDO = sQ0 + st * L::kQStage + L::kTile;
+      if (leader) {
+#pragma unroll
+        for (int k16 = 0; k16 < HD / 16; ++k16)
+          umma_ss(tmem_base + kColDPt, make_sdesc_sw128(sVT + k16 * 2048, kSubKT, 1024), SW::desc(sDO + k16 * 32), id_s2, k16 > 0 ? 1u : 0u);
+      }
+      commit(BB_DPT + 0);
+      commit(BB_DPT + 1);
+    };
+    auto finish_tile_m = [&](int t) {
+      mbar_wait(&bar[BB_DS + 1], t & 1, 25);
+      tc_fence_after();
+      issue_dk(1, t % kQStages, t & 1, false);
+      if (t + 1 < nQ) issue_dpt_full((t + 1) % kQStages);
+      if (t > 0) { mbar_wait(&bar[BB_DQFREE], (t - 1) & 1, 26); tc_fence_after(); }
+      issue_dq(t & 1);
+      commit(BB_QE + t % kQStages);
+    };
+#endif
     // tail of tile t (needs dS_1(t)): dP^T_1(t+1), dK_1(t), dQ(t); releases the Q/dO stage of tile t
     auto finish_tile = [&](int t) {
       mbar_wait(&bar[BB_DS + 1], t & 1, 25);
@@ -378,6 +418,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(&bar[BB_QF + 0], 0, 21);
     tc_fence_after();
     issue_st(0);
+#ifndef HVC_BWD_DPT_SPLIT
+    issue_dpt_full(0);
+    for (int i = 0; i < nQ; ++i) {
+      const int st = i % kQStages;
+      const int st1 = (i + 1) % kQStages;
+      if (i > 0) finish_tile_m(i - 1);
+      if (i + 1 < nQ) {                             // S^T(i+1) once both warpgroups have pulled S^T(i) out of TMEM
+        mbar_wait(&bar[BB_STFREE + 0], i & 1, 22);
+        mbar_wait(&bar[BB_STFREE + 1], i & 1, 27);
+        mbar_wait(&bar[BB_QF + st1], ((i + 1) / kQStages) & 1, 23);
+        tc_fence_after();
+        issue_st(st1);
+      }
+      mbar_wait(&bar[BB_PT + 0], i & 1, 24);
+      tc_fence_after();
+      issue_dv(0, st, i == 0);
+      mbar_wait(&bar[BB_DS + 0], i & 1, 28);
+      tc_fence_after();
+      issue_dk(0, st, i & 1, i == 0);
+      mbar_wait(&bar[BB_PT + 1], i & 1, 29);
+      tc_fence_after();
+      issue_dv(1, st, false);
+    }
+    finish_tile_m(nQ - 1);
+    commit(BB_DONE);
+#else
     issue_dpt(0, 0);
     issue_dpt(1, 0);
     for (int i = 0; i < nQ; ++i) {
@@ -416,6 +482,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     finish_tile(nQ - 1);
     commit(BB_DONE);        // every product issued: dV and dK are complete when this fires
+#endif
   } else if (warp >= kDrainWarp0 && warp < kTmaWarp) {
     // ===================== dQ drain warpgroup: thread == query row of the tile =====================
     reg_dealloc<kRegsDrain>();
