@@ -124,8 +124,12 @@ __device__ __forceinline__ void softmax_exp_chunk(const uint32_t (&v)[32], uint3
   for (int c = 0; c < 32; c += 2) {
     const float2 a = ffma2(make_float2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), scale2v, neg_m);
     float2 e;
+#ifdef HVC_FWD_EXP_NO_EXP          // timing experiment only (wrong results): the exp replaced by one FMUL2
+    e = fmul2(a, a);
+#else
     if (((c >> 1) * EMU) % 16 < EMU) e = ex2_poly2(a);
     else e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+#endif
     if (MASKED) {
       e.x = (c0 + c < tail) ? e.x : 0.f;
       e.y = (c0 + c + 1 < tail) ? e.y : 0.f;
@@ -238,7 +242,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t idesc_o = make_idesc_bf16(kQTile, HD, kMajorK, kMajorMN);
     const uint32_t sQ = smem_u32(smem + L::kQ), sK = smem_u32(smem + L::kK), sV = smem_u32(smem + L::kV);
     auto issue_s = [&](int x, int st) {   // S_x = Q_x K^T
+#ifdef HVC_FWD_EXP_SKIP_S
+      if (false) {
+#else
       if (leader) {
+#endif
 #pragma unroll
         for (int k16 = 0; k16 < HD / 16; ++k16)
           umma_ss(tmem_base + kColS + x * kKTile, SW::desc(sQ + x * L::kTile + k16 * 32),
@@ -246,7 +254,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     };
     auto issue_pv = [&](int x, int st, bool acc) {   // O_x (+)= P_x V   (P: TMEM, 8 columns per K=16 step)
+#ifdef HVC_FWD_EXP_SKIP_PV
+      if (false) {
+#else
       if (leader) {
+#endif
 #pragma unroll
         for (int k16 = 0; k16 < kKTile / 16; ++k16)
           umma_ts(tmem_base + kColO + x * HD, tmem_base + kColS + x * kKTile + k16 * 8,
