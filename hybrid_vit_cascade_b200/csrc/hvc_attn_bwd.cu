@@ -170,13 +170,19 @@ __device__ __forceinline__ void bwd_phase_a(const uint32_t (&sv)[kWgCols], uint3
     }
   }
 }
+// x clamped to [0, 1] on the FMA pipe (add.sat): the kept probability P keep from the signed value s = +-P
+__device__ __forceinline__ float sat01(float x) {
+  float y;
+  asm("add.sat.ftz.f32 %0, %1, 0f00000000;" : "=f"(y) : "f"(x));
+  return y;
+}
 // Phase B: dS^T = P^T * (dP^T - delta) -> four 16-byte chunks (chunk0 ..) of this thread's row in a swizzled sub-tile
 // DROP: dS = P * (keep ? dP / (1-p) : 0  -  delta), keep = sign of the stored P value.
 template <bool FULL, bool DROP, bool TSDK>
 __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[kWgCols], uint32_t delta_saddr, const float2 (&pv)[kWgCols / 2],
                                             bool key_ok, int q_valid, uint32_t sub_saddr, int r, int chunk0, float inv_keep, uint32_t t_ds) {
-  const float2 neg1 = make_float2(-1.f, -1.f);
-  const float2 rp2 = make_float2(0.5f * inv_keep, 0.5f * inv_keep);
+  const float2 neg1 = make_float2(-1.f, -1.f), neg2 = make_float2(-2.f, -2.f);
+  const float2 rp2 = make_float2(inv_keep, inv_keep);
 #pragma unroll
   for (int g = 0; g < kWgCols; g += 4 * kDeltaPre) {
     uint32_t dsp[2 * kDeltaPre];            // the group's dS^T as bf16 pairs: also written to TMEM (A operand of dK)
@@ -193,16 +199,18 @@ __device__ __forceinline__ void bwd_phase_b(const uint32_t (&dv)[kWgCols], uint3
         const float4 d4 = dq4[2 * kk + u];
         float2 x0, x1;
         if (DROP) {
-          // s = +-P (sign = kept): s + |s| = 2 P keep, so dS = (s + |s|) * (dP / (2 (1-p))) - |s| * delta -- adds and multiplies
-          // only (FMA pipe; |.| is an operand modifier): the compare + select form put two more instructions per element on
-          // the ALU pipe, which the mask hash of phase A already saturates
-          const float2 p0 = pv[t >> 1], p1 = pv[(t >> 1) + 1];
-          const float2 h0 = fmul2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), rp2);       // rp2 = 1 / (2 (1-p))
+          // s = +-P (sign = kept) and P <= 1, so P keep = sat(s) and   dS = P keep dP / (1-p) - P delta = sat(s) (dP / (1-p) - 2 delta) + s delta:
+          // one saturating add per element plus packed multiplies and FMAs -- 3 issue slots per element.  (Round 1 formed |s| with operand
+          // modifiers, which the packed instructions do not have: abs + add + multiply per element, 4 slots;
+          // profiles/r02_attn_bwd_limiter_experiments.log.)
+          const float2 s0 = pv[t >> 1], s1 = pv[(t >> 1) + 1];
+          const float2 d0 = make_float2(d4.x, d4.y), d1 = make_float2(d4.z, d4.w);
+          const float2 h0 = fmul2(make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])), rp2);       // rp2 = 1 / (1-p)
           const float2 h1 = fmul2(make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])), rp2);
-          const float2 t0 = make_float2(p0.x + fabsf(p0.x), p0.y + fabsf(p0.y)), t1 = make_float2(p1.x + fabsf(p1.x), p1.y + fabsf(p1.y));
-          const float2 w0 = make_float2(-fabsf(p0.x) * d4.x, -fabsf(p0.y) * d4.y), w1 = make_float2(-fabsf(p1.x) * d4.z, -fabsf(p1.y) * d4.w);
-          x0 = ffma2(t0, h0, w0);
-          x1 = ffma2(t1, h1, w1);
+          const float2 g0 = ffma2(d0, neg2, h0), g1 = ffma2(d1, neg2, h1);
+          const float2 k0 = make_float2(sat01(s0.x), sat01(s0.y)), k1 = make_float2(sat01(s1.x), sat01(s1.y));
+          x0 = ffma2(k0, g0, fmul2(s0, d0));
+          x1 = ffma2(k1, g1, fmul2(s1, d1));
         } else {
           x0 = ffma2(make_float2(d4.x, d4.y), neg1, make_float2(__uint_as_float(dv[t]), __uint_as_float(dv[t + 1])));
           x1 = ffma2(make_float2(d4.z, d4.w), neg1, make_float2(__uint_as_float(dv[t + 2]), __uint_as_float(dv[t + 3])));

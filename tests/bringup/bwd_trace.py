@@ -11,14 +11,16 @@ sys.path.insert(0, ROOT)
 from hybrid_vit_cascade_b200 import _lib, kernels as K  # noqa: E402
 
 B, H, N, d = (int(v) for v in (sys.argv[1:5] if len(sys.argv) > 4 else (1, 4, 8192, 64)))
+DROP = len(sys.argv) > 5 and sys.argv[5] == "drop"      # python bwd_trace.py 1 4 8192 64 drop
 Cc = H * d
 g = torch.Generator(device="cuda").manual_seed(3)
 q, k, v, d_o = (torch.randn(B * N, Cc, device="cuda", generator=g).bfloat16() for _ in range(4))
 dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-o, lse = K.attn_fwd(q, k, v, B, H, N, N, d, d ** -0.5)
+drop = K.Drop(torch.tensor([123, -456], dtype=torch.int32, device="cuda"), 5, 0.1) if DROP else None
+o, lse = K.attn_fwd(q, k, v, B, H, N, N, d, d ** -0.5, drop=drop)
 assert _lib.lib().hvc_debug_bwd_trace_enable(1) == 0
 for _ in range(2):
-    K.attn_bwd(q, k, v, o, lse, d_o, B, H, N, N, d, d ** -0.5, dq, dk, dv)
+    K.attn_bwd(q, k, v, o, lse, d_o, B, H, N, N, d, d ** -0.5, dq, dk, dv, drop=drop)
 torch.cuda.synchronize()
 IT, PTS, ROLES = 8, 12, 3
 buf = (C.c_ulonglong * (ROLES * IT * PTS))()
