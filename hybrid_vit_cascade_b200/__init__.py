@@ -12,11 +12,11 @@ from .vit_components import (AdaLNModulation, MultiHeadCrossAttention, MultiHead
 from .hybrid_vit_backbone import HybridViT3D, HybridViTBlock3D  # noqa: F401
 from .xray_encoder import (DirectCTRegression, MultiScaleXrayEncoder, Stage1Base64, Stage2Refiner128, Stage3Refiner256, ProgressiveCascadeModel,  # noqa: F401
                            XrayConditioningModule)
-from .losses import (DirectRegressionLoss, DRRReprojectionLoss, FrequencyLoss, MultiScaleLoss, SSIMLoss, Stage1Loss, Stage2Loss, Stage3Loss,  # noqa: F401
+from .losses import (DirectRegressionLoss, DRRReprojectionLoss, FrequencyLoss, MultiScaleLoss, SSIMLoss, Stage1Loss, Stage2Loss, Stage3Loss, TriPlanarVGGLoss,  # noqa: F401
                      TotalVariationLoss, compute_psnr, compute_ssim_loss, compute_ssim_metric)
 from . import checkpoint  # noqa: F401
 from .optim import FlatAdamW  # noqa: F401
 
 __all__ = ["AdaLNModulation", "MultiHeadCrossAttention", "MultiHeadSelfAttention", "SinusoidalTimeEmbedding",
-           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "MultiScaleXrayEncoder", "DirectCTRegression", "Stage1Base64", "Stage2Refiner128", "Stage3Refiner256", "ProgressiveCascadeModel", "DirectRegressionLoss", "compute_ssim_loss", "SSIMLoss", "TotalVariationLoss", "FrequencyLoss", "DRRReprojectionLoss", "Stage1Loss", "Stage2Loss", "Stage3Loss", "MultiScaleLoss", "compute_psnr", "compute_ssim_metric", "checkpoint", "FlatAdamW", "set_dropout_policy", "set_precision",
+           "HybridViTBlock3D", "HybridViT3D", "XrayConditioningModule", "MultiScaleXrayEncoder", "DirectCTRegression", "Stage1Base64", "Stage2Refiner128", "Stage3Refiner256", "ProgressiveCascadeModel", "DirectRegressionLoss", "compute_ssim_loss", "SSIMLoss", "TotalVariationLoss", "FrequencyLoss", "DRRReprojectionLoss", "TriPlanarVGGLoss", "Stage1Loss", "Stage2Loss", "Stage3Loss", "MultiScaleLoss", "compute_psnr", "compute_ssim_metric", "checkpoint", "FlatAdamW", "set_dropout_policy", "set_precision",
            "precision"]

@@ -187,6 +187,72 @@ class DRRReprojectionLoss(nn.Module):
         return _DRR.apply(pred_volume, input_xrays[:, 0], input_xrays[:, 1], int(self.img_size))
 
 
+class TriPlanarVGGLoss(nn.Module):
+    """reference: loss_multiscale.py:54-137 -- L1 between VGG16 relu1_2 / relu2_2 / relu3_3 features of the three central slices
+    (axial, sagittal, coronal) of prediction and target, each slice mapped to [0, 1] and replicated to RGB; mean over the planes.
+
+    The reference constructor downloads torchvision's ImageNet VGG16; here the weights are an argument, so the loss also works on a
+    machine without network access: `weights` = a torchvision VGG module, its state_dict ('features.N.weight' / '.bias', N in
+    0 2 5 7 10 12 14), or a path to one saved with torch.save.  With weights=None the torchvision ImageNet weights are looked up exactly
+    as the reference does (local hub cache or download) and the failure, if any, is raised.
+
+    Same values, less work: the three taps come from ONE pass (the reference runs features[:4], [:9] and [:16] from the input each,
+    recomputing the shared prefix), the RGB replication is folded into the first convolution (its weights summed over the input
+    channels), all same-shaped slices go through the network as one batch, and the target features are computed without autograd.
+    The convolutions are cuDNN's (library calls outside the hot path)."""
+
+    _CONVS = ((0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256), (12, 256, 256), (14, 256, 256))
+    _TAPS = {2: 0, 7: 1, 14: 2}          # feature index of the convolution whose ReLU output is relu1_2 / relu2_2 / relu3_3
+    _POOL_BEFORE = (5, 10)               # max-pool 2x2 (features[4], features[9]) sits in front of these convolutions
+
+    def __init__(self, weights=None, layer_weights=(1.0, 1.0, 1.0)):
+        super().__init__()
+        if weights is None:
+            from torchvision.models import vgg16, VGG16_Weights
+            weights = vgg16(weights=VGG16_Weights.IMAGENET1K_V1)
+        if isinstance(weights, (str, bytes)) or hasattr(weights, "__fspath__"):
+            weights = torch.load(weights, map_location="cpu", weights_only=True)
+        if isinstance(weights, nn.Module):
+            weights = weights.state_dict()
+        for idx, cin, cout in self._CONVS:
+            w, b = weights[f"features.{idx}.weight"].detach().float(), weights[f"features.{idx}.bias"].detach().float()
+            assert w.shape == (cout, cin, 3, 3), f"features.{idx}.weight: {tuple(w.shape)}"
+            if idx == 0:
+                w = w.sum(1, keepdim=True)            # the same grey slice in all three input channels
+            self.register_buffer(f"w{idx}", w.contiguous(), persistent=False)      # frozen (:78-80); not part of any checkpoint
+            self.register_buffer(f"b{idx}", b.contiguous(), persistent=False)
+        self.layer_weights = list(layer_weights)
+
+    def extract_features(self, x):
+        """x: (n, 1, h, w) in [0, 1] -> [relu1_2, relu2_2, relu3_3]"""
+        feats = []
+        for idx, _, _ in self._CONVS:
+            if idx in self._POOL_BEFORE:
+                x = torch.nn.functional.max_pool2d(x, 2, 2)
+            x = torch.relu(torch.nn.functional.conv2d(x, getattr(self, f"w{idx}").to(x.dtype), getattr(self, f"b{idx}").to(x.dtype), padding=1))
+            if idx in self._TAPS:
+                feats.append(x)
+        return feats
+
+    def forward(self, pred_volume, target_volume):
+        D, H, W = pred_volume.shape[2:]
+        planes = lambda v: (v[:, :, D // 2, :, :], v[:, :, :, H // 2, :], v[:, :, :, :, W // 2])
+        groups = {}                                    # slice shape -> (pred slices, target slices)
+        for ps, ts in zip(planes(pred_volume), planes(target_volume)):
+            g = groups.setdefault(tuple(ps.shape[2:]), ([], []))
+            g[0].append(ps)
+            g[1].append(ts)
+        total = 0.0
+        for ps, ts in groups.values():
+            n = len(ps)
+            fp = self.extract_features((torch.cat(ps, 0) + 1) / 2)
+            with torch.no_grad():
+                ft = self.extract_features((torch.cat(ts, 0).detach() + 1) / 2)
+            for a, b, w in zip(fp, ft, self.layer_weights):
+                total = total + (w * n) * torch.nn.functional.l1_loss(a, b)      # equal-sized slices: sum of the planes' means = n * mean of the batch
+        return total / 3
+
+
 class Stage1Loss(nn.Module):
     """reference: loss_multiscale.py:296-324 (L1 + SSIM; one fused pass)"""
 
@@ -203,9 +269,9 @@ class Stage1Loss(nn.Module):
 
 
 class _StageLossBase(nn.Module):
-    """Stage 2 / 3: L1 + SSIM (fused) + TV(pred, target) + frequency [+ DRR].  The reference's TriPlanarVGGLoss (:54-137) needs the
-    ImageNet VGG16 weights from a download (the reference cannot construct Stage2Loss / MultiScaleLoss offline either): a module can
-    be passed as `vgg_loss`; without one the term is reported as 0 and leaves the total unchanged."""
+    """Stage 2 / 3: L1 + SSIM (fused) + VGG + TV(pred, target) + frequency [+ DRR].  The reference builds TriPlanarVGGLoss (:54-137) from
+    downloaded ImageNet weights inside its constructor (so Stage2Loss / MultiScaleLoss cannot be constructed offline); here the term is
+    passed in as `vgg_loss=TriPlanarVGGLoss(weights)`.  Without one it is reported as 0 and leaves the total unchanged."""
 
     def __init__(self, l1_weight, ssim_weight, vgg_weight, tv_weight, freq_weight, vgg_loss=None):
         super().__init__()

@@ -4,8 +4,9 @@
     TotalVariationLoss       :140-188
     FrequencyLoss            :191-236
     DRRReprojectionLoss      :239-293
-    Stage1Loss / Stage2Loss / Stage3Loss   :296-432   (TriPlanarVGGLoss, :54-137, needs downloaded ImageNet weights and cannot be
-                             constructed offline -- neither here nor in the reference; the stage totals below take its value as an argument)
+    TriPlanarVGGLoss         :54-137   (the VGG16 `features` weights are an ARGUMENT here: the reference downloads the ImageNet ones in
+                             its constructor, which cannot happen offline; tests use seeded stand-in weights, `vgg16_features_state`)
+    Stage1Loss / Stage2Loss / Stage3Loss   :296-432   (the stage totals take the VGG term's value as an argument)
 
 Plain torch ops in the reference's order; autograd gives the gradients.  Pinned against outputs of the real reference classes
 (tests/golden/make_golden_r02.py -> tests/golden/r02_losses.pt, replayed by tests/test_oracle_golden_r02.py).
@@ -65,6 +66,43 @@ def generate_drr(vol, view_angle, img_size):
 def drr_reprojection_loss(pred, input_xrays, img_size=512):
     ap, lat = generate_drr(pred, 0, img_size), generate_drr(pred, 90, img_size)             # :281-282
     return (F.l1_loss(ap, input_xrays[:, 0]) + F.l1_loss(lat, input_xrays[:, 1])) / 2        # :285-293
+
+
+# torchvision vgg16().features[:16]: (index, in, out) of its convolutions (3x3, padding 1, each followed by ReLU); max-pool 2x2 at 4 and 9
+VGG16_CONVS = ((0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256), (12, 256, 256), (14, 256, 256))
+VGG16_POOLS = (4, 9)
+
+
+def vgg16_features_state(seed=0):
+    """Seeded stand-in for the ImageNet weights, keyed like torchvision's vgg16().state_dict() ('features.N.weight' / '.bias')."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for idx, cin, cout in VGG16_CONVS:
+        sd[f"features.{idx}.weight"] = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+        sd[f"features.{idx}.bias"] = torch.randn(cout, generator=g) * 0.05
+    return sd
+
+
+def _vgg_prefix(x, sd, stop):
+    """vgg.features[:stop](x), from the input every time as the reference does (:84-92)."""
+    convs = {i for i, _, _ in VGG16_CONVS}
+    for i in range(stop):
+        if i in convs:
+            x = F.relu(F.conv2d(x, sd[f"features.{i}.weight"].to(x), sd[f"features.{i}.bias"].to(x), padding=1))
+        elif i in VGG16_POOLS:
+            x = F.max_pool2d(x, 2, 2)
+    return x
+
+
+def triplanar_vgg_loss(pred, target, vgg_state):
+    D, H, W = pred.shape[2:]
+    planes = lambda v: (v[:, :, D // 2, :, :], v[:, :, :, H // 2, :], v[:, :, :, :, W // 2])          # :101-114 axial / sagittal / coronal
+    total = 0.0
+    for ps, ts in zip(planes(pred), planes(target)):
+        ps, ts = ((ps + 1) / 2).repeat(1, 3, 1, 1), ((ts + 1) / 2).repeat(1, 3, 1, 1)                    # :121-126
+        for stop in (4, 9, 16):                                                                        # relu1_2, relu2_2, relu3_3 (:72-76), weights 1
+            total = total + F.l1_loss(_vgg_prefix(ps, vgg_state, stop), _vgg_prefix(ts, vgg_state, stop))   # :133-135
+    return total / 3                                                                                   # :137
 
 
 def stage1_loss(pred, target, l1_weight=1.0, ssim_weight=0.5):

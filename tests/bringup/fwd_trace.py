@@ -16,8 +16,10 @@ Cc = H * d
 g = torch.Generator(device="cuda").manual_seed(3)
 q, k, v = (torch.randn(B * N, Cc, device="cuda", generator=g).bfloat16() for _ in range(3))
 assert _lib.lib().hvc_debug_fwd_trace_enable(1) == 0
+DROP = len(sys.argv) > 5 and sys.argv[5] == "drop"      # python fwd_trace.py 1 4 8192 64 drop
+drop = K.Drop(torch.tensor([123, -456], dtype=torch.int32, device="cuda"), 5, 0.1) if DROP else None
 for _ in range(2):
-    K.attn_fwd(q, k, v, B, H, N, N, d, d ** -0.5)
+    K.attn_fwd(q, k, v, B, H, N, N, d, d ** -0.5, drop=drop)
 torch.cuda.synchronize()
 IT, PTS = 8, 8
 buf = (C.c_ulonglong * (3 * IT * PTS))()

@@ -6,6 +6,7 @@
     direct_regression/progressive_cascade/loss_multiscale.py on seeded non-cubic volumes: values and d loss / d pred.
   * r02_checkpoint_direct.pt: a checkpoint written by the reference trainer's own save lines (train_direct_4gpu.py:277-297) for a small
     DirectCTRegression after one AdamW step on the CPU, plus the eval-mode output of the saved model on a recorded input.
+  * r02_vgg.pt: TriPlanarVGGLoss, Stage2Loss, Stage3Loss (with X-rays) and MultiScaleLoss(stage=2) with seeded stand-in VGG16 weights.
   * r02_views.pt: XrayConditioningModule constructed with num_views=1 (its default) fed a TWO-view input (diagnostic_losses.py:118-125
     decides on the input's view count).
 """
@@ -115,9 +116,42 @@ def views():
     torch.save(dict(sd=sd0, xrays=xr, t=t, ctx=c.detach(), cond=d.detach(), feats=f.detach()), os.path.join(HERE, "r02_views.pt"))
 
 
+def vgg():
+    """TriPlanarVGGLoss / Stage2Loss / Stage3Loss of the reference, with torchvision's vgg16 constructor pointed at seeded stand-in
+    weights (oracle.loss_oracle.vgg16_features_state(5)) instead of the ImageNet download -- the only change; the classes are the
+    reference's own.  Inputs: pred / target / xrays of r02_losses.pt."""
+    import torchvision.models as tvm
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.loss_oracle import vgg16_features_state
+    import loss_multiscale as LM
+    real_vgg16 = tvm.vgg16
+
+    def seeded_vgg16(*a, **k):
+        m = real_vgg16(weights=None)
+        m.load_state_dict(vgg16_features_state(5), strict=False)
+        return m
+
+    tvm.vgg16 = seeded_vgg16
+    try:
+        base = torch.load(os.path.join(HERE, "r02_losses.pt"))
+        pred, target, xrays = base["pred"], base["target"], base["xrays"]
+        out = {"vgg_seed": 5}
+        out["vgg"] = val_and_grad(lambda p: LM.TriPlanarVGGLoss()(p, target), pred)
+        out["stage2"] = val_and_grad(lambda p: LM.Stage2Loss()(p, target), pred)
+        s3 = LM.Stage3Loss()
+        s3.drr_loss = LM.DRRReprojectionLoss(img_size=48)
+        out["stage3"] = val_and_grad(lambda p: s3(p, target, xrays), pred)
+        ms = LM.MultiScaleLoss()
+        out["multiscale_stage2_parts"] = {k: float(v) for k, v in ms(pred, target, stage=2).items()}
+        torch.save(out, os.path.join(HERE, "r02_vgg.pt"))
+    finally:
+        tvm.vgg16 = real_vgg16
+
+
 if __name__ == "__main__":
     losses()
     checkpoint()
     views()
-    for f in ("r02_losses.pt", "r02_checkpoint_layout.json", "r02_views.pt"):
+    vgg()
+    for f in ("r02_losses.pt", "r02_checkpoint_layout.json", "r02_views.pt", "r02_vgg.pt"):
         print(f, os.path.getsize(os.path.join(HERE, f)))

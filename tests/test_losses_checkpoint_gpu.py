@@ -79,6 +79,28 @@ def test_stage2_stage3_multiscale_losses_vs_oracle():
         assert O.max_rel(drr.generate_drr(p0.cuda(), angle), L.generate_drr(p0, angle, c["img_size"])) < 1e-5
 
 
+def test_stage2_stage3_with_vgg_term_match_reference_fixture():
+    """Stage2Loss / Stage3Loss / MultiScaleLoss WITH the tri-planar VGG term (seeded stand-in weights) against the reference classes'
+    own outputs (tests/golden/r02_vgg.pt): every reported part, the totals, and d total / d pred."""
+    import hybrid_vit_cascade_b200 as hvc
+    c, v = _gold("r02_losses.pt"), _gold("r02_vgg.pt")
+    t, x = c["target"].cuda(), c["xrays"].cuda()
+    vgg = hvc.TriPlanarVGGLoss(weights=L.vgg16_features_state(v["vgg_seed"])).cuda()
+    ms = hvc.MultiScaleLoss(vgg_loss=vgg)
+    ms.stage3_loss.drr_loss.img_size = c["img_size"]
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # the fixture is fp32 (CPU); cuDNN's default TF32 convolutions are ~1e-3
+        parts = ms(c["pred"].cuda(), t, stage=2)
+        for k, want in v["multiscale_stage2_parts"].items():
+            assert abs(float(parts[k]) - want) <= 3e-5 * max(1.0, abs(want)), (k, float(parts[k]), want)
+        for name, fn in (("vgg", lambda p: vgg(p, t)), ("stage2", lambda p: ms(p, t, stage=2)), ("stage3", lambda p: ms(p, t, stage=3, input_xrays=x))):
+            val, g = _val_grad(fn, c["pred"])
+            v_ref, g_ref = v[name]
+            assert abs(val - v_ref) <= 3e-5 * max(1.0, abs(v_ref)), (name, val, v_ref)
+            assert O.cosine(g, g_ref) >= 0.9999 and O.rel_fro(g, g_ref) <= 1e-2, name
+    val_tf32 = float(vgg(c["pred"].cuda(), t))                           # torch's default (what the reference trainer runs with)
+    assert abs(val_tf32 - v["vgg"][0]) <= 5e-3 * v["vgg"][0]
+
+
 def test_stage_losses_at_cascade_resolution_properties():
     """128^3 (stage 2's resolution), batch 2: size-independent properties -- TV and frequency losses vanish for pred == target and their
     gradients are zero there; the DRR loss is linear along the projected axis (a constant shift of the volume shifts both projections)."""

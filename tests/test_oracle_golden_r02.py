@@ -53,6 +53,29 @@ def test_loss_oracle_metrics_and_stage_totals():
     assert abs(float(s3["total_loss"]) - want3) < 1e-5 and "drr_loss" in s3
 
 
+def test_triplanar_vgg_oracle_and_module_match_reference():
+    """TriPlanarVGGLoss (loss_multiscale.py:54-137) with seeded stand-in VGG16 weights: the oracle restatement AND the shipped module (plain
+    torch convolutions: it runs on the CPU too) against the reference class; Stage2Loss / Stage3Loss totals of the reference = the oracle's
+    weighted sums with that VGG term."""
+    c, v = _gold("r02_losses.pt"), _gold("r02_vgg.pt")
+    p, t, x = c["pred"], c["target"], c["xrays"]
+    sd = L.vgg16_features_state(v["vgg_seed"])
+    val, g = _val_grad(lambda q: L.triplanar_vgg_loss(q, t, sd), p)
+    assert abs(val - v["vgg"][0]) <= 1e-6 and float((g - v["vgg"][1]).abs().max()) <= 1e-5 * float(v["vgg"][1].abs().max())
+    from hybrid_vit_cascade_b200.losses import TriPlanarVGGLoss
+    mod = TriPlanarVGGLoss(weights=sd)
+    assert not list(mod.parameters()) and not mod.state_dict()           # frozen, and absent from checkpoints
+    val, g = _val_grad(lambda q: mod(q, t), p)
+    assert abs(val - v["vgg"][0]) <= 2e-6 and float((g - v["vgg"][1]).abs().max()) <= 2e-5 * float(v["vgg"][1].abs().max())
+    cube = torch.rand(1, 1, 16, 16, 16, generator=torch.Generator().manual_seed(3)) * 2 - 1          # the three slices as ONE batch
+    tc = torch.rand(1, 1, 16, 16, 16, generator=torch.Generator().manual_seed(4)) * 2 - 1
+    assert abs(float(mod(cube, tc)) - float(L.triplanar_vgg_loss(cube, tc, sd))) <= 2e-6
+    s2, g2 = _val_grad(lambda q: L.stage2_loss(q, t, vgg=L.triplanar_vgg_loss(q, t, sd)), p)
+    assert abs(s2 - v["stage2"][0]) <= 2e-6 * v["stage2"][0] and float((g2 - v["stage2"][1]).abs().max()) <= 1e-5 * float(v["stage2"][1].abs().max())
+    s3, g3 = _val_grad(lambda q: L.stage3_loss(q, t, x, vgg=L.triplanar_vgg_loss(q, t, sd), img_size=c["img_size"]), p)
+    assert abs(s3 - v["stage3"][0]) <= 2e-6 * v["stage3"][0] and float((g3 - v["stage3"][1]).abs().max()) <= 1e-5 * float(v["stage3"][1].abs().max())
+
+
 def test_encoder_oracle_two_views_into_default_constructor():
     """XrayConditioningModule() defaults to num_views=1 but decides on the INPUT's view count (diagnostic_losses.py:118-125)."""
     c = _gold("r02_views.pt")
