@@ -246,6 +246,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // dK += dS^T Q with dS^T as a TMEM operand (bf16 pairs written over the dP^T columns by phase B) instead of the K-major smem tile:
   // 53 vs 76 clk per MMA step at d = 64 (+1.6 % on the kernel); at d = 32 the smem form is the faster one (65 clk, no extra TMEM store)
   constexpr bool kTsDk = HD == 64;
+  // The warpgroups take turns on the exp unit (staggers them: one in phase A while the other is in phase B).  Without the turns, same box:
+  // d = 64 dropout off 857 -> 817 TFLOP/s, with dropout 692 -> 691; d = 32 off 485 -> 473, with dropout 393 -> 407 -- so every instantiation
+  // keeps them except <32, dropout> (profiles/r02_attn_bwd_limiter_experiments.log).
+  constexpr bool kTurns = !(HD == 32 && DROP);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
@@ -595,7 +599,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       thr = p.drop.thr;
       inv_keep = p.drop.inv_keep;
     }
-    if (wg == 1) named_bar_arrive(NB_TURN + 0, 256);          // warpgroup 0 takes the first turn on the exp unit
+    if (kTurns && wg == 1) named_bar_arrive(NB_TURN + 0, 256);          // warpgroup 0 takes the first turn on the exp unit
     for (int i = 0; i < nQ; ++i) {
       const int st = i % kQStages;
       const uint32_t lse_saddr = smem_u32(smem + L::kQ + st * L::kQStage + 2 * L::kTile) + wg * kWgCols * 4;
@@ -620,12 +624,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_before();
         mbar_arrive_warp(&bar[BB_STFREE + wg]);
         if (wg_lead) HVC_TR(wg, i, 1);
-        named_bar_sync(NB_TURN + wg, 256);                    // my turn on the exp unit
+        if (kTurns) named_bar_sync(NB_TURN + wg, 256);                    // my turn on the exp unit
         if (wg_lead) HVC_TR(wg, i, 2);
         uint32_t ppk[kWgCols / 2];
         if (full) bwd_phase_a<true, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
         else      bwd_phase_a<false, DROP>(sv, lse_saddr, nss, key_ok, q_valid, pv, ppk, rk_saddr, colkey, thr);
-        if (!(wg == 1 && i == nQ - 1)) named_bar_arrive(NB_TURN + (wg ^ 1), 256);
+        if (kTurns && !(wg == 1 && i == nQ - 1)) named_bar_arrive(NB_TURN + (wg ^ 1), 256);
         if (wg_lead) HVC_TR(wg, i, 3);
         // dP^T_x(i) was issued after dV_x(i-1): once it has completed, dV_x(i-1) has finished reading P^T_x(i-1) and the
         // P^T columns may be overwritten (the wait is long satisfied by now; it is also phase B's input)
